@@ -1,0 +1,189 @@
+/* vdesens.h — C-ABI of the B200-native face-anonymisation hot path (libvdesens.so).
+ *
+ * The reference (xdu-Liu-learn/Video-desensitization) is pure Python and has no FFI of its own
+ * (zero C/CUDA sources).  This header is therefore the thin native layer that sits
+ * directly beneath the reference's Python call surface; each entry point names the reference
+ * interface it replaces (paths relative to the reference tree):
+ *
+ *   vd_ingest_u8hwc          <- Retinaface.preprocess          detect_face/face.py:65-88
+ *                               letterbox_image/preprocess_input detect_face/utils/utils.py:8-29
+ *   vd_conv_* / vd_maxpool   <- RetinaFace.forward             detect_face/retinaface.py:114-148
+ *                               conv_bn/SSH/FPN                 detect_face/nets/layers.py:10-114
+ *   vd_decode_threshold      <- decode/decode_landm/conf>=thr  detect_face/utils/utils_bbox.py:49-79,116
+ *                               Anchors.get_anchors            detect_face/utils/anchors.py:22-41
+ *   vd_nms_batched           <- non_max_suppression + retinaface_correct_boxes
+ *                                                              detect_face/utils/utils_bbox.py:103-130,12-43
+ *   vd_composite_rois        <- mosaic_rectangle_region_single + the per-frame box loop
+ *                                                              combine_detect.py:138-161,241-249
+ *                               (Gaussian mode: the cv2.GaussianBlur ROI idiom named by BASELINE.json)
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns 0 on success
+ * or a vd_status code, never aborts, never allocates device memory and never synchronises the
+ * device; all device work is enqueued on the caller's stream.  Device pointers are marked [dev],
+ * host pointers [host].  vd_last_error() returns the message of the last failure on this thread.
+ */
+#ifndef VDESENS_H
+#define VDESENS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VD_ABI_VERSION 1
+
+typedef void* vd_stream_t; /* cudaStream_t */
+
+enum vd_status {
+  VD_OK = 0,
+  VD_ERR_INVALID = 1,      /* bad argument */
+  VD_ERR_CUDA = 2,         /* a CUDA runtime / driver call failed */
+  VD_ERR_UNSUPPORTED = 3,  /* shape outside what the kernels implement */
+  VD_ERR_NO_DEVICE = 4     /* no sm_100 device / driver entry point missing */
+};
+
+/* device-side status word bits written by kernels into `status` arguments */
+#define VD_STAT_CAND_OVERFLOW 1u   /* more candidates than `cap` in some frame */
+#define VD_STAT_DET_OVERFLOW 2u    /* more kept boxes than `max_det` */
+#define VD_STAT_WORK_OVERFLOW 4u   /* composite workspace too small */
+#define VD_STAT_WATCHDOG 8u        /* a device-side wait timed out */
+
+int vd_abi_version(void);
+const char* vd_build_info(void);
+int vd_last_error(char* buf, size_t n);
+/* fills SM count and compute capability of the current device */
+int vd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1 ingest: uint8 HWC frames -> mean-subtracted bf16 network input                           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct vd_frame {
+  const uint8_t* ptr; /* [dev] first byte of the frame, HWC, 3 channels */
+  int32_t h, w;       /* frame size in pixels */
+  int32_t pitch;      /* bytes per row */
+  int32_t reserved;
+} vd_frame_t;
+
+/* Layout of the ingested tensor "x0": [B][H][Wp][8] bf16, channels 0..2 = pixel - mean,
+ * channels 3..7 = 0, pixel column x stored at column x+3, columns outside [3, W+3) are zero.
+ * Wp = vd_x0_pitch(W).  conv1 reads it through a sliding-window tensor map (8 taps x 8 ch). */
+int vd_x0_pitch(int W);
+
+/* Letterboxes each frame to HxW (cv2 INTER_LINEAR uint8 fixed-point arithmetic, grey 128 pad,
+ * integer-truncated target size and floor-divided placement exactly as utils.py:8-18), subtracts
+ * mean[c] from channel c in caller order, writes x0.  frames: [dev] array of B descriptors.
+ * The pad columns of x0 must have been zeroed once by the caller (cudaMemset at allocation). */
+int vd_ingest_u8hwc(const vd_frame_t* frames, int B, void* x0, int H, int W,
+                    const float mean[3], vd_stream_t stream);
+
+/* Fast path for frames that already have the network's size (h == H, w == W for every frame:
+ * the letterbox is the identity, BASELINE configs 2-5).  Same output as vd_ingest_u8hwc. */
+int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x0, int H, int W,
+                             const float mean[3], vd_stream_t stream);
+
+/* Optional fp32 NCHW output identical to Retinaface.preprocess()'s tensor (face.py:87). */
+int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H, int W,
+                             const float mean[3], vd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2 convolution: implicit GEMM on tcgen05 (TMEM accumulators, TMA operand feed)              */
+/* ------------------------------------------------------------------------------------------ */
+#define VD_CONV_RELU 1u        /* ReLU in the epilogue (after the residual add)            */
+#define VD_CONV_RESIDUAL 2u    /* + residual[pixel][co] before ReLU                         */
+#define VD_CONV_UPADD 4u       /* + nearest-upsampled half-resolution tensor AFTER ReLU     */
+#define VD_CONV_OUT_F32 8u     /* store fp32 instead of bf16 (head GEMM)                    */
+#define VD_CONV_IN_X0 16u      /* input is the ingest layout (conv1: 7x7 s2 p3, 3->64)       */
+
+typedef struct vd_conv_desc {
+  int32_t B;                 /* frames */
+  int32_t Hin, Win, Cin;     /* input NHWC (Cin multiple of 64; for IN_X0: H, W of the frame) */
+  int32_t Hout, Wout, Cout;  /* output extent, Cout multiple of 32 */
+  int32_t R, S;              /* filter height / width */
+  int32_t stride, pad;
+  int32_t dst_C, dst_coff;   /* channels of the destination buffer and first channel written */
+  int32_t up_H, up_W;        /* extent of the UPADD source (half resolution) */
+  uint32_t flags;
+  const void* x;             /* [dev] input activations, bf16 NHWC (or x0) */
+  const void* w;             /* [dev] packed weights bf16 [Cout][R][S][Cin] (BN folded) */
+  const float* bias;         /* [dev] fp32 [Cout] (BN folded / conv bias) */
+  const void* residual;      /* [dev] bf16 [B][Hout][Wout][Cout] or NULL */
+  const void* upadd;         /* [dev] bf16 [B][up_H][up_W][Cout] or NULL */
+  void* y;                   /* [dev] output */
+} vd_conv_desc_t;
+
+typedef struct vd_conv_plan vd_conv_plan_t;
+
+/* Encodes the TMA tensor maps and picks the tiling; host-only work, no device access. */
+int vd_conv_plan_create(const vd_conv_desc_t* desc, vd_conv_plan_t** plan);
+int vd_conv_plan_destroy(vd_conv_plan_t* plan);
+int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream);
+/* tiling chosen for the plan: tile = TW x TH pixels x NB frames (<= 128 rows), BN output channels */
+int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, int* NB, int* BN,
+                      int* num_tiles, int* grid);
+
+/* max-pool 3x3 stride 2 pad 1 on bf16 NHWC (torchvision resnet stem) */
+int vd_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K3 decode + threshold + compaction                                                          */
+/* ------------------------------------------------------------------------------------------ */
+/* heads[l]: [dev] fp32 [B][h_l*w_l][32] from the fused head GEMM of level l; per cell:
+ *   [0:8) bbox (2 anchors x 4), [8:12) class logits (2 anchors x (bg, face)), [12:32) landmarks.
+ * Writes candidates with softmax face score >= conf_thr: cand [B][cap][16] fp32 =
+ *   x1,y1,x2,y2,score,10 landmark coords (normalised letterbox space), anchor index (int bits);
+ * cand_count [B] is zeroed by this call.  Order inside a frame is unspecified (NMS sorts). */
+int vd_decode_threshold(const float* heads_l0, const float* heads_l1, const float* heads_l2,
+                        int B, int H, int W, float conf_thr, int cap, float* cand,
+                        int32_t* cand_count, uint32_t* status, vd_stream_t stream);
+
+/* Same decode for separately laid-out reference tensors loc [B][A][4], conf [B][A][2] (already
+ * softmaxed), landms [B][A][10] (the signature of Retinaface.postprocess, face.py:93). */
+int vd_decode_threshold_lcl(const float* loc, const float* conf, const float* landms, int B, int H,
+                            int W, float conf_thr, int cap, float* cand, int32_t* cand_count,
+                            uint32_t* status, vd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K4 batched NMS + un-letterbox                                                               */
+/* ------------------------------------------------------------------------------------------ */
+#define VD_NMS_MAX_CAND 8192
+size_t vd_nms_workspace_bytes(int B, int cap);
+/* Greedy NMS per frame, torchvision semantics (descending score, ties by lower anchor index,
+ * suppress when IoU > iou_thr, areas without +1).  unletterbox [B][4] = offx, offy, scalex, scaley
+ * (fp32, computed as utils_bbox.py:26-31); out_rows [B][max_det][16]: 15 corrected values +
+ * anchor index, in descending score; out_count [B]. */
+int vd_nms_batched(const float* cand, const int32_t* cand_count, int B, int cap, float iou_thr,
+                   const float* unletterbox, int max_det, float* out_rows, int32_t* out_count,
+                   uint32_t* status, void* workspace, size_t workspace_bytes, vd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K5 compositing: sequential mosaic / Gaussian blur over boxes, in place                      */
+/* ------------------------------------------------------------------------------------------ */
+#define VD_MODE_MOSAIC 0
+#define VD_MODE_GAUSS 1
+#define VD_MAX_KSIZE 255
+#define VD_MAX_BOXES_PER_FRAME 1024
+
+/* cv::getGaussianKernel + 8.8 fixed point with error diffusion (cv2.GaussianBlur uint8 path);
+ * taps_q8 [host] receives ksize values summing to 256. */
+int vd_gaussian_taps_q8(int ksize, double sigma, uint16_t* taps_q8);
+
+size_t vd_composite_workspace_bytes(int B, int max_boxes, size_t scratch_pixels_per_frame);
+
+/* frames [dev] B descriptors (ptr is written through: const is cast away by the library);
+ * det_rows/det_count: [dev] output of vd_nms_batched (may be NULL): face boxes, applied first in
+ * row order, coordinates = int(row[0..3] * (w,h,w,h)) truncated toward zero (combine_detect.py:243);
+ * ext_boxes [dev] [B][max_ext][4] int32 + ext_count [dev] [B]: externally supplied (plate) boxes
+ * applied after the faces (combine_detect.py:244).  Boxes are clipped to the frame and skipped if
+ * empty (combine_detect.py:145-150).  Each box sees the result of the previous ones. */
+int vd_composite_rois(const vd_frame_t* frames, int B, const float* det_rows,
+                      const int32_t* det_count, int max_det, const int32_t* ext_boxes,
+                      const int32_t* ext_count, int max_ext, int mode, int mosaic_level,
+                      const uint16_t* taps_q8, int ksize, uint32_t* status, void* workspace,
+                      size_t workspace_bytes, vd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDESENS_H */

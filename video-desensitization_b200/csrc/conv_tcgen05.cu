@@ -1,0 +1,515 @@
+// conv_tcgen05.cu — K2: convolution as implicit GEMM on the 5th-gen tensor cores.
+//
+// Replaces every conv+BN(+ReLU)(+residual)(+FPN top-down add) of RetinaFace.forward
+// (reference detect_face/retinaface.py:114-148, detect_face/nets/layers.py:10-114, torchvision
+// resnet50 Bottleneck) with ONE persistent, warp-specialised kernel:
+//
+//   D[pixel, co] = sum_{r,s,ci} X[n, y*sh-ph+r, x*sw-pw+s, ci] * W[co, r, s, ci]
+//
+//   * activations are bf16 NHWC; an M-tile is a TW x TH x NB box of output pixels (<= 128 rows);
+//     for every filter tap (r,s) and 64-channel slice the A operand is fetched by ONE 4-D TMA
+//     tile load at shifted coordinates — TMA's out-of-bounds zero fill implements the padding and
+//     `elementStrides` implements the convolution stride, so there is no im2col buffer anywhere;
+//   * each pixel's 64 channels are one 128-byte row of a SWIZZLE_128B K-major UMMA operand;
+//   * weights [Cout][R*S*Cin] bf16 (BN folded) are the K-major B operand, 2-D TMA;
+//   * tcgen05.mma (M=128, N=BN, K=16) accumulates fp32 in TMEM; two accumulator buffers so the
+//     epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> +bias -> (+residual) -> ReLU
+//     -> (+nearest-upsampled FPN tensor) -> bf16 (or fp32 for the head GEMM) -> global.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <cuda.h>
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+struct ConvKParams {
+  int TW, TH, NB;
+  int tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;
+  int rows_used;          // TW*TH*NB
+  int a_bytes;            // rows_used * 128
+  int B, Hout, Wout, Cout;
+  int R, S, cin_blocks;
+  int stride_h, stride_w, pad_h, pad_w;
+  int dst_C, dst_coff;
+  int up_H, up_W;
+  uint32_t flags;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* upadd;
+  void* y;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+};
+
+constexpr int kThreads = 192;
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows*128B)
+// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int KB = p.R * p.S * p.cin_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tb = m / p.tiles_y;
+        const int xin0 = tx * p.TW * p.stride_w - p.pad_w;
+        const int yin0 = ty * p.TH * p.stride_h - p.pad_h;
+        const int b0 = tb * p.NB;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.a_bytes + Cfg::B_BYTES));
+              tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + s, yin0 + r, b0);
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, n_tile * BN);
+              if (++stage == Cfg::STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+      // a/b K-major, N>>3 [17,23), M>>4 [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                 (static_cast<uint32_t>(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                      static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int tx_ = row % p.TW;
+    const int ty_ = (row / p.TW) % p.TH;
+    const int nb_ = row / (p.TW * p.TH);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int tb = m / p.tiles_y;
+      const int x = tx * p.TW + tx_;
+      const int y = ty * p.TH + ty_;
+      const int b = tb * p.NB + nb_;
+      const bool valid = (row < p.rows_used) && (x < p.Wout) && (y < p.Hout) && (b < p.B);
+      const size_t pix = (static_cast<size_t>(b) * p.Hout + y) * p.Wout + x;
+      size_t up_pix = 0;
+      if (p.flags & VD_CONV_UPADD) {
+        const int uy = min(y >> 1, p.up_H - 1), ux = min(x >> 1, p.up_W - 1);
+        up_pix = (static_cast<size_t>(b) * p.up_H + uy) * p.up_W + ux;
+      }
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c0), v);
+        tmem_ld_wait();
+        if (valid) {
+          const int n0 = n_tile * BN + c0;
+          float f[32];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(bp + j);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+          }
+          if (p.flags & VD_CONV_RESIDUAL) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = __ldg(rp + j);
+              f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
+              f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
+              f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
+              f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+            }
+          }
+          if (p.flags & VD_CONV_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.flags & VD_CONV_UPADD) {
+            const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * p.Cout + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = __ldg(up + j);
+              f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
+              f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
+              f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
+              f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+            }
+          }
+          if (p.flags & VD_CONV_OUT_F32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.dst_C + p.dst_coff + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + pix * p.dst_C + p.dst_coff + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              op[j] = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // teardown: everyone done with TMEM before the allocating warp frees it
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+}  // namespace
+
+struct vd_conv_plan {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  ConvKParams kp;
+  int BN;
+  int grid;
+  vd_conv_desc_t desc;
+};
+
+static void choose_tile(int Wout, int Hout, int B, int sw, int sh, int* TW, int* TH, int* NB) {
+  long best_tiles = -1;
+  int bw = 1, bh = 1, bn = 1;
+  for (int tw = 1; tw <= Wout && tw <= 128; ++tw) {
+    if (tw * sw > 256) break;
+    for (int th = 1; th <= Hout && tw * th <= 128; ++th) {
+      if (th * sh > 256) break;
+      int nb = 128 / (tw * th);
+      if (nb > B) nb = B;
+      if (nb < 1) nb = 1;
+      long tiles = static_cast<long>(vd_cdiv(Wout, tw)) * vd_cdiv(Hout, th) * vd_cdiv(B, nb);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && tw > bw)) {
+        best_tiles = tiles;
+        bw = tw; bh = th; bn = nb;
+      }
+    }
+  }
+  *TW = bw; *TH = bh; *NB = bn;
+}
+
+extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out) {
+  VD_REQUIRE(d && out, "vd_conv_plan_create: null argument");
+  const bool x0 = (d->flags & VD_CONV_IN_X0) != 0;
+  VD_REQUIRE(d->B > 0 && d->Hout > 0 && d->Wout > 0, "vd_conv_plan_create: empty extent");
+  VD_REQUIRE(d->Cout % 32 == 0 && d->Cout >= 32, "vd_conv_plan_create: Cout=%d must be a multiple of 32", d->Cout);
+  VD_REQUIRE(x0 || (d->Cin % 64 == 0), "vd_conv_plan_create: Cin=%d must be a multiple of 64", d->Cin);
+  VD_REQUIRE(d->x && d->w && d->bias && d->y, "vd_conv_plan_create: null tensor pointer");
+  VD_REQUIRE(!(d->flags & VD_CONV_RESIDUAL) || d->residual, "vd_conv_plan_create: residual flag without tensor");
+  VD_REQUIRE(!(d->flags & VD_CONV_UPADD) || (d->upadd && d->up_H > 0 && d->up_W > 0),
+             "vd_conv_plan_create: upadd flag without tensor");
+  VD_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->y) & 15) == 0,
+             "vd_conv_plan_create: tensors must be 16-byte aligned");
+  VD_REQUIRE(d->dst_coff % 32 == 0 && d->dst_C % 8 == 0 && d->dst_coff + d->Cout <= d->dst_C,
+             "vd_conv_plan_create: bad destination slice");
+  if (d->flags & VD_CONV_UPADD) {
+    // the FPN's F.interpolate(mode="nearest") source index floor(dst*in/out) must equal dst>>1
+    // (reference layers.py:102,110; true for every ceil(n/2) pyramid) — checked, not assumed
+    for (int yy = 0; yy < d->Hout; ++yy) {
+      int ref = static_cast<int>(floorf(yy * (static_cast<float>(d->up_H) / d->Hout)));
+      if (ref > d->up_H - 1) ref = d->up_H - 1;
+      int got = yy >> 1; if (got > d->up_H - 1) got = d->up_H - 1;
+      VD_REQUIRE(ref == got, "vd_conv_plan_create: nearest-upsample row map is not y>>1 (%d<-%d)", d->Hout, d->up_H);
+    }
+    for (int xx = 0; xx < d->Wout; ++xx) {
+      int ref = static_cast<int>(floorf(xx * (static_cast<float>(d->up_W) / d->Wout)));
+      if (ref > d->up_W - 1) ref = d->up_W - 1;
+      int got = xx >> 1; if (got > d->up_W - 1) got = d->up_W - 1;
+      VD_REQUIRE(ref == got, "vd_conv_plan_create: nearest-upsample col map is not x>>1 (%d<-%d)", d->Wout, d->up_W);
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    vd_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return VD_ERR_NO_DEVICE;
+  }
+
+  vd_conv_plan* pl = new (std::nothrow) vd_conv_plan();
+  VD_REQUIRE(pl, "out of host memory");
+  pl->desc = *d;
+  ConvKParams& k = pl->kp;
+  memset(&k, 0, sizeof(k));
+  int BN = d->Cout >= 256 ? 256 : d->Cout;
+  if (BN != 32 && BN != 64 && BN != 128 && BN != 256) {
+    delete pl;
+    vd_set_error("vd_conv_plan_create: unsupported Cout=%d", d->Cout);
+    return VD_ERR_UNSUPPORTED;
+  }
+  pl->BN = BN;
+
+  int sw, sh, pw, ph, R, S, cin_blocks;
+  if (x0) {
+    // conv1 7x7/2 p3 on the ingest layout: each filter row is one K block of 8 taps x 8 channels;
+    // the x stride/pad are baked into the sliding-window tensor map.
+    R = 7; S = 1; cin_blocks = 1; sh = 2; ph = 3; sw = 1; pw = 0;
+    VD_REQUIRE(d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3, "IN_X0 conv must be 7x7 s2 p3");
+  } else {
+    R = d->R; S = d->S; cin_blocks = d->Cin / 64; sh = sw = d->stride; ph = pw = d->pad;
+  }
+  choose_tile(d->Wout, d->Hout, d->B, sw, sh, &k.TW, &k.TH, &k.NB);
+  k.tiles_x = vd_cdiv(d->Wout, k.TW);
+  k.tiles_y = vd_cdiv(d->Hout, k.TH);
+  k.tiles_b = vd_cdiv(d->B, k.NB);
+  k.n_tiles = d->Cout / BN;
+  k.num_tiles = k.tiles_x * k.tiles_y * k.tiles_b * k.n_tiles;
+  k.rows_used = k.TW * k.TH * k.NB;
+  k.a_bytes = k.rows_used * 128;
+  k.B = d->B; k.Hout = d->Hout; k.Wout = d->Wout; k.Cout = d->Cout;
+  k.R = R; k.S = S; k.cin_blocks = cin_blocks;
+  k.stride_h = sh; k.stride_w = sw; k.pad_h = ph; k.pad_w = pw;
+  k.dst_C = d->dst_C; k.dst_coff = d->dst_coff;
+  k.up_H = d->up_H; k.up_W = d->up_W;
+  k.flags = d->flags;
+  k.bias = d->bias;
+  k.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  k.upadd = static_cast<const __nv_bfloat16*>(d->upadd);
+  k.y = d->y;
+
+  // ---- A: activations ----
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4], estr[4];
+  if (x0) {
+    const int Wp = vd_x0_pitch(d->Win);
+    gdim[0] = 64; gdim[1] = static_cast<cuuint64_t>(d->Wout); gdim[2] = static_cast<cuuint64_t>(d->Hin);
+    gdim[3] = static_cast<cuuint64_t>(d->B);
+    gstr[0] = 32;                                         // next output column = 2 pixels * 16 B
+    gstr[1] = static_cast<cuuint64_t>(Wp) * 16;
+    gstr[2] = static_cast<cuuint64_t>(Wp) * 16 * d->Hin;
+  } else {
+    gdim[0] = static_cast<cuuint64_t>(d->Cin); gdim[1] = static_cast<cuuint64_t>(d->Win);
+    gdim[2] = static_cast<cuuint64_t>(d->Hin); gdim[3] = static_cast<cuuint64_t>(d->B);
+    gstr[0] = static_cast<cuuint64_t>(d->Cin) * 2;
+    gstr[1] = gstr[0] * d->Win;
+    gstr[2] = gstr[1] * d->Hin;
+  }
+  box[0] = 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
+  box[3] = static_cast<cuuint32_t>(k.NB);
+  estr[0] = 1; estr[1] = static_cast<cuuint32_t>(sw); estr[2] = static_cast<cuuint32_t>(sh); estr[3] = 1;
+  CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vd_set_error("cuTensorMapEncodeTiled(A) failed: CUresult %d (dims %llu %llu %llu %llu, box %u %u %u %u)", (int)r,
+                 (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                 (unsigned long long)gdim[3], box[0], box[1], box[2], box[3]);
+    delete pl;
+    return VD_ERR_CUDA;
+  }
+  // ---- B: weights [Cout][Ktot] ----
+  const cuuint64_t Ktot = static_cast<cuuint64_t>(R) * S * cin_blocks * 64;
+  cuuint64_t wdim[2] = {Ktot, static_cast<cuuint64_t>(d->Cout)};
+  cuuint64_t wstr[1] = {Ktot * 2};
+  cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(BN)};
+  cuuint32_t wes[2] = {1, 1};
+  r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), wdim, wstr, wbox, wes,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vd_set_error("cuTensorMapEncodeTiled(B) failed: CUresult %d", (int)r);
+    delete pl;
+    return VD_ERR_CUDA;
+  }
+  int sms = vd_num_sms();
+  if (sms <= 0) sms = 148;
+  pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
+  *out = pl;
+  return VD_OK;
+}
+
+extern "C" int vd_conv_plan_destroy(vd_conv_plan_t* plan) {
+  delete plan;
+  return VD_OK;
+}
+
+extern "C" int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, int* NB, int* BN, int* num_tiles,
+                                 int* grid) {
+  VD_REQUIRE(plan, "vd_conv_plan_info: null plan");
+  if (TW) *TW = plan->kp.TW;
+  if (TH) *TH = plan->kp.TH;
+  if (NB) *NB = plan->kp.NB;
+  if (BN) *BN = plan->BN;
+  if (num_tiles) *num_tiles = plan->kp.num_tiles;
+  if (grid) *grid = plan->grid;
+  return VD_OK;
+}
+
+template <int BN>
+static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN><<<pl->grid, kThreads, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->kp);
+  VD_LAUNCH_CHECK();
+  return VD_OK;
+}
+
+extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
+  VD_REQUIRE(plan, "vd_conv_run: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (plan->BN) {
+    case 32: return launch_conv<32>(plan, st);
+    case 64: return launch_conv<64>(plan, st);
+    case 128: return launch_conv<128>(plan, st);
+    case 256: return launch_conv<256>(plan, st);
+  }
+  vd_set_error("vd_conv_run: bad BN");
+  return VD_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,192 @@
+// ingest.cu — K1: uint8 HWC frames -> letterboxed, mean-subtracted network input.
+//
+// Replaces Retinaface.preprocess (reference detect_face/face.py:65-88) = letterbox_image
+// (detect_face/utils/utils.py:8-18: cv2.resize INTER_LINEAR on uint8, grey-128 canvas, floor-divided
+// placement, int()-truncated target size) + preprocess_input (utils.py:27-29: subtract (104,117,123)
+// from channels in caller order) + HWC->CHW + float conversion + H2D.  Frames are already resident
+// on the device as uint8, so the 4 B/px/channel host tensor and its H2D copy disappear.
+//
+// The bilinear resize restates cv2's fixed-point path bit-for-bit: coefficients
+// rint(f*2048), horizontal sums in int32, vertical (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
+// HBM-bound: 3 B read + 16 B written per output pixel (x0 layout), coalesced 16-byte stores.
+#include "common.cuh"
+
+namespace {
+
+struct LetterGeom {
+  int nw, nh, dx, dy;      // resized size and placement inside the HxW canvas
+  double sx, sy;           // src/dst scale of cv2.resize
+};
+
+__device__ __forceinline__ LetterGeom letter_geom(int ih, int iw, int H, int W) {
+  LetterGeom g;
+  // python: scale = min(w/iw, h/ih); nw = int(iw*scale); nh = int(ih*scale)   (float64)
+  const double scale = fmin(static_cast<double>(W) / iw, static_cast<double>(H) / ih);
+  g.nw = static_cast<int>(iw * scale);
+  g.nh = static_cast<int>(ih * scale);
+  g.dx = (W - g.nw) / 2;     // operands are non-negative: C division == python floor division
+  g.dy = (H - g.nh) / 2;
+  g.sx = static_cast<double>(iw) / g.nw;   // cv2: scale_x = 1. / (dsize.width / (double)ssize.width)
+  g.sy = static_cast<double>(ih) / g.nh;
+  return g;
+}
+
+__device__ __forceinline__ void lin_coeff(int d, double scale, int n, int& s0, int& a0, int& a1) {
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= n - 1) { f = 0.f; s = n - 1; }
+  s0 = s;
+  a0 = __float2int_rn((1.f - f) * 2048.f);   // cvRound: half to even
+  a1 = __float2int_rn(f * 2048.f);
+}
+
+// one letterboxed pixel (3 channels, uint8 values 0..255)
+__device__ __forceinline__ void letter_pixel(const vd_frame_t& fr, const LetterGeom& g, int y, int x, int v[3]) {
+  const int yy = y - g.dy, xx = x - g.dx;
+  if (yy < 0 || yy >= g.nh || xx < 0 || xx >= g.nw) {
+    v[0] = v[1] = v[2] = 128;
+    return;
+  }
+  if (g.nw == fr.w && g.nh == fr.h) {       // cv2.resize to the same size is a copy
+    const uint8_t* p = fr.ptr + static_cast<size_t>(yy) * fr.pitch + xx * 3;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    return;
+  }
+  int x0, xa0, xa1, y0, yb0, yb1;
+  lin_coeff(xx, g.sx, fr.w, x0, xa0, xa1);
+  lin_coeff(yy, g.sy, fr.h, y0, yb0, yb1);
+  const int x1 = min(x0 + 1, fr.w - 1), y1 = min(y0 + 1, fr.h - 1);
+  const uint8_t* r0 = fr.ptr + static_cast<size_t>(y0) * fr.pitch;
+  const uint8_t* r1 = fr.ptr + static_cast<size_t>(y1) * fr.pitch;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[x0 * 3 + c] * xa0 + r0[x1 * 3 + c] * xa1;
+    const int h1 = r1[x0 * 3 + c] * xa0 + r1[x1 * 3 + c] * xa1;
+    v[c] = (((yb0 * (h0 >> 4)) >> 16) + ((yb1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  }
+}
+
+// x0 layout: [B][H][Wp][8] bf16, pixel x at column x+3.  One thread = one output pixel = one 16 B store.
+__global__ void __launch_bounds__(256)
+ingest_x0_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp, float m0,
+                 float m1, float m2) {
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const vd_frame_t fr = frames[b];
+  const LetterGeom g = letter_geom(fr.h, fr.w, H, W);
+  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * Wp;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    int v[3];
+    letter_pixel(fr, g, y, x, v);
+    uint4 o;
+    o.x = pack_bf16x2(static_cast<float>(v[0]) - m0, static_cast<float>(v[1]) - m1);
+    o.y = pack_bf16x2(static_cast<float>(v[2]) - m2, 0.f);
+    o.z = 0u;
+    o.w = 0u;
+    row[x + 3] = o;
+  }
+}
+
+// fast path: frame size == network input (BASELINE configs 2-5): no resize, no pad.
+// Each thread converts 4 pixels: 12 B in (3 x u32), 64 B out (4 x uint4).
+__global__ void __launch_bounds__(256)
+ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp,
+                          float m0, float m1, float m2) {
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const vd_frame_t fr = frames[b];
+  const uint8_t* src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
+  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * Wp + 3;
+  const int groups = W >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    uint8_t px[12];
+    if (aligned) {
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src) + gi * 3;
+      const uint32_t a = __ldg(s32), bb = __ldg(s32 + 1), c = __ldg(s32 + 2);
+      *reinterpret_cast<uint32_t*>(px) = a;
+      *reinterpret_cast<uint32_t*>(px + 4) = bb;
+      *reinterpret_cast<uint32_t*>(px + 8) = c;
+    } else {
+      for (int i = 0; i < 12; ++i) px[i] = src[gi * 12 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(static_cast<float>(px[3 * i]) - m0, static_cast<float>(px[3 * i + 1]) - m1);
+      o.y = pack_bf16x2(static_cast<float>(px[3 * i + 2]) - m2, 0.f);
+      o.z = 0u;
+      o.w = 0u;
+      row[gi * 4 + i] = o;
+    }
+  }
+  // tail pixels (W % 4)
+  if (blockIdx.x == 0 && threadIdx.x < (W & 3)) {
+    const int x = (groups << 2) + threadIdx.x;
+    uint4 o;
+    o.x = pack_bf16x2(static_cast<float>(src[x * 3]) - m0, static_cast<float>(src[x * 3 + 1]) - m1);
+    o.y = pack_bf16x2(static_cast<float>(src[x * 3 + 2]) - m2, 0.f);
+    o.z = 0u;
+    o.w = 0u;
+    row[x] = o;
+  }
+}
+
+// fp32 NCHW output, byte-identical to the tensor Retinaface.preprocess returns (face.py:87)
+__global__ void __launch_bounds__(256)
+ingest_nchw_kernel(const vd_frame_t* __restrict__ frames, float* __restrict__ out, int H, int W, float m0, float m1,
+                   float m2) {
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const vd_frame_t fr = frames[b];
+  const LetterGeom g = letter_geom(fr.h, fr.w, H, W);
+  const size_t plane = static_cast<size_t>(H) * W;
+  float* o = out + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * W;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    int v[3];
+    letter_pixel(fr, g, y, x, v);
+    o[x] = static_cast<float>(v[0]) - m0;
+    o[plane + x] = static_cast<float>(v[1]) - m1;
+    o[2 * plane + x] = static_cast<float>(v[2]) - m2;
+  }
+}
+
+}  // namespace
+
+extern "C" int vd_ingest_u8hwc(const vd_frame_t* frames, int B, void* x0, int H, int W, const float mean[3],
+                               vd_stream_t stream) {
+  VD_REQUIRE(frames && x0 && mean, "vd_ingest_u8hwc: null argument");
+  VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc: bad extent");
+  const int Wp = vd_x0_pitch(W);
+  dim3 grid(vd_cdiv(W, 256), H, B);
+  ingest_x0_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, static_cast<uint4*>(x0), H, W, Wp,
+                                                                         mean[0], mean[1], mean[2]);
+  VD_LAUNCH_CHECK();
+  return VD_OK;
+}
+
+// identity fast path, selected by the host when every frame already has the network's size
+extern "C" int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x0, int H, int W,
+                                        const float mean[3], vd_stream_t stream) {
+  VD_REQUIRE(frames && x0 && mean, "vd_ingest_u8hwc_identity: null argument");
+  VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc_identity: bad extent");
+  const int Wp = vd_x0_pitch(W);
+  dim3 grid(vd_cdiv(vd_cdiv(W, 4), 256), H, B);
+  ingest_x0_identity_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
+  VD_LAUNCH_CHECK();
+  return VD_OK;
+}
+
+extern "C" int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H, int W,
+                                        const float mean[3], vd_stream_t stream) {
+  VD_REQUIRE(frames && out && mean, "vd_ingest_u8hwc_nchw_f32: null argument");
+  VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc_nchw_f32: bad extent");
+  dim3 grid(vd_cdiv(W, 256), H, B);
+  ingest_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, out, H, W, mean[0], mean[1],
+                                                                           mean[2]);
+  VD_LAUNCH_CHECK();
+  return VD_OK;
+}

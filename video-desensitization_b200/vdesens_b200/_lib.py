@@ -1,0 +1,98 @@
+"""ctypes binding of libvdesens.so (include/vdesens.h).  There is NO fallback: if the CUDA
+library is missing or a call fails, a RuntimeError is raised — the product path never computes on
+the CPU."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvdesens.so")
+
+VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0 = 1, 2, 4, 8, 16
+VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
+VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
+VD_NMS_MAX_CAND = 8192
+VD_MAX_BOXES_PER_FRAME = 1024
+
+
+class VdFrame(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("pitch", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class VdConvDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin", C.c_int32),
+                ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout", C.c_int32),
+                ("R", C.c_int32), ("S", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("dst_C", C.c_int32), ("dst_coff", C.c_int32), ("up_H", C.c_int32), ("up_W", C.c_int32),
+                ("flags", C.c_uint32),
+                ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+                ("upadd", C.c_void_p), ("y", C.c_void_p)]
+
+
+_SIGS = {
+    "vd_abi_version": (C.c_int, []),
+    "vd_build_info": (C.c_char_p, []),
+    "vd_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "vd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "vd_x0_pitch": (C.c_int, [C.c_int]),
+    "vd_ingest_u8hwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "vd_ingest_u8hwc_identity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "vd_ingest_u8hwc_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "vd_conv_plan_create": (C.c_int, [C.POINTER(VdConvDesc), C.POINTER(C.c_void_p)]),
+    "vd_conv_plan_destroy": (C.c_int, [C.c_void_p]),
+    "vd_conv_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vd_conv_plan_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6),
+    "vd_maxpool3x3s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vd_decode_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vd_decode_threshold_lcl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vd_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "vd_nms_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vd_gaussian_taps_q8": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_uint16)]),
+    "vd_composite_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_size_t]),
+    "vd_composite_rois": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+EXPORTED = tuple(_SIGS)
+
+_lib = None
+
+
+def lib():
+    """Loads libvdesens.so once.  Raises if it has not been built (see __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                f"g.build()' or make -C video-desensitization_b200/csrc). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)       # AttributeError if the library does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().vd_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    """reference behaviour at the boundary: Python exceptions, never an abort (combine_detect.py:226-228
+    catches Exception and skips the batch)."""
+    if rc != 0:
+        raise RuntimeError(f"libvdesens {what} failed (status {rc}): {last_error()}")
+
+
+def gaussian_taps_q8(ksize: int, sigma: float = 0.0):
+    arr = (C.c_uint16 * 256)()
+    check(lib().vd_gaussian_taps_q8(int(ksize), float(sigma), arr), "vd_gaussian_taps_q8")
+    return [int(arr[i]) for i in range(ksize)]

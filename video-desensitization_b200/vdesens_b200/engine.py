@@ -1,0 +1,313 @@
+"""Device engine: one persistent RetinaFace-ResNet50 replica on one GPU.
+
+Owns the packed weights, every activation buffer for a fixed (B, H, W), one conv plan (TMA tensor
+maps + tiling) per layer, the post-processing workspaces and a private CUDA stream.  `forward`
+enqueues ingest -> 82 convs + max-pool -> decode/threshold -> NMS/un-letterbox with no host sync;
+`composite` enqueues the mosaic / Gaussian pass over the same resident frames.  Replaces the body
+of Retinaface.detect_images (reference detect_face/face.py:120-150) and nn.DataParallel
+(face.py:56): one process / engine per GPU, no per-forward weight broadcast.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, arch, weights
+
+MEAN = (104.0, 117.0, 123.0)       # reference detect_face/utils/utils.py:28
+# vd_frame_t (include/vdesens.h): 24 bytes
+FRAME_DTYPE = np.dtype([("ptr", "<u8"), ("h", "<i4"), ("w", "<i4"), ("pitch", "<i4"), ("reserved", "<i4")])
+assert FRAME_DTYPE.itemsize == 24
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class DetectorEngine:
+    def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
+                 cand_cap=4096, max_det=1024, max_ext=256, scratch_frames=8.0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        self.B, self.H, self.W = int(batch), int(in_h), int(in_w)
+        self.confidence, self.nms_iou = float(confidence), float(nms_iou)
+        assert cand_cap >= 64 and (cand_cap & (cand_cap - 1)) == 0 and cand_cap <= _lib.VD_NMS_MAX_CAND
+        self.cap, self.max_det, self.max_ext = int(cand_cap), int(max_det), int(max_ext)
+        self.launches_per_forward = 0
+        with torch.cuda.device(self.device):
+            sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
+            _lib.check(self.lib.vd_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), "vd_device_info")
+            if mj.value != 10:
+                raise RuntimeError(f"libvdesens is built for sm_100a only; device is sm_{mj.value}{mn.value}")
+            self.sm_count = sm.value
+            self.stream = torch.cuda.Stream(device=self.device)
+            self._mean = (C.c_float * 3)(*MEAN)
+            self._build(state_dict, scratch_frames)
+
+    # ------------------------------------------------------------------------------------------
+    def _build(self, state_dict, scratch_frames):
+        dev, B, H, W = self.device, self.B, self.H, self.W
+        convs, ops, bufs = arch.build_graph()
+        packed = weights.pack_all(state_dict)
+        self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
+        self.Wp = self.lib.vd_x0_pitch(W)
+        self.buf, self.buf_hw = {}, {}
+        for bs in bufs:
+            h, w = arch.feature_hw(H, W, bs.stride)
+            self.buf_hw[bs.name] = (h, w, bs.channels)
+            if bs.name == "x0":
+                self.buf["x0"] = torch.zeros((B, H, self.Wp, 8), dtype=torch.bfloat16, device=dev)
+            else:
+                self.buf[bs.name] = torch.empty((B, h, w, bs.channels), dtype=torch.bfloat16, device=dev)
+        self.heads = []
+        for lvl, s in enumerate(arch.CFG_RE50["steps"]):
+            h, w = arch.feature_hw(H, W, s)
+            self.heads.append(torch.empty((B, h * w, arch.HEAD_ROWS), dtype=torch.float32, device=dev))
+        self.A = arch.num_anchors(H, W)
+
+        # ---- plans ----
+        self.plans = []      # list of ("conv", handle, name) / ("maxpool", (src, dst)) in execution order
+        self._plan_handles = []
+        for op in ops:
+            if op.kind == "conv":
+                c = op.conv
+                flags = _lib.VD_CONV_RELU if c.relu else 0
+                hin, win, cin = self.buf_hw[op.src]
+                hout, wout, dst_c = self.buf_hw[op.dst]
+                d = _lib.VdConvDesc()
+                d.B, d.Hin, d.Win = B, hin, win
+                if op.src == "x0":
+                    flags |= _lib.VD_CONV_IN_X0
+                    d.Cin = 3
+                else:
+                    d.Cin = cin
+                d.Hout, d.Wout, d.Cout = hout, wout, c.cout
+                d.R = d.S = c.k
+                d.stride, d.pad = c.stride, c.pad
+                d.dst_C, d.dst_coff = dst_c, op.dst_coff
+                res = up = None
+                if op.residual:
+                    flags |= _lib.VD_CONV_RESIDUAL
+                    res = self.buf[op.residual]
+                    assert tuple(res.shape) == (B, hout, wout, c.cout)
+                if op.upsample_add:
+                    flags |= _lib.VD_CONV_UPADD
+                    up = self.buf[op.upsample_add]
+                    d.up_H, d.up_W = up.shape[1], up.shape[2]
+                d.flags = flags
+                wt, bt = self.w[c.name]
+                d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
+                d.residual = res.data_ptr() if res is not None else None
+                d.upadd = up.data_ptr() if up is not None else None
+                d.y = self.buf[op.dst].data_ptr()
+                self.plans.append(("conv", self._make_plan(d, c.name), c.name))
+            elif op.kind == "maxpool":
+                self.plans.append(("maxpool", (op.src, op.dst), "maxpool"))
+            elif op.kind == "heads":
+                hin, win, cin = self.buf_hw[op.src]
+                d = _lib.VdConvDesc()
+                d.B, d.Hin, d.Win, d.Cin = B, hin, win, cin
+                d.Hout, d.Wout, d.Cout = hin, win, arch.HEAD_ROWS
+                d.R = d.S = 1
+                d.stride, d.pad = 1, 0
+                d.dst_C, d.dst_coff = arch.HEAD_ROWS, 0
+                d.flags = _lib.VD_CONV_OUT_F32
+                wt, bt = self.w[f"heads.{op.level}"]
+                d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
+                d.y = self.heads[op.level].data_ptr()
+                self.plans.append(("conv", self._make_plan(d, f"heads.{op.level}"), f"heads.{op.level}"))
+
+        # ---- post-processing state ----
+        self.frame_desc_host = torch.zeros((B, 6), dtype=torch.int32).pin_memory()   # 24-byte vd_frame_t rows
+        self.frame_desc = torch.zeros((B, 6), dtype=torch.int32, device=dev)
+        self.cand = torch.empty((B, self.cap, 16), dtype=torch.float32, device=dev)
+        self.cand_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.unlb_host = torch.zeros((B, 4), dtype=torch.float32).pin_memory()
+        self.unlb = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+        self.out_rows = torch.zeros((B, self.max_det, 16), dtype=torch.float32, device=dev)
+        self.out_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.nms_ws_bytes = int(self.lib.vd_nms_workspace_bytes(B, self.cap))
+        self.nms_ws = torch.empty((self.nms_ws_bytes,), dtype=torch.uint8, device=dev)
+        self.ext_boxes = torch.zeros((B, self.max_ext, 4), dtype=torch.int32, device=dev)
+        self.ext_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.scratch_px = int(scratch_frames * H * W)
+        self.comp_ws_bytes = int(self.lib.vd_composite_workspace_bytes(B, self.max_det + self.max_ext, self.scratch_px))
+        self.comp_ws = torch.empty((self.comp_ws_bytes,), dtype=torch.uint8, device=dev)
+        # pinned result mirrors: one D2H per batch
+        self.out_rows_host = torch.zeros((B, self.max_det, 16), dtype=torch.float32).pin_memory()
+        self.out_count_host = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.status_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.launches_per_forward = 1 + sum(1 for p in self.plans) + 1 + 3
+        self._graph = None
+
+    def _make_plan(self, d, name):
+        h = C.c_void_p()
+        _lib.check(self.lib.vd_conv_plan_create(C.byref(d), C.byref(h)), f"vd_conv_plan_create({name})")
+        self._plan_handles.append(h)
+        return h
+
+    def plan_info(self):
+        out = []
+        for kind, h, name in self.plans:
+            if kind != "conv":
+                continue
+            v = [C.c_int() for _ in range(6)]
+            _lib.check(self.lib.vd_conv_plan_info(h, *[C.byref(x) for x in v]), "vd_conv_plan_info")
+            out.append((name,) + tuple(x.value for x in v))
+        return out
+
+    def __del__(self):
+        try:
+            for h in getattr(self, "_plan_handles", []):
+                self.lib.vd_conv_plan_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def set_frames(self, frames_u8, shapes=None):
+        """frames_u8: device uint8 tensor (B,h,w,3) or list of device tensors (h_i,w_i,3).
+        Fills the frame descriptors and the un-letterbox parameters (fp32 arithmetic of reference
+        utils_bbox.py:26-31).  Returns True when every frame already has the network's size."""
+        B = self.B
+        fl = list(frames_u8) if not isinstance(frames_u8, torch.Tensor) else [frames_u8[i] for i in range(frames_u8.shape[0])]
+        assert len(fl) == B, f"engine built for batch {B}, got {len(fl)}"
+        d = self.frame_desc_host.numpy().view(FRAME_DTYPE).reshape(B)      # vd_frame_t records
+        u = self.unlb_host.numpy()
+        identity = True
+        inp = np.array([self.H, self.W], np.float32)
+        for i, f in enumerate(fl):
+            assert f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.stride(2) == 1 and f.stride(1) == 3
+            h, w = int(f.shape[0]), int(f.shape[1])
+            p = f.data_ptr()
+            d[i] = (p, h, w, int(f.stride(0)), 0)
+            identity &= (h == self.H and w == self.W)
+            ish = np.array([h, w], np.float32)
+            new_shape = (ish * np.min(inp / ish)).astype(np.float32)
+            offset = ((inp - new_shape) / np.float32(2.0) / inp).astype(np.float32)
+            scale = (inp / new_shape).astype(np.float32)
+            u[i] = (offset[1], offset[0], scale[1], scale[0])
+        self._frames_keepalive = fl
+        self.frame_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in fl]
+        with torch.cuda.stream(self.stream):
+            self.frame_desc.copy_(self.frame_desc_host, non_blocking=True)
+            self.unlb.copy_(self.unlb_host, non_blocking=True)
+        self.identity = identity
+        return identity
+
+    # ------------------------------------------------------------------------------------------
+    def enqueue_ingest(self):
+        s = C.c_void_p(self.stream.cuda_stream)
+        fn = self.lib.vd_ingest_u8hwc_identity if self.identity else self.lib.vd_ingest_u8hwc
+        _lib.check(fn(_ptr(self.frame_desc), self.B, _ptr(self.buf["x0"]), self.H, self.W, self._mean, s), "vd_ingest")
+
+    def enqueue_network(self, upto=None):
+        s = C.c_void_p(self.stream.cuda_stream)
+        for kind, h, name in self.plans:
+            if kind == "conv":
+                _lib.check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
+            else:
+                src, dst = h
+                hh, ww, cc = self.buf_hw[src]
+                _lib.check(self.lib.vd_maxpool3x3s2(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s),
+                           "vd_maxpool3x3s2")
+            if upto is not None and name == upto:
+                break
+
+    def enqueue_postprocess(self):
+        s = C.c_void_p(self.stream.cuda_stream)
+        _lib.check(self.lib.vd_decode_threshold(_ptr(self.heads[0]), _ptr(self.heads[1]), _ptr(self.heads[2]),
+                                                self.B, self.H, self.W, self.confidence, self.cap, _ptr(self.cand),
+                                                _ptr(self.cand_count), _ptr(self.status), s), "vd_decode_threshold")
+        self.enqueue_nms()
+
+    def enqueue_nms(self):
+        s = C.c_void_p(self.stream.cuda_stream)
+        _lib.check(self.lib.vd_nms_batched(_ptr(self.cand), _ptr(self.cand_count), self.B, self.cap, self.nms_iou,
+                                           _ptr(self.unlb), self.max_det, _ptr(self.out_rows), _ptr(self.out_count),
+                                           _ptr(self.status), _ptr(self.nms_ws), self.nms_ws_bytes, s), "vd_nms_batched")
+
+    def enqueue_composite(self, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, use_faces=True, use_ext=True):
+        s = C.c_void_p(self.stream.cuda_stream)
+        m = _lib.VD_MODE_MOSAIC if mode == "mosaic" else _lib.VD_MODE_GAUSS
+        taps = None
+        if m == _lib.VD_MODE_GAUSS:
+            key = (int(ksize), float(sigma))
+            if getattr(self, "_taps_key", None) != key:
+                arr = (C.c_uint16 * 256)()
+                _lib.check(self.lib.vd_gaussian_taps_q8(int(ksize), float(sigma), arr), "vd_gaussian_taps_q8")
+                self._taps, self._taps_key = arr, key
+            taps = self._taps
+        _lib.check(self.lib.vd_composite_rois(
+            _ptr(self.frame_desc), self.B,
+            _ptr(self.out_rows) if use_faces else None, _ptr(self.out_count) if use_faces else None, self.max_det,
+            _ptr(self.ext_boxes) if use_ext else None, _ptr(self.ext_count) if use_ext else None, self.max_ext,
+            m, int(mosaic_level), taps, int(ksize), _ptr(self.status), _ptr(self.comp_ws), self.comp_ws_bytes, s),
+            "vd_composite_rois")
+
+    def forward(self):
+        """ingest -> network -> decode/threshold -> NMS, enqueued on the engine stream."""
+        self.enqueue_ingest()
+        self.enqueue_network()
+        self.enqueue_postprocess()
+
+    def set_ext_boxes(self, boxes_per_frame):
+        """externally supplied (plate) boxes: list (len B) of lists of (x1,y1,x2,y2) ints."""
+        eb = np.zeros((self.B, self.max_ext, 4), np.int32)
+        ec = np.zeros((self.B,), np.int32)
+        for i, bl in enumerate(boxes_per_frame):
+            n = min(len(bl), self.max_ext)
+            if len(bl) > self.max_ext:
+                raise RuntimeError(f"{len(bl)} external boxes exceed max_ext={self.max_ext}")
+            if n:
+                eb[i, :n] = np.asarray([[int(v) for v in b] for b in bl[:n]], np.int32)
+            ec[i] = n
+        with torch.cuda.stream(self.stream):
+            self.ext_boxes.copy_(torch.from_numpy(eb).pin_memory(), non_blocking=True)
+            self.ext_count.copy_(torch.from_numpy(ec).pin_memory(), non_blocking=True)
+        self.stream.synchronize()
+
+    def fetch_results(self):
+        """one D2H per batch + status check.  Returns (rows (B,max_det,16) numpy, counts (B,))."""
+        with torch.cuda.stream(self.stream):
+            self.out_rows_host.copy_(self.out_rows, non_blocking=True)
+            self.out_count_host.copy_(self.out_count, non_blocking=True)
+            self.status_host.copy_(self.status, non_blocking=True)
+        self.stream.synchronize()
+        self.check_status(int(self.status_host[0]))
+        return self.out_rows_host.numpy(), self.out_count_host.numpy()
+
+    def check_status(self, st):
+        if st:
+            self.status.zero_()
+            msgs = []
+            if st & _lib.VD_STAT_CAND_OVERFLOW:
+                msgs.append(f"more than cand_cap={self.cap} candidates above the confidence threshold in a frame")
+            if st & _lib.VD_STAT_DET_OVERFLOW:
+                msgs.append(f"more than max_det={self.max_det} boxes survived NMS in a frame")
+            if st & _lib.VD_STAT_WORK_OVERFLOW:
+                msgs.append("compositing workspace too small for the boxes of a frame")
+            if st & _lib.VD_STAT_WATCHDOG:
+                msgs.append("device-side dependency wait timed out")
+            raise RuntimeError("libvdesens device status: " + "; ".join(msgs))
+
+    # debugging / tests: activations as NCHW fp32
+    def activation(self, name):
+        self.stream.synchronize()
+        if name == "x0":
+            return self.buf["x0"][:, :, 3:3 + self.W, :3].permute(0, 3, 1, 2).float()
+        return self.buf[name].permute(0, 3, 1, 2).float()
+
+    def head_tensors(self):
+        """(loc (B,A,4), cls logits (B,A,2), landms (B,A,10)) assembled from the fused head outputs in
+        the reference's anchor order (retinaface.py:140-142)."""
+        self.stream.synchronize()
+        locs, clss, ldms = [], [], []
+        for h in self.heads:
+            B, n, _ = h.shape
+            locs.append(h[:, :, 0:8].reshape(B, n * 2, 4))
+            clss.append(h[:, :, 8:12].reshape(B, n * 2, 2))
+            ldms.append(h[:, :, 12:32].reshape(B, n * 2, 10))
+        return torch.cat(locs, 1), torch.cat(clss, 1), torch.cat(ldms, 1)

@@ -1,0 +1,65 @@
+"""Weight packer: reference state_dict (.pth format of detect_face/face.py:52-56) -> BN-folded bf16
+K-major GEMM operands for conv_tcgen05.cu.
+
+Eval-mode BN (eps 1e-5) folds into the convolution:  w' = w * g/sqrt(v+eps),  b' = beta - mean * g/sqrt(v+eps)
+(SURVEY §8a epilogue kinds).  K order of the packed matrix is (r, s, cin), matching the TMA tap loop.
+"""
+import numpy as np
+import torch
+
+from . import arch
+
+
+def _fold(sd, c: arch.ConvSpec):
+    w = np.asarray(sd[c.wkey], np.float64)
+    if c.bnkey:
+        g = np.asarray(sd[c.bnkey + ".weight"], np.float64)
+        beta = np.asarray(sd[c.bnkey + ".bias"], np.float64)
+        mean = np.asarray(sd[c.bnkey + ".running_mean"], np.float64)
+        var = np.asarray(sd[c.bnkey + ".running_var"], np.float64)
+        scale = g / np.sqrt(var + arch.BN_EPS)
+        w = w * scale[:, None, None, None]
+        b = beta - mean * scale
+    else:
+        b = np.zeros(w.shape[0], np.float64)
+    if c.biaskey:
+        b = b + np.asarray(sd[c.biaskey], np.float64)
+    return w.astype(np.float32), b.astype(np.float32)
+
+
+def to_numpy_sd(sd):
+    out = {}
+    for k, v in sd.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k[7:] if k.startswith("module.") else k] = v
+    return out
+
+
+def pack_all(sd):
+    """Returns {layer name: (w_packed bf16 CPU tensor [Cout, K], bias fp32 CPU tensor [Cout])} for every
+    conv of the graph plus 'heads.{0,1,2}' (the three 1x1 heads of a level fused to one N=32 GEMM)."""
+    sd = to_numpy_sd(sd)
+    convs, _, _ = arch.build_graph()
+    packed = {}
+    for c in convs:
+        w, b = _fold(sd, c)
+        if c.name == "body.conv1":
+            # conv1 on the ingest layout: K = 7 filter rows x (8 taps x 8 channels); tap 7 and
+            # channels 3..7 are zero padding
+            wp = np.zeros((c.cout, 7, 8, 8), np.float32)
+            wp[:, :, :7, :3] = np.transpose(w, (0, 2, 3, 1))
+            mat = wp.reshape(c.cout, -1)
+        else:
+            mat = np.transpose(w, (0, 2, 3, 1)).reshape(c.cout, -1)
+        packed[c.name] = (torch.from_numpy(np.ascontiguousarray(mat)).to(torch.bfloat16),
+                          torch.from_numpy(b.copy()))
+    for lvl in range(3):
+        ws, bs = [], []
+        for hk in arch.head_keys(lvl):
+            ws.append(np.asarray(sd[hk + ".weight"], np.float32).reshape(-1, 256))
+            bs.append(np.asarray(sd[hk + ".bias"], np.float32))
+        mat = np.concatenate(ws, 0)
+        assert mat.shape == (arch.HEAD_ROWS, 256)
+        packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(torch.bfloat16), torch.from_numpy(np.concatenate(bs)))
+    return packed
