@@ -163,7 +163,7 @@ int vd_nms_batched(const float* cand, const int32_t* cand_count, int B, int cap,
 #define VD_MODE_MOSAIC 0
 #define VD_MODE_GAUSS 1
 #define VD_MAX_KSIZE 255
-#define VD_MAX_BOXES_PER_FRAME 1024
+#define VD_MAX_BOXES_PER_FRAME 4096
 
 /* cv::getGaussianKernel + 8.8 fixed point with error diffusion (cv2.GaussianBlur uint8 path);
  * taps_q8 [host] receives ksize values summing to 256. */

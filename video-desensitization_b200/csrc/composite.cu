@@ -105,71 +105,82 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
     const int nd = det_rows ? min(det_count[f], max_det) : 0;
     const int ne = ext_boxes ? min(ext_count[f], max_ext) : 0;
     const int nbx = min(nd + ne, maxb);
-    BoxMeta m;
-    memset(&m, 0, sizeof(m));
-    unsigned int items = 0;
-    unsigned long long scr = 0;
-    if (tid < nbx) {
-      int x1, y1, x2, y2;
-      if (tid < nd) {
-        // face.py:144-146: result[:, :4] *= [w, h, w, h] in float32; combine_detect.py:243: int() truncation
-        const float* r = det_rows + (static_cast<size_t>(f) * max_det + tid) * 16;
-        x1 = static_cast<int>(__fmul_rn(r[0], static_cast<float>(fr.w)));
-        y1 = static_cast<int>(__fmul_rn(r[1], static_cast<float>(fr.h)));
-        x2 = static_cast<int>(__fmul_rn(r[2], static_cast<float>(fr.w)));
-        y2 = static_cast<int>(__fmul_rn(r[3], static_cast<float>(fr.h)));
-      } else {
-        const int* e = ext_boxes + (static_cast<size_t>(f) * max_ext + (tid - nd)) * 4;
-        x1 = e[0]; y1 = e[1]; x2 = e[2]; y2 = e[3];
-      }
-      x1 = max(0, x1); y1 = max(0, y1); x2 = min(fr.w, x2); y2 = min(fr.h, y2);   // combine_detect.py:145-148
-      m.x1 = x1; m.y1 = y1; m.x2 = x2; m.y2 = y2;
-      if (x2 > x1 && y2 > y1) {                                                   // :150
-        const int bw = x2 - x1, bh = y2 - y1;
-        if (mode == VD_MODE_MOSAIC) {
-          m.sw = max(1, bw / mosaic_level);
-          m.sh = max(1, bh / mosaic_level);
-          m.tA = (m.sw * m.sh + MA_PIX - 1) / MA_PIX;
-          m.tB = ((bw + MB_W - 1) / MB_W) * ((bh + MB_H - 1) / MB_H);
-          scr = (static_cast<unsigned long long>(m.sw) * m.sh * 3 + 1) / 2;
+    unsigned int item_carry = 0;
+    unsigned long long scr_carry = 0;
+    // pass 1: metadata + prefix sums, 1024 boxes per chunk
+    for (int base = 0; base < maxb; base += 1024) {
+      const int k = base + tid;
+      BoxMeta m;
+      memset(&m, 0, sizeof(m));
+      unsigned int items = 0;
+      unsigned long long scr = 0;
+      if (k < nbx) {
+        int x1, y1, x2, y2;
+        if (k < nd) {
+          // face.py:144-146: result[:, :4] *= [w, h, w, h] in float32; combine_detect.py:243: int() truncation
+          const float* r = det_rows + (static_cast<size_t>(f) * max_det + k) * 16;
+          x1 = static_cast<int>(__fmul_rn(r[0], static_cast<float>(fr.w)));
+          y1 = static_cast<int>(__fmul_rn(r[1], static_cast<float>(fr.h)));
+          x2 = static_cast<int>(__fmul_rn(r[2], static_cast<float>(fr.w)));
+          y2 = static_cast<int>(__fmul_rn(r[3], static_cast<float>(fr.h)));
         } else {
-          m.tA = ((bw + GA_W - 1) / GA_W) * ((bh + GA_H - 1) / GA_H);
-          m.tB = ((bw + GB_W - 1) / GB_W) * ((bh + GB_H - 1) / GB_H);
-          scr = static_cast<unsigned long long>(bw) * bh * 3;
+          const int* e = ext_boxes + (static_cast<size_t>(f) * max_ext + (k - nd)) * 4;
+          x1 = e[0]; y1 = e[1]; x2 = e[2]; y2 = e[3];
         }
-        scr = (scr + 7) & ~7ull;
-        items = static_cast<unsigned int>(m.tA + m.tB);
+        x1 = max(0, x1); y1 = max(0, y1); x2 = min(fr.w, x2); y2 = min(fr.h, y2);   // combine_detect.py:145-148
+        m.x1 = x1; m.y1 = y1; m.x2 = x2; m.y2 = y2;
+        if (x2 > x1 && y2 > y1) {                                                   // :150
+          const int bw = x2 - x1, bh = y2 - y1;
+          if (mode == VD_MODE_MOSAIC) {
+            m.sw = max(1, bw / mosaic_level);
+            m.sh = max(1, bh / mosaic_level);
+            m.tA = (m.sw * m.sh + MA_PIX - 1) / MA_PIX;
+            m.tB = ((bw + MB_W - 1) / MB_W) * ((bh + MB_H - 1) / MB_H);
+            scr = (static_cast<unsigned long long>(m.sw) * m.sh * 3 + 1) / 2;
+          } else {
+            m.tA = ((bw + GA_W - 1) / GA_W) * ((bh + GA_H - 1) / GA_H);
+            m.tB = ((bw + GB_W - 1) / GB_W) * ((bh + GB_H - 1) / GB_H);
+            scr = static_cast<unsigned long long>(bw) * bh * 3;
+          }
+          scr = (scr + 7) & ~7ull;
+          items = static_cast<unsigned int>(m.tA + m.tB);
+        }
       }
-    }
-    // exclusive scan over boxes (Hillis-Steele in shared memory; <= 1024 boxes)
-    s_items[tid] = items;
-    s_scr[tid] = scr;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      unsigned int a = 0;
-      unsigned long long c = 0;
-      if (tid >= off) { a = s_items[tid - off]; c = s_scr[tid - off]; }
+      // inclusive scan over the chunk (Hillis-Steele in shared memory)
+      s_items[tid] = items;
+      s_scr[tid] = scr;
       __syncthreads();
-      s_items[tid] += a;
-      s_scr[tid] += c;
+      for (int off = 1; off < 1024; off <<= 1) {
+        unsigned int a = 0;
+        unsigned long long c = 0;
+        if (tid >= off) { a = s_items[tid - off]; c = s_scr[tid - off]; }
+        __syncthreads();
+        s_items[tid] += a;
+        s_scr[tid] += c;
+        __syncthreads();
+      }
+      if (k < maxb) {
+        m.item_base = item_carry + s_items[tid] - items;
+        m.scratch_off = scr_carry + s_scr[tid] - scr;
+        ws.meta[static_cast<size_t>(f) * maxb + k] = m;
+        ws.doneA[static_cast<size_t>(f) * maxb + k] = 0;
+        ws.doneB[static_cast<size_t>(f) * maxb + k] = 0;
+      }
+      item_carry += s_items[1023];
+      scr_carry += s_scr[1023];
       __syncthreads();
     }
-    const unsigned long long scr_total = s_scr[1023];
-    unsigned int frame_items = s_items[1023];
-    const bool overflow = scr_total > ws.scratch_elems;
-    if (overflow) frame_items = 0;
-    if (tid < maxb) {
-      m.item_base = s_items[tid] - items;
-      m.scratch_off = s_scr[tid] - scr;
-      if (overflow || tid >= nbx) { m.tA = 0; m.tB = 0; }
-      ws.meta[static_cast<size_t>(f) * maxb + tid] = m;
-      ws.doneA[static_cast<size_t>(f) * maxb + tid] = 0;
-      ws.doneB[static_cast<size_t>(f) * maxb + tid] = 0;
+    // pass 2: a frame whose boxes do not fit the scratch region is skipped entirely (status bit)
+    const bool overflow = scr_carry > ws.scratch_elems;
+    if (overflow) {
+      for (int k = tid; k < maxb; k += 1024) {
+        BoxMeta* mp = ws.meta + static_cast<size_t>(f) * maxb + k;
+        mp->tA = 0; mp->tB = 0; mp->item_base = 0;
+      }
     }
     if (tid == 0) {
-      if (overflow) atomicOr(status, VD_STAT_WORK_OVERFLOW);
-      if (nd + ne > maxb) atomicOr(status, VD_STAT_WORK_OVERFLOW);
-      s_total += frame_items;
+      if (overflow || nd + ne > maxb) atomicOr(status, VD_STAT_WORK_OVERFLOW);
+      s_total += overflow ? 0u : item_carry;
       ws.hdr->frame_prefix[f + 1] = s_total;
     }
     __syncthreads();

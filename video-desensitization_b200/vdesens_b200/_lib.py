@@ -11,7 +11,7 @@ VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0 = 
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
 VD_NMS_MAX_CAND = 8192
-VD_MAX_BOXES_PER_FRAME = 1024
+VD_MAX_BOXES_PER_FRAME = 4096
 
 
 class VdFrame(C.Structure):

@@ -26,7 +26,7 @@ def _ptr(t):
 
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
-                 cand_cap=4096, max_det=1024, max_ext=256, scratch_frames=8.0):
+                 cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.lib()

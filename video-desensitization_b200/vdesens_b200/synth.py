@@ -35,7 +35,7 @@ def synthetic_frame(h: int, w: int, seed: int) -> np.ndarray:
     g11 = grid[y0 + 1][:, x0 + 1]
     img = (g00 * (1 - fy) * (1 - fx) + g01 * (1 - fy) * fx + g10 * fy * (1 - fx) + g11 * fy * fx)
     img += rng.uniform(-6.0, 6.0, size=img.shape).astype(np.float32)
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def synthetic_clip(n: int, h: int, w: int, base_seed: int = 1000):
