@@ -128,7 +128,7 @@ def run_reference(args):
     from vdesens_b200 import synth
     threads = os.cpu_count() or 1
     sample = 2
-    sd_t = ro.to_torch_sd(synth.synthetic_state_dict(0, face_rate="r01"))
+    sd_t = ro.to_torch_sd(synth.synthetic_state_dict(0, face_rate="r001"))
     frames = [synth.synthetic_frame(H, W, 1000 + i) for i in range(sample)]
     plates = [synth.synthetic_boxes(N_PLATES, H, W, seed=50 + i) for i in range(sample)]
     for _ in range(args.warmup):
@@ -152,7 +152,7 @@ def workload_config(n_gpus):
     return {"workload": "BASELINE configs[1]: 1080p synthetic frames, batch 16 per GPU, RetinaFace-ResNet50 bf16 detect "
                         f"+ Gaussian blur k={KSIZE} over detected faces + {N_PLATES} plate boxes/frame",
             "batch_per_gpu": BATCH, "frame": [H, W, 3], "input_shape": [H, W, 3], "confidence": 0.5, "nms_iou": 0.4,
-            "weights": "seeded random init, BN calibrated, ~1% anchors above threshold",
+            "weights": "seeded random init, BN calibrated, ~0.1% of anchors above threshold (~90 faces/frame)",
             "l2": "inputs cycle through 3 distinct 100 MB batches; each step streams > 10 GB of activations (>> 126 MB L2)",
             "parallelism": f"frame-parallel x{n_gpus}, no collective"}
 
@@ -170,7 +170,7 @@ def run_ours(args):
     from vdesens_b200.pipeline import Anonymizer
 
     hbm_peak, tf_peak, peak_src = load_peaks()
-    sd = synth.synthetic_state_dict(0, face_rate="r01")
+    sd = synth.synthetic_state_dict(0, face_rate="r001")
     eng = DetectorEngine(sd, BATCH, H, W, device=dev, confidence=0.5, nms_iou=0.4)
     NB = 3                                   # distinct resident batches, cycled
     base = rank * 100000                     # every rank owns different frames (sharded stream)

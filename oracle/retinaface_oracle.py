@@ -267,3 +267,60 @@ def detect_images(sd, images, input_hw, confidence=0.5, nms_iou=0.45, return_row
             boxes = rr[:, :4].tolist()
         out.append((images[i].copy(), boxes))
     return (out, results) if return_rows else out
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 emulation of the device network (same packed weights, same rounding points, fp32 math):
+# separates "the CUDA pipeline computes the right function" from "bf16 differs from fp32".
+# ----------------------------------------------------------------------------------------------
+def forward_bf16_emulated(packed, x, capture=None):
+    """packed: vdesens_b200.weights.pack_all(sd) (BN-folded bf16 GEMM operands).  x: (B,3,H,W) fp32
+    mean-subtracted (exact integers).  Activations are rounded to bf16 where the device stores them."""
+    from vdesens_b200 import arch
+    convs, ops, _ = arch.build_graph()
+    cap = capture if capture is not None else {}
+
+    def bf(t):
+        return t.to(torch.bfloat16).float()
+
+    bufs = {"x0": x}
+    heads = [None, None, None]
+    with torch.no_grad():
+        for op in ops:
+            if op.kind == "maxpool":
+                bufs[op.dst] = F.max_pool2d(bufs[op.src], 3, 2, 1)
+            elif op.kind == "conv":
+                c = op.conv
+                wp, b = packed[c.name]
+                if c.name == "body.conv1":
+                    w = wp.float().view(c.cout, 7, 8, 8)[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()
+                else:
+                    w = wp.float().view(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
+                y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad)
+                if op.residual:
+                    y = y + bufs[op.residual]
+                if c.relu:
+                    y = F.relu(y)
+                if op.upsample_add:
+                    y = y + F.interpolate(bufs[op.upsample_add], size=y.shape[2:], mode="nearest")
+                y = bf(y)
+                if op.dst in bufs and (op.dst_coff or bufs[op.dst].shape[1] != c.cout):
+                    bufs[op.dst][:, op.dst_coff:op.dst_coff + c.cout] = y
+                elif op.dst.endswith(".out") and op.dst.startswith("ssh"):
+                    full = torch.zeros((y.shape[0], 256, y.shape[2], y.shape[3]))
+                    full[:, op.dst_coff:op.dst_coff + c.cout] = y
+                    bufs[op.dst] = full
+                else:
+                    bufs[op.dst] = y
+            elif op.kind == "heads":
+                wp, b = packed[f"heads.{op.level}"]
+                heads[op.level] = F.conv2d(bufs[op.src], wp.float().view(32, 256, 1, 1), b)
+        cap.update(bufs)
+        locs, clss, ldms = [], [], []
+        for h in heads:
+            hh = h.permute(0, 2, 3, 1).contiguous()
+            B = hh.shape[0]
+            locs.append(hh[..., 0:8].reshape(B, -1, 4))
+            clss.append(hh[..., 8:12].reshape(B, -1, 2))
+            ldms.append(hh[..., 12:32].reshape(B, -1, 10))
+    return torch.cat(locs, 1), torch.cat(clss, 1), torch.cat(ldms, 1)
