@@ -232,7 +232,11 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
   for (int i = tid; i <= B; i += kThreads) s_fprefix[i] = ws.hdr->frame_prefix[i];
   s_q[tid] = taps.q[tid];
   __syncthreads();
-  const unsigned int total = s_fprefix[B];
+  // tickets interleave the frames (ticket t -> frame t % B, item t / B) so the sequential box chains
+  // of all frames advance concurrently; inside a frame the (box, phase, tile) order is kept
+  unsigned int max_items = 0;
+  for (int i = 0; i < B; ++i) max_items = max(max_items, s_fprefix[i + 1] - s_fprefix[i]);
+  const unsigned int total = max_items * static_cast<unsigned int>(B);
   const int r = ksize >> 1;
 
   while (true) {
@@ -241,9 +245,9 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     __syncthreads();
     const unsigned int t = s_ticket;
     if (t >= total) break;
-    int f = 0;
-    while (s_fprefix[f + 1] <= t) ++f;
-    const unsigned int local = t - s_fprefix[f];
+    const int f = static_cast<int>(t % static_cast<unsigned int>(B));
+    const unsigned int local = t / static_cast<unsigned int>(B);
+    if (local >= s_fprefix[f + 1] - s_fprefix[f]) continue;      // this frame has fewer items
     const BoxMeta* fm = ws.meta + static_cast<size_t>(f) * maxb;
     // binary search: last box with item_base <= local and a non-empty item range containing local
     int lo = 0, hi = maxb - 1;

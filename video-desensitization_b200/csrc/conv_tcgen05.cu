@@ -14,10 +14,12 @@
 //   * weights [Cout][R*S*Cin] bf16 (BN folded) are the K-major B operand, 2-D TMA;
 //   * tcgen05.mma (M=128, N=BN, K=16) accumulates fp32 in TMEM; two accumulator buffers so the
 //     epilogue of tile i overlaps the MMAs of tile i+1;
-//   * epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> +bias -> (+residual) -> ReLU
-//     -> (+nearest-upsampled FPN tensor) -> bf16 (or fp32 for the head GEMM) -> global.
+//   * epilogue (8 warps, two per TMEM lane quarter): tcgen05.ld -> +bias -> (+residual, prefetched
+//     from global while the MMAs still run) -> ReLU -> (+nearest-upsampled FPN tensor) -> bf16 (or
+//     fp32 for the head GEMM) -> SWIZZLE_128B staging tile in shared memory -> TMA tile store
+//     (full 128-byte lines per pixel, clipped by the tensor map at the image borders).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 #include <cuda.h>
 #include <new>
 
@@ -50,10 +52,12 @@ struct ConvCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows*128B)
@@ -71,13 +75,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const ConvKParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sOut = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + Cfg::OUT_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -89,6 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -98,7 +104,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], 8);
       }
       fence_barrier_init();
     }
@@ -183,14 +189,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which 32 of the chunk's 64 columns this warp converts
     const int row = q * 32 + lane;
     const int tx_ = row % p.TW;
     const int ty_ = (row / p.TW) % p.TH;
     const int nb_ = row / (p.TW * p.TH);
+    const bool issuer = (threadIdx.x == 64);        // lane 0 of warp 2 issues the TMA stores
+    const bool f32out = (p.flags & VD_CONV_OUT_F32) != 0;
+    constexpr int NCHUNK = (BN >= 64) ? BN / 64 : 1;
+    const bool active = (BN >= 64) || (half == 0);  // BN == 32 (head GEMM): one 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m = tile / p.n_tiles;
@@ -208,17 +220,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int uy = min(y >> 1, p.up_H - 1), ux = min(x >> 1, p.up_W - 1);
         up_pix = (static_cast<size_t>(b) * p.up_H + uy) * p.up_W + ux;
       }
+      const bool has_res = (p.flags & VD_CONV_RESIDUAL) && valid && active;
+      const int ncol0 = n_tile * BN + half * 32;       // first output channel of this thread in chunk 0
+      uint4 rnext[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rnext[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (has_res) {                                   // residual of chunk 0: in flight while the MMAs run
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + ncol0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+      }
 
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int ch = 0; ch < NCHUNK; ++ch, ++chunk_ctr) {
+        const int n0 = ncol0 + ch * 64;
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c0), v);
-        tmem_ld_wait();
-        if (valid) {
-          const int n0 = n_tile * BN + c0;
-          float f[32];
+        if (active) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(acc * BN + ch * 64 + half * 32), v);
+        }
+        uint4 rcur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (has_res && ch + 1 < NCHUNK) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0 + 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+        }
+        float f[32];
+        if (active) {
+          tmem_ld_wait();
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -229,10 +262,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
           }
           if (p.flags & VD_CONV_RESIDUAL) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 rv = __ldg(rp + j);
+              const uint4 rv = rcur[j];
               f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
               f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
               f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
@@ -243,7 +275,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (p.flags & VD_CONV_UPADD) {
+          if ((p.flags & VD_CONV_UPADD) && valid) {
             const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * p.Cout + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -254,12 +286,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
             }
           }
-          if (p.flags & VD_CONV_OUT_F32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.dst_C + p.dst_coff + n0);
+        }
+        // staging tile `sbuf` is free once the TMA store issued two chunks ago has read it
+        uint8_t* sbuf = sOut + (chunk_ctr & 1u) * (128 * 128);
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, kEpiThreads);
+        if (active) {
+          // SWIZZLE_128B staging: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+          uint8_t* srow = sbuf + row * 128;
+          if (f32out) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + pix * p.dst_C + p.dst_coff + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -267,9 +307,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              op[j] = o;
+              *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = o;
             }
           }
+        }
+        fence_proxy_async_smem();              // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1, kEpiThreads);
+        if (issuer) {
+          const int cch = f32out ? 0 : (p.dst_coff + n_tile * BN + ch * 64);
+          tma_store_4d(&tmY, sbuf, cch, tx * p.TW, ty * p.TH, tb * p.NB);
+          tma_store_commit();
         }
       }
       tcgen05_fence_before();
@@ -278,6 +325,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (issuer) tma_store_wait_all<0>();       // all output bytes written before the CTA retires
   }
 
   // teardown: everyone done with TMEM before the allocating warp frees it
@@ -315,6 +363,7 @@ EncodeTiledFn get_encode_fn() {
 struct vd_conv_plan {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmY;
   ConvKParams kp;
   int BN;
   int grid;
@@ -463,6 +512,36 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     delete pl;
     return VD_ERR_CUDA;
   }
+  // ---- Y: output tile store (box = one 128-byte line per pixel of the M tile) ----
+  {
+    const bool f32 = (d->flags & VD_CONV_OUT_F32) != 0;
+    const int esz = f32 ? 4 : 2;
+    if (f32 && (d->dst_C != 32 || d->dst_coff != 0 || BN != 32)) {
+      vd_set_error("vd_conv_plan_create: fp32 output is implemented for the 32-channel head GEMM only");
+      delete pl;
+      return VD_ERR_UNSUPPORTED;
+    }
+    if (!f32 && (BN < 64 || d->dst_coff % 64 != 0)) {
+      vd_set_error("vd_conv_plan_create: bf16 output needs Cout >= 64 and a 64-aligned channel offset");
+      delete pl;
+      return VD_ERR_UNSUPPORTED;
+    }
+    cuuint64_t ydim[4] = {static_cast<cuuint64_t>(d->dst_C), static_cast<cuuint64_t>(d->Wout),
+                          static_cast<cuuint64_t>(d->Hout), static_cast<cuuint64_t>(d->B)};
+    cuuint64_t ystr[3] = {static_cast<cuuint64_t>(d->dst_C) * esz, static_cast<cuuint64_t>(d->dst_C) * esz * d->Wout,
+                          static_cast<cuuint64_t>(d->dst_C) * esz * d->Wout * d->Hout};
+    cuuint32_t ybox[4] = {static_cast<cuuint32_t>(f32 ? 32 : 64), static_cast<cuuint32_t>(k.TW),
+                          static_cast<cuuint32_t>(k.TH), static_cast<cuuint32_t>(k.NB)};
+    cuuint32_t yes[4] = {1, 1, 1, 1};
+    r = enc(&pl->tmY, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->y, ydim, ystr,
+            ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vd_set_error("cuTensorMapEncodeTiled(Y) failed: CUresult %d", (int)r);
+      delete pl;
+      return VD_ERR_CUDA;
+    }
+  }
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
@@ -496,7 +575,7 @@ static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_igemm_kernel<BN><<<pl->grid, kThreads, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->kp);
+  conv_igemm_kernel<BN><<<pl->grid, kThreads, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
