@@ -1,0 +1,141 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol (no compute calls),
+header/binding consistency, graph/weights bookkeeping, sharding + ordered gather over gloo (world 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vdesens_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vdesens.h")).read()
+    declared = set(re.findall(r"\b(vd_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vd_frame", "vd_status"}
+    lib = _lib.lib()                       # raises if the .so is missing: there is no fallback
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libvdesens.so does not export {name}"
+    assert set(_lib.EXPORTED) == declared, (set(_lib.EXPORTED) ^ declared)
+    assert lib.vd_abi_version() == 1
+    assert b"sm_100a" in lib.vd_build_info()
+
+
+def test_host_only_entry_points():
+    from vdesens_b200 import _lib
+    from oracle import cv_oracle as co
+    lib = _lib.lib()
+    assert lib.vd_x0_pitch(1920) == 1928 and lib.vd_x0_pitch(7) == 16 and lib.vd_x0_pitch(640) % 8 == 0
+    for k, s in [(1, 0), (3, 0), (7, 0), (9, 0), (31, 0), (99, 0), (15, 2.5), (255, 0)]:
+        assert _lib.gaussian_taps_q8(k, s) == co.gaussian_taps_q8(k, s).tolist()
+    assert lib.vd_gaussian_taps_q8(4, 0.0, (ctypes.c_uint16 * 256)()) != 0      # even ksize rejected
+    assert "ksize" in _lib.last_error()
+    assert lib.vd_nms_workspace_bytes(16, 4096) > 16 * 4096 * 64 * 8
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.vd_conv_plan_create(None, None), "vd_conv_plan_create")
+
+
+def test_graph_bookkeeping():
+    from vdesens_b200 import arch, synth, weights
+    convs, ops, bufs = arch.build_graph()
+    assert len(convs) == 73 and sum(1 for o in ops if o.kind == "heads") == 3        # 73 + 9 head convs = 82
+    spec = arch.state_dict_spec()
+    assert len(spec) == 456
+    assert sum(int(np.prod(s)) for _, s, k in spec if k not in ("bn_mean", "bn_var", "bn_count")) == 27293600
+    # every buffer is written before it is read
+    written = {"x0"}
+    for o in ops:
+        assert o.src in written, o
+        for extra in (o.residual, o.upsample_add):
+            assert not extra or extra in written
+        written.add(o.dst)
+    flops = 0
+    for o in ops:
+        if o.kind == "conv":
+            h, w = arch.feature_hw(1080, 1920, next(b.stride for b in bufs if b.name == o.dst))
+            flops += 2 * o.conv.cin * o.conv.cout * o.conv.k ** 2 * h * w
+    for lvl, s in enumerate((8, 16, 32)):
+        h, w = arch.feature_hw(1080, 1920, s)
+        flops += 2 * 256 * 32 * h * w
+    assert abs(flops / 1e9 - 449.71) < 0.2
+    sd = synth.synthetic_state_dict(0)
+    packed = weights.pack_all(sd)
+    assert packed["body.conv1"][0].shape == (64, 448) and packed["heads.1"][0].shape == (32, 256)
+    w0 = packed["body.conv1"][0].float().view(64, 7, 8, 8)
+    assert float(w0[:, :, 7].abs().max()) == 0 and float(w0[..., 3:].abs().max()) == 0
+    # BN fold: folded conv == conv + BN on a random input (fp32 check of the algebra, not of the device)
+    c = next(c for c in convs if c.name == "body.layer2.0.conv2")
+    w, b = weights._fold(weights.to_numpy_sd(sd), c)
+    x = torch.randn(1, c.cin, 9, 9)
+    y = torch.nn.functional.conv2d(x, torch.from_numpy(sd[c.wkey]), None, c.stride, c.pad)
+    y = torch.nn.functional.batch_norm(y, torch.from_numpy(sd[c.bnkey + ".running_mean"]),
+                                       torch.from_numpy(sd[c.bnkey + ".running_var"]),
+                                       torch.from_numpy(sd[c.bnkey + ".weight"]), torch.from_numpy(sd[c.bnkey + ".bias"]),
+                                       False, 0.0, 1e-5)
+    y2 = torch.nn.functional.conv2d(x, torch.from_numpy(w), torch.from_numpy(b), c.stride, c.pad)
+    assert torch.allclose(y, y2, atol=1e-4, rtol=1e-4)
+
+
+def test_anchor_table_matches_oracle():
+    from detect_face.utils.anchors import Anchors
+    from detect_face.utils.config import cfg_re50
+    from oracle import retinaface_oracle as ro
+    for h, w in [(96, 128), (135, 241), (640, 640)]:
+        assert torch.equal(Anchors(cfg_re50, image_size=[h, w]).get_anchors(), ro.anchors(h, w))
+
+
+def test_shard_ranges_cover_stream():
+    from vdesens_b200 import shard
+    for n, world, batch in [(8192, 8, 16), (100, 3, 16), (5, 4, 2), (0, 2, 4), (17, 2, 1)]:
+        seen = []
+        for r in range(world):
+            s, e = shard.shard_range(n, r, world, batch)
+            assert s <= e and (s % batch == 0 or s == n)
+            seen += list(range(s, e))
+        assert seen == list(range(n))
+
+
+def test_no_cpu_fallback_without_device():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from detect_face.face import Retinaface
+    with pytest.raises(RuntimeError):
+        Retinaface(state_dict={}, input_shape=[64, 64, 3])
+    import combine_detect
+    with pytest.raises(RuntimeError):
+        combine_detect.mosaic_rectangle_region_single(np.zeros((8, 8, 3), np.uint8), 0, 0, 4, 4)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "video-desensitization_b200"))
+import torch.distributed as dist
+from vdesens_b200 import shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 37
+s, e = shard.shard_range(n, rank, world, batch=4)
+local = [{"frame": i, "boxes": [[i, i, i + 1, i + 1]] * (i % 3)} for i in range(s, e)]
+out = shard.gather_ordered(local, s)
+if rank == 0:
+    assert [o["frame"] for o in out] == list(range(n)), out
+    print("GATHER_OK", len(out))
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_ordered_gather_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GATHER_OK 37" in r.stdout
