@@ -85,6 +85,9 @@ CONV_CASES = [
     ("3x3_512_small",   4,  3,   4, 512,  512, 3, 1, 1, True, False, False),
     ("1x1_upadd",       2, 17,  31, 1024, 256, 1, 1, 0, True, False, True),
     ("3x3_big_m",       1, 68, 120,  64,   64, 3, 1, 1, True, False, False),      # many tiles per CTA
+    ("1x1_res_bn64",    2, 24,  32, 128,   64, 1, 1, 0, True, True, False),       # residual ring, BN = 64
+    ("3x3_res_bn128",   2, 17,  31,  64,  128, 3, 1, 1, True, True, False),       # residual ring, BN = 128
+    ("1x1_res_many",    1, 68, 120, 128,  512, 1, 1, 0, True, True, False),       # residual ring wraps many times
 ]
 
 

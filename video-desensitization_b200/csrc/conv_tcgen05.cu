@@ -44,19 +44,24 @@ struct ConvKParams {
   void* y;
 };
 
-template <int BN>
+// RES = the layer adds a residual tensor: it is prefetched by a dedicated TMA warp into a ring of
+// RES_SLOTS 16 KB tiles (one per 64-channel chunk), paid for with fewer operand stages.
+template <int BN, bool RES>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = RES ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int RES_SLOTS = 3;
+  static constexpr int RES_BYTES = RES ? RES_SLOTS * 128 * 128 : 0;
+  static constexpr int BIAS_BYTES = 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = RES ? 352 : 320;                             // +1 warp: residual producer
 };
 
-constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -72,21 +77,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool RES>
+__global__ void __launch_bounds__((ConvCfg<BN, RES>::THREADS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const ConvKParams p) {
-  using Cfg = ConvCfg<BN>;
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                  const ConvKParams p) {
+  using Cfg = ConvCfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sOut = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + Cfg::OUT_BYTES);
+  uint8_t* sRes = sOut + Cfg::OUT_BYTES;
+  float* sBias = reinterpret_cast<float*>(sRes + Cfg::RES_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;
+  uint64_t* rempty = rfull + Cfg::RES_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + Cfg::RES_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,6 +105,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
+    if (RES) tma_prefetch_desc(&tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -105,6 +116,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8);
+      }
+      for (int i = 0; i < Cfg::RES_SLOTS; ++i) {
+        mbar_init(&rfull[i], 1);
+        mbar_init(&rempty[i], 8);
       }
       fence_barrier_init();
     }
@@ -188,6 +203,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if (RES && warp == 10) {
+    // ===================== residual producer =====================
+    if (lane == 0) {
+      constexpr int NCHUNK_R = (BN >= 64) ? BN / 64 : 1;
+      int slot = 0;
+      uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tb = m / p.tiles_y;
+        for (int ch = 0; ch < NCHUNK_R; ++ch) {
+          mbar_wait(&rempty[slot], rphase ^ 1u);
+          mbar_expect_tx(&rfull[slot], static_cast<uint32_t>(p.a_bytes));
+          tma_load_4d(sRes + slot * (128 * 128), &tmR, &rfull[slot], n_tile * BN + ch * 64, tx * p.TW, ty * p.TH,
+                      tb * p.NB);
+          if (++slot == Cfg::RES_SLOTS) {
+            slot = 0;
+            rphase ^= 1u;
+          }
+        }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -203,6 +243,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
+    int rslot = 0;
+    uint32_t rphase = 0;
+    int bias_tile = -1;
+    const int etid = threadIdx.x - 64;               // 0..255 inside the epilogue group
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m = tile / p.n_tiles;
@@ -214,21 +258,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int y = ty * p.TH + ty_;
       const int b = tb * p.NB + nb_;
       const bool valid = (row < p.rows_used) && (x < p.Wout) && (y < p.Hout) && (b < p.B);
-      const size_t pix = (static_cast<size_t>(b) * p.Hout + y) * p.Wout + x;
       size_t up_pix = 0;
       if (p.flags & VD_CONV_UPADD) {
         const int uy = min(y >> 1, p.up_H - 1), ux = min(x >> 1, p.up_W - 1);
         up_pix = (static_cast<size_t>(b) * p.up_H + uy) * p.up_W + ux;
       }
-      const bool has_res = (p.flags & VD_CONV_RESIDUAL) && valid && active;
       const int ncol0 = n_tile * BN + half * 32;       // first output channel of this thread in chunk 0
-      uint4 rnext[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rnext[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (has_res) {                                   // residual of chunk 0: in flight while the MMAs run
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + ncol0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+      if (n_tile != bias_tile) {                       // folded-BN bias of this N tile -> shared memory
+        named_bar_sync(1, kEpiThreads);
+        if (etid < BN) sBias[etid] = __ldg(p.bias + n_tile * BN + etid);
+        named_bar_sync(1, kEpiThreads);
+        bias_tile = n_tile;
       }
 
       mbar_wait(&tfull[acc], acc_phase);
@@ -242,26 +282,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             static_cast<uint32_t>(acc * BN + ch * 64 + half * 32), v);
         }
         uint4 rcur[4];
+        if (RES) {
+          // residual chunk staged by the residual-producer warp (SWIZZLE_128B tile, same geometry as the output)
+          mbar_wait(&rfull[rslot], rphase);
+          const uint8_t* rrow = sRes + rslot * (128 * 128) + row * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-        if (has_res && ch + 1 < NCHUNK) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0 + 64);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+          for (int j = 0; j < 4; ++j)
+            rcur[j] = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rempty[rslot]);
+          if (++rslot == Cfg::RES_SLOTS) {
+            rslot = 0;
+            rphase ^= 1u;
+          }
         }
         float f[32];
         if (active) {
           tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+          const float4* bp = reinterpret_cast<const float4*>(sBias + ch * 64 + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(bp + j);
+            const float4 bv = bp[j];
             f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
             f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
             f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
             f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
           }
-          if (p.flags & VD_CONV_RESIDUAL) {
+          if (RES) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 rv = rcur[j];
@@ -364,6 +411,7 @@ struct vd_conv_plan {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmY;
+  CUtensorMap tmR;
   ConvKParams kp;
   int BN;
   int grid;
@@ -542,6 +590,30 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
       return VD_ERR_CUDA;
     }
   }
+  // ---- R: residual tile load (same tile geometry as the output) ----
+  pl->tmR = pl->tmY;
+  if (d->flags & VD_CONV_RESIDUAL) {
+    if ((reinterpret_cast<uintptr_t>(d->residual) & 15) != 0 || (d->flags & VD_CONV_OUT_F32)) {
+      vd_set_error("vd_conv_plan_create: residual must be 16-byte aligned bf16");
+      delete pl;
+      return VD_ERR_INVALID;
+    }
+    cuuint64_t rdim[4] = {static_cast<cuuint64_t>(d->Cout), static_cast<cuuint64_t>(d->Wout),
+                          static_cast<cuuint64_t>(d->Hout), static_cast<cuuint64_t>(d->B)};
+    cuuint64_t rstr[3] = {static_cast<cuuint64_t>(d->Cout) * 2, static_cast<cuuint64_t>(d->Cout) * 2 * d->Wout,
+                          static_cast<cuuint64_t>(d->Cout) * 2 * d->Wout * d->Hout};
+    cuuint32_t rbox[4] = {64, static_cast<cuuint32_t>(k.TW), static_cast<cuuint32_t>(k.TH),
+                          static_cast<cuuint32_t>(k.NB)};
+    cuuint32_t res1[4] = {1, 1, 1, 1};
+    r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->residual), rdim, rstr, rbox, res1,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vd_set_error("cuTensorMapEncodeTiled(R) failed: CUresult %d", (int)r);
+      delete pl;
+      return VD_ERR_CUDA;
+    }
+  }
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
@@ -566,16 +638,18 @@ extern "C" int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, i
   return VD_OK;
 }
 
-template <int BN>
+template <int BN, bool RES>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, RES>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_igemm_kernel<BN><<<pl->grid, kThreads, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->kp);
+  conv_igemm_kernel<BN, RES><<<pl->grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
+                                                                               pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
@@ -583,11 +657,12 @@ static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
 extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
   VD_REQUIRE(plan, "vd_conv_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool res = (plan->kp.flags & VD_CONV_RESIDUAL) != 0;
   switch (plan->BN) {
-    case 32: return launch_conv<32>(plan, st);
-    case 64: return launch_conv<64>(plan, st);
-    case 128: return launch_conv<128>(plan, st);
-    case 256: return launch_conv<256>(plan, st);
+    case 32: return launch_conv<32, false>(plan, st);
+    case 64: return res ? launch_conv<64, true>(plan, st) : launch_conv<64, false>(plan, st);
+    case 128: return res ? launch_conv<128, true>(plan, st) : launch_conv<128, false>(plan, st);
+    case 256: return res ? launch_conv<256, true>(plan, st) : launch_conv<256, false>(plan, st);
   }
   vd_set_error("vd_conv_run: bad BN");
   return VD_ERR_UNSUPPORTED;
