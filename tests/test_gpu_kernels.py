@@ -426,3 +426,32 @@ def test_facade_detect_images_and_frame_loop(sd_np):
     assert np.array_equal(g, co.gauss_box(img, -5, 20, 90, 500, 31))
     with pytest.raises(ValueError):
         Retinaface(state_dict=sd_np, input_shape=[160, 224, 3], letterbox_image=False).detect_images(frames)
+
+
+def test_streaming_pipeline_matches_oracle_compositing(sd_np):
+    """the pipelined public path (double-buffered H2D / compute / D2H): results come back in order,
+    frames are anonymised exactly as the oracle does with the boxes the detector returned, and the
+    input buffers are untouched."""
+    from vdesens_b200.engine import DetectorEngine
+    from vdesens_b200.pipeline import Anonymizer, StreamingAnonymizer
+    H, W, B = 160, 224, 2
+    eng = DetectorEngine(sd_np, B, H, W, device=DEV, confidence=0.5, nms_iou=0.4)
+    batches = [[synth.synthetic_frame(H, W, 500 + 10 * k + i) for i in range(B)] for k in range(5)]
+    batches[-1] = batches[-1][:1]                                   # ragged tail batch
+    plates = [[synth.synthetic_boxes(2, H, W, seed=900 + 10 * k + i, min_size=8, max_size=60) for i in range(len(b))]
+              for k, b in enumerate(batches)]
+    pinned = [torch.from_numpy(np.stack(b)).pin_memory() for b in batches]
+    keep = [p.clone() for p in pinned]
+    sa = StreamingAnonymizer(eng, "gauss", ksize=15)
+    got = [(o.numpy().copy() if isinstance(o, torch.Tensor) else o.copy(), bx)
+           for o, bx in sa.run(pinned, plates)]
+    assert len(got) == 5
+    ref = Anonymizer(eng, "gauss", ksize=15)
+    for k, (out, boxes) in enumerate(got):
+        assert torch.equal(pinned[k], keep[k])
+        assert out.shape[0] == len(batches[k])
+        out2, boxes2 = ref.process_batch(batches[k], plates[k])
+        assert boxes == boxes2 and np.array_equal(out, out2)
+        for i in range(len(batches[k])):
+            allb = [tuple(int(v) for v in b) for b in boxes[i]] + plates[k][i]
+            assert np.array_equal(out[i], co.composite(batches[k][i], allb, "gauss", ksize=15)), (k, i)

@@ -197,6 +197,31 @@ class DetectorEngine:
         self.identity = identity
         return identity
 
+    def frame_records(self, frames_dev):
+        """(desc (B,6) int32 device tensor of vd_frame_t records, unlb (B,4) fp32 device tensor, identity)
+        for a resident frame tensor/list — built once per buffer and re-bound with bind_frames_async."""
+        self.set_frames(frames_dev)
+        self.stream.synchronize()
+        return self.frame_desc.clone(), self.unlb.clone(), self.identity
+
+    def bind_frames_async(self, desc_dev, unlb_dev, identity, shapes=None):
+        """stream-ordered switch of the frame set (device-to-device copies of the small records)."""
+        with torch.cuda.stream(self.stream):
+            self.frame_desc.copy_(desc_dev, non_blocking=True)
+            self.unlb.copy_(unlb_dev, non_blocking=True)
+        self.identity = identity
+
+    def upload_ext_async(self, eb_pinned, ec_pinned):
+        with torch.cuda.stream(self.stream):
+            self.ext_boxes.copy_(eb_pinned, non_blocking=True)
+            self.ext_count.copy_(ec_pinned, non_blocking=True)
+
+    def download_results_async(self, rows_host, count_host, status_host):
+        with torch.cuda.stream(self.stream):
+            rows_host.copy_(self.out_rows, non_blocking=True)
+            count_host.copy_(self.out_count, non_blocking=True)
+            status_host.copy_(self.status, non_blocking=True)
+
     # ------------------------------------------------------------------------------------------
     def enqueue_ingest(self):
         s = C.c_void_p(self.stream.cuda_stream)

@@ -57,3 +57,121 @@ class Anonymizer:
             r *= scale
             boxes.append(r.tolist())
         return out, boxes
+
+
+class _Slot:
+    """one in-flight batch of the pipelined path: pinned staging, resident frames, result mirrors"""
+
+    def __init__(self, eng, h, w):
+        B, dev = eng.B, eng.device
+        self.pin_in = torch.empty((B, h, w, 3), dtype=torch.uint8).pin_memory()
+        self.pin_out = torch.empty((B, h, w, 3), dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev)
+        self.desc, self.unlb, self.identity = eng.frame_records(self.dev)
+        self.eb = torch.zeros((B, eng.max_ext, 4), dtype=torch.int32).pin_memory()
+        self.ec = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.rows = torch.zeros((B, eng.max_det, 16), dtype=torch.float32).pin_memory()
+        self.counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.status = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.ev_in = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.ev_out = torch.cuda.Event()
+        self.n = 0
+        self.busy = False
+
+
+class StreamingAnonymizer:
+    """Pipelined detect + anonymise over a stream of equally sized batches on one GPU: the H2D copy of
+    batch i+1 and the D2H copy of batch i-1 run on their own streams while batch i computes, so the
+    end-to-end rate approaches the device rate (PCIe moves 2 x 100 MB per 16-frame 1080p batch).
+    Results are yielded strictly in input order."""
+
+    def __init__(self, engine: DetectorEngine, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, depth=2):
+        self.eng = engine
+        self.mode, self.mosaic_level, self.ksize, self.sigma = mode, int(mosaic_level), int(ksize), float(sigma)
+        self.depth = max(2, int(depth))
+        self.slots = None
+        self.s_in = torch.cuda.Stream(device=engine.device)
+        self.s_out = torch.cuda.Stream(device=engine.device)
+
+    def _ensure(self, h, w):
+        if self.slots is None or tuple(self.slots[0].dev.shape[1:3]) != (h, w):
+            self.slots = [_Slot(self.eng, h, w) for _ in range(self.depth)]
+
+    def _submit(self, slot, batch, ext):
+        eng = self.eng
+        if isinstance(batch, torch.Tensor):                       # (n,h,w,3) uint8, ideally pinned
+            n = batch.shape[0]
+            src = batch if n == eng.B else None
+            if src is None:
+                slot.pin_in[:n].copy_(batch)
+                slot.pin_in[n:] = slot.pin_in[n - 1]
+                src = slot.pin_in
+        else:                                                     # list of numpy frames
+            n = len(batch)
+            pi = slot.pin_in.numpy()
+            for i in range(eng.B):
+                pi[i] = batch[min(i, n - 1)]
+            src = slot.pin_in
+        slot.n = n
+        eb, ec = slot.eb.numpy(), slot.ec.numpy()
+        ec[:] = 0
+        for i, bl in enumerate(ext or []):
+            if len(bl) > eng.max_ext:
+                raise RuntimeError(f"{len(bl)} external boxes exceed max_ext={eng.max_ext}")
+            ec[i] = len(bl)
+            for j, b in enumerate(bl):
+                eb[i, j] = [int(v) for v in b]
+        with torch.cuda.stream(self.s_in):
+            slot.dev.copy_(src, non_blocking=True)                # H2D
+            slot.ev_in.record(self.s_in)
+        eng.stream.wait_event(slot.ev_in)
+        eng.bind_frames_async(slot.desc, slot.unlb, slot.identity)
+        eng.upload_ext_async(slot.eb, slot.ec)
+        eng.forward()
+        eng.enqueue_composite(self.mode, self.mosaic_level, self.ksize, self.sigma)
+        eng.download_results_async(slot.rows, slot.counts, slot.status)
+        slot.ev_done.record(eng.stream)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot.ev_done)
+            slot.pin_out.copy_(slot.dev, non_blocking=True)       # D2H of the processed frames
+            slot.ev_out.record(self.s_out)
+        # the next H2D into this slot must not overtake this D2H
+        self.s_in.wait_event(slot.ev_out)
+        slot.busy = True
+
+    def _collect(self, slot, copy_out):
+        slot.ev_out.synchronize()
+        slot.busy = False
+        self.eng.check_status(int(slot.status[0]))
+        n = slot.n
+        h, w = slot.dev.shape[1:3]
+        rows, counts = slot.rows.numpy(), slot.counts.numpy()
+        scale = np.array([w, h, w, h], np.float32)
+        boxes = []
+        for i in range(n):
+            r = rows[i, :counts[i], :4].copy()
+            r *= scale
+            boxes.append(r.tolist())
+        out = slot.pin_out[:n]
+        return (out.numpy().copy() if copy_out else out), boxes
+
+    def run(self, batches, ext_boxes=None, copy_out=False):
+        """batches: iterable of batches — a pinned uint8 tensor (n,h,w,3) (zero extra host copies) or a
+        list of numpy frames.  ext_boxes: optional iterable aligned with `batches` of per-frame box lists.
+        Yields (processed frames, face boxes per frame) in input order.  With copy_out=False the frames
+        are a view of a pinned buffer that stays valid until `depth` more batches have been yielded."""
+        ext_iter = iter(ext_boxes) if ext_boxes is not None else None
+        pending = []
+        k = 0
+        for batch in batches:
+            h, w = (batch.shape[1:3] if isinstance(batch, torch.Tensor) else batch[0].shape[:2])
+            self._ensure(int(h), int(w))
+            slot = self.slots[k % self.depth]
+            if slot.busy:                                         # oldest in-flight batch owns this slot
+                yield self._collect(pending.pop(0), copy_out)
+            self._submit(slot, batch, next(ext_iter) if ext_iter is not None else None)
+            pending.append(slot)
+            k += 1
+        while pending:
+            yield self._collect(pending.pop(0), copy_out)
