@@ -282,6 +282,31 @@ def test_composite_random_overlapping(ops, mode, ksize):
         assert np.array_equal(got, want[i]), f"frame {i}: {(got != want[i]).sum()} bytes differ"
 
 
+@pytest.mark.parametrize("mode,ksize", [("mosaic", 0), ("gauss", 31), ("gauss", 99)])
+def test_composite_large_overlapping_boxes(ops, mode, ksize):
+    """big boxes that overlap each other and contain small ones: exercises the per-tile dependency
+    tracking (A/B tiles of different boxes in flight together) and the fused small-box path."""
+    H, W = 540, 960
+    frames = [synth.synthetic_frame(H, W, 700 + i) for i in range(2)]
+    boxes = []
+    for i in range(2):
+        big = synth.synthetic_boxes(10, H, W, seed=70 + i, min_size=150, max_size=420)
+        small = synth.synthetic_boxes(40, H, W, seed=80 + i, min_size=6, max_size=70)
+        thin = [(100, -20, 107, 2000), (-30, 300, 3000, 309)]
+        mixed = []
+        for j in range(40):
+            mixed.append(small[j])
+            if j % 4 == 0:
+                mixed.append(big[j // 4])
+        boxes.append(mixed + thin)
+    want = [co.composite(f, b, mode, 8, ksize) for f, b in zip(frames, boxes)]
+    dfr = _dev_frames([f.copy() for f in frames])
+    ops.composite(dfr, boxes, mode, mosaic_level=8, ksize=max(ksize, 1))
+    for i in range(2):
+        got = dfr[i].cpu().numpy()
+        assert np.array_equal(got, want[i]), f"frame {i}: {(got != want[i]).sum()} bytes differ"
+
+
 def test_gaussian_taps_match_oracle():
     from vdesens_b200 import _lib
     for k, s in [(3, 0), (5, 0), (7, 0), (9, 0), (15, 2.5), (31, 0), (51, 0), (99, 0), (31, 30.0), (255, 0)]:

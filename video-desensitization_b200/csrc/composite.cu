@@ -10,15 +10,21 @@
 // (v + 32768) >> 16, BORDER_REFLECT_101 inside the ROI).
 //
 // Semantics kept: boxes are truncated toward zero, clipped to the frame, skipped when empty, and
-// applied ONE AFTER ANOTHER — a later box reads the pixels earlier boxes wrote.  Parallelism comes
-// from a ticket-ordered persistent kernel: every box contributes "phase A" tiles (frame -> scratch:
-// mosaic = gather the down-sampled image, Gaussian = horizontal pass) and "phase B" tiles (scratch
-// -> frame: mosaic = expand, Gaussian = vertical pass).  Tickets are handed out by an atomic in
-// (frame, box, phase, tile) order; a tile waits until the phase-B tiles of every EARLIER OVERLAPPING
-// box (phase A) or the phase-A tiles of its own box (phase B) are done.  Dependencies only point to
-// smaller tickets, which are always already running or finished, so the wait cannot deadlock; it is
-// also bounded (watchdog bit in `status`).  Frame and scratch reads use ld.global.cg because other
-// SMs rewrite those bytes during the kernel (L1 is not coherent).
+// applied ONE AFTER ANOTHER — a later box reads the pixels earlier boxes wrote.
+//
+// Parallel schedule.  Every box contributes work items in a fixed order: "A" tiles (frame -> scratch:
+// Gaussian horizontal pass / mosaic down-sample gather), then "B" tiles (scratch -> frame: vertical
+// pass / mosaic expand); a Gaussian box of at most FUSE_MAX_PX pixels is ONE fused item that runs
+// both passes in shared memory.  A persistent grid takes tickets from an atomic counter; ticket t
+// is item t / B of frame t % B, so the box chains of all frames advance together.  Dependencies are
+// tracked PER TILE with one flag per item:
+//   * an A (or fused) tile waits for the B/fused tiles of EARLIER boxes whose write rectangle
+//     intersects the rectangle it reads;
+//   * a B tile waits for the A tiles of its own box that produce its scratch rows (+-radius) and for
+//     the A tiles that still have to read the frame pixels it is about to overwrite.
+// Every dependency is an item with a smaller index in the same frame, hence a smaller ticket, hence
+// already running or finished: the waits cannot deadlock (and are bounded by a watchdog bit).
+// Frame and scratch reads use ld.global.cg because other SMs rewrite those bytes during the kernel.
 #include "common.cuh"
 
 namespace {
@@ -26,15 +32,18 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int MA_PIX = 256;               // mosaic phase A: small pixels per tile
 constexpr int MB_W = 64, MB_H = 16;       // mosaic phase B tile
-constexpr int GA_W = 128, GA_H = 8;       // Gaussian phase A tile (horizontal pass)
-constexpr int GB_W = 32, GB_H = 32;       // Gaussian phase B tile (vertical pass)
+constexpr int GA_W = 128, GA_H = 8;       // Gaussian phase A tile (horizontal pass), pixels
+constexpr int GB_E = 64, GB_H = 64;       // Gaussian phase B tile (vertical pass): 64 flat u16 elements x 64 rows
+constexpr int FUSE_MAX_PX = 2048;         // fused Gaussian box: 3 B (u8) + 6 B (u16) per pixel in smem (18 KB)
+constexpr int kMaxDynSmem = 64 * 1024;
+constexpr int KW_MAX = 32;                // dp4a fast path: ceil((ksize + 3) / 4) <= KW_MAX  (ksize <= 125)
 
 struct BoxMeta {
   int x1, y1, x2, y2;      // clipped; empty boxes have tA = tB = 0
-  int tA, tB;
+  int tA, tB;              // fused box: tA = 1, tB = 0
   int sw, sh;              // mosaic: down-sampled size
-  unsigned int item_base;  // first ticket of this box inside its frame
-  unsigned int pad;
+  unsigned int item_base;  // first item of this box inside its frame
+  int fused;
   unsigned long long scratch_off;   // in u16 elements inside the frame's scratch region
 };
 
@@ -47,35 +56,45 @@ struct Header {
 struct Ws {
   Header* hdr;
   BoxMeta* meta;       // [B][maxb]
-  int* doneA;          // [B][maxb]
-  int* doneB;          // [B][maxb]
+  int* done;           // [B][items_cap] one flag per item
   uint16_t* scratch;   // [B][scratch_elems]
   size_t scratch_elems;
+  unsigned int items_cap;
 };
 
 struct Taps {
   uint16_t q[256];
+  // dp4a fast path: taps shifted by a = 0..3 bytes and packed 4 per word: qa[a][j] byte b = q[4j + b - a]
+  uint32_t qa[4][KW_MAX];
+  int kw;                  // words per shifted tap vector, 0 = fast path not applicable (a tap > 255 or ksize > 125)
 };
 
 __host__ __device__ inline size_t al256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
+__host__ inline size_t items_cap_for(int maxb, size_t scratch_px) { return 4 * static_cast<size_t>(maxb) + scratch_px / 128 + 1024; }
+
 __host__ size_t ws_bytes(int B, int maxb, size_t scratch_px) {
   return al256(sizeof(unsigned int) * (B + 4)) + al256(sizeof(BoxMeta) * static_cast<size_t>(B) * maxb) +
-         2 * al256(sizeof(int) * static_cast<size_t>(B) * maxb) + al256(static_cast<size_t>(B) * scratch_px * 3 * 2) +
-         256;
+         al256(sizeof(int) * static_cast<size_t>(B) * items_cap_for(maxb, scratch_px)) +
+         al256(static_cast<size_t>(B) * scratch_px * 3 * 2) + 256;
 }
 
-__host__ Ws carve(void* p0, int B, int maxb, size_t total_bytes) {
+__host__ Ws carve(void* p0, int B, int maxb, size_t total_bytes, size_t* flag_bytes) {
   Ws w;
   uint8_t* p = static_cast<uint8_t*>(p0);
   w.hdr = reinterpret_cast<Header*>(p);
   p += al256(sizeof(unsigned int) * (B + 4));
   w.meta = reinterpret_cast<BoxMeta*>(p);
   p += al256(sizeof(BoxMeta) * static_cast<size_t>(B) * maxb);
-  w.doneA = reinterpret_cast<int*>(p);
-  p += al256(sizeof(int) * static_cast<size_t>(B) * maxb);
-  w.doneB = reinterpret_cast<int*>(p);
-  p += al256(sizeof(int) * static_cast<size_t>(B) * maxb);
+  // split what is left: flags get 1 int per 128 scratch pixels (+ 4 per box), the rest is scratch
+  const size_t left = total_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(p0)) - 256;
+  const size_t fixed = sizeof(int) * static_cast<size_t>(B) * (4 * static_cast<size_t>(maxb) + 1024);
+  // scratch_px * (6 + 4/128) * B + fixed = left
+  const size_t scratch_px = static_cast<size_t>((left > fixed ? left - fixed : 0) / (static_cast<double>(B) * (6.0 + 4.0 / 128.0)));
+  w.items_cap = static_cast<unsigned int>(4 * static_cast<size_t>(maxb) + scratch_px / 128 + 1024 - 8);
+  w.done = reinterpret_cast<int*>(p);
+  *flag_bytes = sizeof(int) * static_cast<size_t>(B) * w.items_cap;
+  p += al256(*flag_bytes);
   w.scratch = reinterpret_cast<uint16_t*>(p);
   const size_t used = static_cast<size_t>(p - static_cast<uint8_t*>(p0));
   w.scratch_elems = ((total_bytes - used) / 2 / B) & ~static_cast<size_t>(7);
@@ -107,7 +126,6 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
     const int nbx = min(nd + ne, maxb);
     unsigned int item_carry = 0;
     unsigned long long scr_carry = 0;
-    // pass 1: metadata + prefix sums, 1024 boxes per chunk
     for (int base = 0; base < maxb; base += 1024) {
       const int k = base + tid;
       BoxMeta m;
@@ -137,9 +155,11 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
             m.tA = (m.sw * m.sh + MA_PIX - 1) / MA_PIX;
             m.tB = ((bw + MB_W - 1) / MB_W) * ((bh + MB_H - 1) / MB_H);
             scr = (static_cast<unsigned long long>(m.sw) * m.sh * 3 + 1) / 2;
+          } else if (static_cast<long long>(bw) * bh <= FUSE_MAX_PX) {
+            m.fused = 1; m.tA = 1; m.tB = 0;
           } else {
             m.tA = ((bw + GA_W - 1) / GA_W) * ((bh + GA_H - 1) / GA_H);
-            m.tB = ((bw + GB_W - 1) / GB_W) * ((bh + GB_H - 1) / GB_H);
+            m.tB = ((bw * 3 + GB_E - 1) / GB_E) * ((bh + GB_H - 1) / GB_H);
             scr = static_cast<unsigned long long>(bw) * bh * 3;
           }
           scr = (scr + 7) & ~7ull;
@@ -163,15 +183,13 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
         m.item_base = item_carry + s_items[tid] - items;
         m.scratch_off = scr_carry + s_scr[tid] - scr;
         ws.meta[static_cast<size_t>(f) * maxb + k] = m;
-        ws.doneA[static_cast<size_t>(f) * maxb + k] = 0;
-        ws.doneB[static_cast<size_t>(f) * maxb + k] = 0;
       }
       item_carry += s_items[1023];
       scr_carry += s_scr[1023];
       __syncthreads();
     }
-    // pass 2: a frame whose boxes do not fit the scratch region is skipped entirely (status bit)
-    const bool overflow = scr_carry > ws.scratch_elems;
+    // a frame whose boxes do not fit the workspace is skipped entirely (status bit)
+    const bool overflow = scr_carry > ws.scratch_elems || item_carry > ws.items_cap;
     if (overflow) {
       for (int k = tid; k < maxb; k += 1024) {
         BoxMeta* mp = ws.meta + static_cast<size_t>(f) * maxb + k;
@@ -204,40 +222,93 @@ __device__ __forceinline__ int nearest_src(int d, int dst_n, int src_n) {
   return min(s, src_n - 1);
 }
 
-__device__ __forceinline__ int ld_volatile(const int* p) {
+__device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.global.acquire.gpu.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.global.release.gpu.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-__device__ __forceinline__ void spin_until(const int* ctr, int target, uint32_t* status) {
+__device__ __forceinline__ void spin_flag(const int* flag, uint32_t* status) {
   uint32_t spins = 0;
-  while (ld_volatile(ctr) < target) {
-    __nanosleep(64);
-    if (++spins > (1u << 24)) {
+  while (ld_acquire(flag) == 0) {
+    if (++spins > 64) __nanosleep(32);
+    if (spins > (1u << 24)) {
       atomicOr(status, VD_STAT_WATCHDOG);
       break;
     }
   }
 }
 
+// wait until every B / fused tile of an earlier box that writes into [rx1,rx2) x [ry1,ry2) is done
+__device__ __forceinline__ void wait_writers(const BoxMeta* fm, const int* done, int k, int rx1, int ry1, int rx2,
+                                             int ry2, int mode, uint32_t* status) {
+  for (int j = threadIdx.x; j < k; j += kThreads) {
+    const BoxMeta o = fm[j];
+    if (o.tA + o.tB == 0) continue;
+    const int ix1 = max(rx1, o.x1), iy1 = max(ry1, o.y1), ix2 = min(rx2, o.x2), iy2 = min(ry2, o.y2);
+    if (ix1 >= ix2 || iy1 >= iy2) continue;
+    if (o.fused) {
+      spin_flag(done + o.item_base, status);
+      continue;
+    }
+    int tiles_x, tx0, tx1, th;
+    if (mode == VD_MODE_MOSAIC) {
+      th = MB_H;
+      tiles_x = (o.x2 - o.x1 + MB_W - 1) / MB_W;
+      tx0 = (ix1 - o.x1) / MB_W; tx1 = (ix2 - 1 - o.x1) / MB_W;
+    } else {                      // Gaussian B tiles span GB_E flat (pixel*3 + channel) elements
+      th = GB_H;
+      tiles_x = ((o.x2 - o.x1) * 3 + GB_E - 1) / GB_E;
+      tx0 = ((ix1 - o.x1) * 3) / GB_E; tx1 = ((ix2 - o.x1) * 3 - 1) / GB_E;
+    }
+    const int ty0 = (iy1 - o.y1) / th, ty1 = (iy2 - 1 - o.y1) / th;
+    const int* base = done + o.item_base + o.tA;
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) spin_flag(base + ty * tiles_x + tx, status);
+  }
+}
+
+// ---- dp4a building blocks --------------------------------------------------------------------
+// out[4m + a] = sum_j dp4a(S[m + j], QA_a[j]) for M consecutive m; S = byte row packed 4 per word.
+template <int M>
+__device__ __forceinline__ void dp4a_run(const uint32_t* __restrict__ S, const uint32_t* __restrict__ qa, int kw,
+                                         uint32_t (&acc)[M]) {
+  uint32_t win[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) { acc[i] = 0; win[i] = S[i]; }
+  for (int j = 0; j < kw; ++j) {
+    const uint32_t q = qa[j];
+#pragma unroll
+    for (int i = 0; i < M; ++i) acc[i] = __dp4a(win[i], q, acc[i]);
+    // slide the window by one word
+#pragma unroll
+    for (int i = 0; i + 1 < M; ++i) win[i] = win[i + 1];
+    win[M - 1] = S[M + j];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int mode, int ksize, Taps taps,
                      uint32_t* __restrict__ status, Ws ws) {
-  extern __shared__ uint8_t dsm[];
+  extern __shared__ __align__(16) uint8_t dsm[];
   __shared__ unsigned int s_ticket;
+  __shared__ int s_box;
   __shared__ unsigned int s_fprefix[130];
   __shared__ uint16_t s_q[256];
+  __shared__ uint32_t s_qa[4][KW_MAX];
   const int tid = threadIdx.x;
   for (int i = tid; i <= B; i += kThreads) s_fprefix[i] = ws.hdr->frame_prefix[i];
   s_q[tid] = taps.q[tid];
+  if (tid < 4 * KW_MAX) s_qa[tid / KW_MAX][tid % KW_MAX] = taps.qa[tid / KW_MAX][tid % KW_MAX];
   __syncthreads();
-  // tickets interleave the frames (ticket t -> frame t % B, item t / B) so the sequential box chains
-  // of all frames advance concurrently; inside a frame the (box, phase, tile) order is kept
   unsigned int max_items = 0;
   for (int i = 0; i < B; ++i) max_items = max(max_items, s_fprefix[i + 1] - s_fprefix[i]);
   const unsigned int total = max_items * static_cast<unsigned int>(B);
   const int r = ksize >> 1;
+  const int kw = taps.kw;
 
   while (true) {
     __syncthreads();
@@ -249,37 +320,85 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     const unsigned int local = t / static_cast<unsigned int>(B);
     if (local >= s_fprefix[f + 1] - s_fprefix[f]) continue;      // this frame has fewer items
     const BoxMeta* fm = ws.meta + static_cast<size_t>(f) * maxb;
-    // binary search: last box with item_base <= local and a non-empty item range containing local
-    int lo = 0, hi = maxb - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (fm[mid].item_base <= local) lo = mid; else hi = mid - 1;
+    int* done = ws.done + static_cast<size_t>(f) * ws.items_cap;
+    // owner box of the item: warp-parallel search over the (non-decreasing) item_base array — the last
+    // box with item_base <= local that actually owns items
+    if (tid < 32) {
+      int lo = 0, hi = maxb;                       // answer in [lo, hi)
+      while (hi - lo > 32) {
+        const int step = (hi - lo + 31) / 32;
+        const int idx = min(lo + tid * step, hi - 1);
+        const bool le = fm[idx].item_base <= local;
+        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, le);
+        const int last = 31 - __clz(bal);          // lane 0 always qualifies (item_base[lo] <= local)
+        const int nlo = min(lo + last * step, hi - 1);
+        hi = min(nlo + step, hi);
+        lo = nlo;
+      }
+      const int idx = lo + tid;
+      bool own = false;
+      if (idx < hi) {
+        const BoxMeta c = fm[idx];
+        own = c.item_base <= local && local < c.item_base + static_cast<unsigned int>(c.tA + c.tB);
+      }
+      const unsigned int bal = __ballot_sync(0xFFFFFFFFu, own);
+      if (tid == 0) s_box = bal ? lo + (__ffs(bal) - 1) : -1;
     }
-    // boxes with zero items share item_base with their successor: step back to the owner
-    int k = lo;
-    while (k > 0 && !(local < fm[k].item_base + static_cast<unsigned int>(fm[k].tA + fm[k].tB))) --k;
+    __syncthreads();
+    int k = s_box;
+    if (k < 0) {                                   // owner sits before `lo` (run of empty boxes): walk back
+      k = 0;
+      int lo2 = 0, hi2 = maxb - 1;
+      while (lo2 < hi2) {
+        const int mid = (lo2 + hi2 + 1) >> 1;
+        if (fm[mid].item_base <= local) lo2 = mid; else hi2 = mid - 1;
+      }
+      k = lo2;
+      while (k > 0 && !(local < fm[k].item_base + static_cast<unsigned int>(fm[k].tA + fm[k].tB))) --k;
+    }
     const BoxMeta m = fm[k];
     const int rel = static_cast<int>(local - m.item_base);
     const bool phaseA = rel < m.tA;
     const int tile = phaseA ? rel : rel - m.tA;
-    int* doneA = ws.doneA + static_cast<size_t>(f) * maxb;
-    int* doneB = ws.doneB + static_cast<size_t>(f) * maxb;
+    const int bw = m.x2 - m.x1, bh = m.y2 - m.y1;
+    const int row3 = bw * 3;
 
-    // ---- dependencies ----
-    if (phaseA) {
-      for (int j = tid; j < k; j += kThreads) {
-        const BoxMeta o = fm[j];
-        if (o.tB > 0 && o.x1 < m.x2 && m.x1 < o.x2 && o.y1 < m.y2 && m.y1 < o.y2) spin_until(doneB + j, o.tB, status);
+    // ---- tile geometry (box-local) and dependencies ----
+    int tx = 0, ty = 0;
+    if (mode == VD_MODE_MOSAIC) {
+      if (phaseA) {
+        wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, status);
+      } else {
+        const int tiles_x = (bw + MB_W - 1) / MB_W;
+        ty = tile / tiles_x; tx = tile - ty * tiles_x;
+        for (int a = tid; a < m.tA; a += kThreads) spin_flag(done + m.item_base + a, status);
       }
-    } else if (tid == 0) {
-      spin_until(doneA + k, m.tA, status);
+    } else if (m.fused) {
+      wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, status);
+    } else if (phaseA) {
+      const int tiles_x = (bw + GA_W - 1) / GA_W;
+      ty = tile / tiles_x; tx = tile - ty * tiles_x;
+      const int cx1 = max(0, tx * GA_W - r), cx2 = min(bw, tx * GA_W + GA_W + r);
+      const int cy1 = ty * GA_H, cy2 = min(bh, ty * GA_H + GA_H);
+      wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, status);
+    } else {
+      const int tiles_x = (row3 + GB_E - 1) / GB_E;
+      ty = tile / tiles_x; tx = tile - ty * tiles_x;
+      // A tiles of this box with rows in (tile rows +- r) and pixel columns in (tile columns +- r)
+      const int px1 = (tx * GB_E) / 3, px2 = min(bw, (tx * GB_E + GB_E + 2) / 3);
+      const int cx1 = max(0, px1 - r), cx2 = min(bw, px2 + r);
+      const int cy1 = max(0, ty * GB_H - r), cy2 = min(bh, ty * GB_H + GB_H + r);
+      const int atx = (bw + GA_W - 1) / GA_W;
+      const int ax0 = cx1 / GA_W, ax1 = (cx2 - 1) / GA_W, ay0 = cy1 / GA_H, ay1 = (cy2 - 1) / GA_H;
+      const int nax = ax1 - ax0 + 1, n = nax * (ay1 - ay0 + 1);
+      for (int i = tid; i < n; i += kThreads)
+        spin_flag(done + m.item_base + (ay0 + i / nax) * atx + ax0 + i % nax, status);
     }
     __threadfence();
     __syncthreads();
 
     const vd_frame_t fr = frames[f];
     uint8_t* img = const_cast<uint8_t*>(fr.ptr);
-    const int bw = m.x2 - m.x1, bh = m.y2 - m.y1;
     uint16_t* scr16 = ws.scratch + static_cast<size_t>(f) * ws.scratch_elems + m.scratch_off;
 
     if (mode == VD_MODE_MOSAIC) {
@@ -295,8 +414,6 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           small[idx * 3 + 2] = __ldcg(p + 2);
         }
       } else {
-        const int tiles_x = (bw + MB_W - 1) / MB_W;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         for (int i = tid; i < MB_W * MB_H; i += kThreads) {
           const int ly = i / MB_W, lx = i - ly * MB_W;
           const int y = ty * MB_H + ly, x = tx * MB_W + lx;
@@ -310,15 +427,80 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           }
         }
       }
-    } else {
-      if (phaseA) {
-        // horizontal pass: tile GA_H rows x GA_W cols; stage (GA_W + 2r) columns with REFLECT_101
-        const int tiles_x = (bw + GA_W - 1) / GA_W;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int x0 = tx * GA_W, y0 = ty * GA_H;
-        const int span = GA_W + 2 * r;                 // staged columns
+    } else if (m.fused) {
+      // whole box in shared memory: u8 source [bh][bw*3], u16 horizontal result [bh][bw*3]
+      uint8_t* src = dsm;
+      uint16_t* mid = reinterpret_cast<uint16_t*>(dsm + ((bh * row3 + 15) & ~15));
+      for (int i = tid; i < bh * row3; i += kThreads) {
+        const int y = i / row3, e = i - y * row3;
+        src[i] = __ldcg(img + static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e);
+      }
+      __syncthreads();
+      for (int i = tid; i < bh * row3; i += kThreads) {
+        const int y = i / row3, e = i - y * row3;
+        const int x = e / 3, c = e - x * 3;
+        const uint8_t* srow = src + y * row3 + c;
+        uint32_t acc = 0;
+        if (x >= r && x + r < bw) {
+          const uint8_t* s = srow + (x - r) * 3;
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * 3];
+        } else {
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * srow[reflect101(x - r + tt, bw) * 3];
+        }
+        mid[i] = static_cast<uint16_t>(min(acc, 65535u));
+      }
+      __syncthreads();
+      for (int i = tid; i < bh * row3; i += kThreads) {
+        const int y = i / row3, e = i - y * row3;
+        uint32_t acc = 0;
+        if (y >= r && y + r < bh) {
+          const uint16_t* s = mid + (y - r) * row3 + e;
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * row3];
+        } else {
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * mid[reflect101(y - r + tt, bh) * row3 + e];
+        }
+        img[static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
+      }
+    } else if (phaseA) {
+      // ---------------- horizontal pass: GA_H rows x GA_W pixels ----------------
+      const int x0 = tx * GA_W, y0 = ty * GA_H;
+      const int rows = min(GA_H, bh - y0);
+      const int cols = min(GA_W, bw - x0);
+      if (kw > 0) {
+        // planar staging: plane c, row ly: bytes s[i] = pixel(x0 - r + i) (REFLECT_101), word-aligned rows
+        const int span = GA_W + 2 * r;                       // bytes used per plane row
+        const int spanw = (span + 3 + 4 * KW_MAX) / 4;       // words per row incl. slack read by the last window
+        uint32_t* planes = reinterpret_cast<uint32_t*>(dsm); // [3][GA_H][spanw]
+        uint8_t* pb = dsm;
+        for (int i = tid; i < rows * span; i += kThreads) {
+          const int ly = i / span, c = i - ly * span;
+          const int xs = reflect101(x0 - r + c, bw);
+          const uint8_t* p = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + (m.x1 + xs) * 3;
+          pb[((0 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p);
+          pb[((1 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p + 1);
+          pb[((2 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p + 2);
+        }
+        __syncthreads();
+        // thread -> (channel, a, row, half): 16 outputs x = 64*half + 4m + a
+        constexpr int M = 16;
+        if (tid < 3 * 4 * GA_H * 2) {
+          const int c = tid % 3, a = (tid / 3) & 3, rest = tid / 12;
+          const int half = rest & 1, ly = rest >> 1;
+          if (ly < rows) {
+            const uint32_t* S = planes + (c * GA_H + ly) * spanw + half * (GA_W / 8);
+            uint32_t acc[M];
+            dp4a_run<M>(S, s_qa[a], kw, acc);
+            uint16_t* orow = scr16 + (static_cast<size_t>(y0 + ly) * bw + x0) * 3 + c;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+              const int lx = half * (GA_W / 2) + 4 * i + a;
+              if (lx < cols) orow[lx * 3] = static_cast<uint16_t>(acc[i]);
+            }
+          }
+        }
+      } else {
+        const int span = GA_W + 2 * r;
         uint8_t* st = dsm;                             // [GA_H][span*3]
-        const int rows = min(GA_H, bh - y0);
         for (int i = tid; i < rows * span; i += kThreads) {
           const int ly = i / span, c = i - ly * span;
           const int xs = reflect101(x0 - r + c, bw);
@@ -327,7 +509,6 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           d[0] = __ldcg(p); d[1] = __ldcg(p + 1); d[2] = __ldcg(p + 2);
         }
         __syncthreads();
-        const int cols = min(GA_W, bw - x0);
         for (int i = tid; i < rows * cols * 3; i += kThreads) {
           const int ly = i / (cols * 3), e = i - ly * cols * 3;      // e = lx*3 + ch
           const uint8_t* s = st + ly * span * 3 + e;
@@ -335,34 +516,63 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * 3];
           scr16[(static_cast<size_t>(y0 + ly) * bw + x0) * 3 + e] = static_cast<uint16_t>(min(acc, 65535u));
         }
-      } else {
-        // vertical pass: tile GB_H rows x GB_W cols (x3 channels); stage (GB_H + 2r) rows of u16
-        const int tiles_x = (bw + GB_W - 1) / GB_W;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int x0 = tx * GB_W, y0 = ty * GB_H;
-        const int cols3 = min(GB_W, bw - x0) * 3;
-        const int rows = min(GB_H, bh - y0);
-        const int span = rows + 2 * r;
-        uint16_t* st = reinterpret_cast<uint16_t*>(dsm);   // [span][GB_W*3]
-        for (int i = tid; i < span * cols3; i += kThreads) {
-          const int ly = i / cols3, e = i - ly * cols3;
+      }
+    } else {
+      // ---------------- vertical pass: GB_H rows x GB_E flat elements ----------------
+      const int e0 = tx * GB_E, y0 = ty * GB_H;
+      const int ne = min(GB_E, row3 - e0);
+      const int rows = min(GB_H, bh - y0);
+      const int span = rows + 2 * r;                       // staged rows
+      if (kw > 0) {
+        // transposed byte planes: hi[e][i], lo[e][i] with i = staged row (REFLECT_101); word-aligned columns;
+        // an odd word pitch keeps the byte stores of consecutive e on different banks
+        int colw = (GB_H + 2 * r + 3 + 4 * KW_MAX) / 4;
+        colw |= 1;
+        uint8_t* hi = dsm;                                  // [GB_E][colw*4]
+        uint8_t* lo = dsm + GB_E * colw * 4;
+        for (int i = tid; i < span * ne; i += kThreads) {
+          const int ly = i / ne, e = i - ly * ne;
           const int ys = reflect101(y0 - r + ly, bh);
-          st[ly * (GB_W * 3) + e] = __ldcg(scr16 + (static_cast<size_t>(ys) * bw + x0) * 3 + e);
+          const uint16_t v = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
+          hi[e * colw * 4 + ly] = static_cast<uint8_t>(v >> 8);
+          lo[e * colw * 4 + ly] = static_cast<uint8_t>(v & 0xFF);
         }
         __syncthreads();
-        for (int i = tid; i < rows * cols3; i += kThreads) {
-          const int ly = i / cols3, e = i - ly * cols3;
-          const uint16_t* s = st + ly * (GB_W * 3) + e;
+        // thread -> (e, a): 16 outputs y = 4m + a
+        constexpr int M = GB_H / 4;
+        const int e = tid & (GB_E - 1), a = tid / GB_E;
+        if (e < ne) {
+          uint32_t ah[M], al[M];
+          dp4a_run<M>(reinterpret_cast<const uint32_t*>(hi) + e * colw, s_qa[a], kw, ah);
+          dp4a_run<M>(reinterpret_cast<const uint32_t*>(lo) + e * colw, s_qa[a], kw, al);
+          uint8_t* ocol = img + static_cast<size_t>(m.y1 + y0) * fr.pitch + m.x1 * 3 + e0 + e;
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            const int ly = 4 * i + a;
+            if (ly < rows) ocol[static_cast<size_t>(ly) * fr.pitch] = static_cast<uint8_t>(((ah[i] << 8) + al[i] + 32768u) >> 16);
+          }
+        }
+      } else {
+        uint16_t* st = reinterpret_cast<uint16_t*>(dsm);   // [span][GB_E]
+        for (int i = tid; i < span * ne; i += kThreads) {
+          const int ly = i / ne, e = i - ly * ne;
+          const int ys = reflect101(y0 - r + ly, bh);
+          st[ly * GB_E + e] = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
+        }
+        __syncthreads();
+        for (int i = tid; i < rows * ne; i += kThreads) {
+          const int ly = i / ne, e = i - ly * ne;
+          const uint16_t* s = st + ly * GB_E + e;
           uint32_t acc = 0;
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * (GB_W * 3)];
-          img[static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + (m.x1 + x0) * 3 + e] =
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * GB_E];
+          img[static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + m.x1 * 3 + e0 + e] =
               static_cast<uint8_t>((acc + 32768u) >> 16);
         }
       }
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) atomicAdd(phaseA ? (doneA + k) : (doneB + k), 1);
+    if (tid == 0) st_release(done + local, 1);
   }
 }
 
@@ -406,6 +616,7 @@ extern "C" int vd_gaussian_taps_q8(int ksize, double sigma, uint16_t* taps) {
 
 extern "C" size_t vd_composite_workspace_bytes(int B, int max_boxes, size_t scratch_pixels_per_frame) {
   if (B <= 0 || max_boxes <= 0) return 0;
+  if (max_boxes > VD_MAX_BOXES_PER_FRAME) max_boxes = VD_MAX_BOXES_PER_FRAME;
   return ws_bytes(B, max_boxes, scratch_pixels_per_frame);
 }
 
@@ -431,27 +642,57 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   } else {
     VD_REQUIRE(taps_q8 && ksize >= 1 && ksize <= VD_MAX_KSIZE && (ksize & 1), "vd_composite_rois: bad Gaussian taps");
     for (int i = 0; i < ksize; ++i) taps.q[i] = taps_q8[i];
+    // dp4a fast path: every tap must fit a byte and the shifted vectors KW_MAX words
+    const int kwords = (ksize + 3 + 3) / 4;
+    bool fits = kwords <= KW_MAX;
+    for (int i = 0; i < ksize; ++i) fits = fits && taps_q8[i] <= 255;
+    if (fits) {
+      taps.kw = kwords;
+      for (int a = 0; a < 4; ++a)
+        for (int j = 0; j < KW_MAX; ++j) {
+          uint32_t w = 0;
+          for (int b = 0; b < 4; ++b) {
+            const int ti = 4 * j + b - a;
+            if (ti >= 0 && ti < ksize) w |= static_cast<uint32_t>(taps_q8[ti]) << (8 * b);
+          }
+          taps.qa[a][j] = w;
+        }
+    }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Ws ws = carve(workspace, B, maxb, workspace_bytes);
+  size_t flag_bytes = 0;
+  const Ws ws = carve(workspace, B, maxb, workspace_bytes, &flag_bytes);
+  VD_CHECK_CUDA(cudaMemsetAsync(ws.done, 0, flag_bytes, st));
   composite_plan_kernel<<<1, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
                                             maxb, mode, mosaic_level, status, ws);
   VD_LAUNCH_CHECK();
   const int r = ksize >> 1;
   size_t smem = 0;
   if (mode == VD_MODE_GAUSS) {
-    const size_t a = static_cast<size_t>(GA_H) * (GA_W + 2 * r) * 3;
-    const size_t b = static_cast<size_t>(GB_H + 2 * r) * GB_W * 3 * 2;
+    size_t a = static_cast<size_t>(GA_H) * (GA_W + 2 * r) * 3;
+    size_t b = static_cast<size_t>(GB_H + 2 * r) * GB_E * 2;
+    if (taps.kw > 0) {
+      a = static_cast<size_t>(3) * GA_H * ((GA_W + 2 * r + 3 + 4 * KW_MAX) / 4) * 4;
+      b = static_cast<size_t>(2) * GB_E * ((((GB_H + 2 * r + 3 + 4 * KW_MAX) / 4) | 1)) * 4;
+    }
+    const size_t fz = static_cast<size_t>(FUSE_MAX_PX) * 9 + 64;
     smem = a > b ? a : b;
+    if (fz > smem) smem = fz;
   }
+  VD_REQUIRE(smem <= static_cast<size_t>(kMaxDynSmem), "vd_composite_rois: kernel size too large for shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(composite_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VD_CHECK_CUDA(cudaFuncSetAttribute(composite_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     attr_set = true;
   }
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
-  composite_run_kernel<<<sms * 4, kThreads, smem, st>>>(frames, B, maxb, mode, ksize, taps, status, ws);
+  int per_sm = 4;
+  if (smem > 0) {
+    const int fit = static_cast<int>((220 * 1024) / (smem + 2048));
+    per_sm = fit < 1 ? 1 : (fit > 4 ? 4 : fit);
+  }
+  composite_run_kernel<<<sms * per_sm, kThreads, smem, st>>>(frames, B, maxb, mode, ksize, taps, status, ws);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
