@@ -88,6 +88,9 @@ CONV_CASES = [
     ("1x1_res_bn64",    2, 24,  32, 128,   64, 1, 1, 0, True, True, False),       # residual ring, BN = 64
     ("3x3_res_bn128",   2, 17,  31,  64,  128, 3, 1, 1, True, True, False),       # residual ring, BN = 128
     ("1x1_res_many",    1, 68, 120, 128,  512, 1, 1, 0, True, True, False),       # residual ring wraps many times
+    ("3x3_64_wres",     4, 68, 120,  64,   64, 3, 1, 1, True, False, False),      # resident weights (72 KB), 255 tiles
+    ("1x1_res_wres",    4, 68, 120,  64,  256, 1, 1, 0, True, True, False),       # resident weights + residual ring
+    ("1x1_256_64_wres", 4, 68, 120, 256,   64, 1, 1, 0, True, False, False),
 ]
 
 
@@ -140,7 +143,7 @@ def test_conv_channel_slice_and_f32(ops):
     assert torch.allclose(got, want, atol=1e-3, rtol=1e-4)
 
 
-@pytest.mark.parametrize("hw", [(32, 48), (45, 77), (96, 128)])
+@pytest.mark.parametrize("hw", [(32, 48), (45, 77), (96, 128), (270, 480)])
 def test_conv1_on_ingest_layout(ops, hw):
     from vdesens_b200 import weights
     H, W = hw

@@ -37,6 +37,9 @@ struct ConvKParams {
   int stride_h, stride_w, pad_h, pad_w;
   int dst_C, dst_coff;
   int up_H, up_W;
+  int stages;             // operand pipeline depth (<= kMaxStages), chosen on the host from the smem budget
+  int wres;               // 1: the whole weight matrix of the (single) N tile stays resident in shared memory
+  int w_bytes;            // wres: KB * BN * 128
   uint32_t flags;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -46,20 +49,31 @@ struct ConvKParams {
 
 // RES = the layer adds a residual tensor: it is prefetched by a dedicated TMA warp into a ring of
 // RES_SLOTS 16 KB tiles (one per 64-channel chunk), paid for with fewer operand stages.
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 232448;        // 227 KB per CTA on sm_100
+constexpr int kWresMaxBytes = 72 * 1024;   // resident-weight limit (3x3 64->64 = 72 KB)
+
 template <int BN, bool RES>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = RES ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
   static constexpr int RES_SLOTS = 3;
   static constexpr int RES_BYTES = RES ? RES_SLOTS * 128 * 128 : 0;
   static constexpr int BIAS_BYTES = 1024;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int FIXED_BYTES = OUT_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // +1024: alignment
   static constexpr int THREADS = RES ? 352 : 320;                             // +1 warp: residual producer
+  // operand region: `stages` A tiles, then either `stages` B tiles or the resident weight matrix
+  static int stages_for(int wres, int w_bytes) {
+    const int avail = kSmemBudget - FIXED_BYTES - (wres ? w_bytes : 0);
+    int st = avail / (wres ? A_BYTES : A_BYTES + B_BYTES);
+    return st > kMaxStages ? kMaxStages : st;
+  }
+  static int smem_for(int stages, int wres, int w_bytes) {
+    return FIXED_BYTES + stages * A_BYTES + (wres ? w_bytes : stages * B_BYTES);
+  }
 };
 
 constexpr int kEpiThreads = 256;
@@ -85,18 +99,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using Cfg = ConvCfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint8_t* sOut = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;             // B stages, or the resident weight matrix (wres)
+  uint8_t* sOut = sB + (p.wres ? p.w_bytes : STAGES * Cfg::B_BYTES);
   uint8_t* sRes = sOut + Cfg::OUT_BYTES;
   float* sBias = reinterpret_cast<float*>(sRes + Cfg::RES_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
-  uint64_t* empty = full + Cfg::STAGES;
-  uint64_t* tfull = empty + Cfg::STAGES;
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* rfull = tempty + 2;
   uint64_t* rempty = rfull + Cfg::RES_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + Cfg::RES_SLOTS);
+  uint64_t* wfull = rempty + Cfg::RES_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,10 +125,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < Cfg::STAGES; ++i) {
+      for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
       }
+      mbar_init(wfull, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8);
@@ -139,6 +156,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.wres) {                                   // weights: loaded once, reused by every tile
+        mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * 64, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int m = tile / p.n_tiles;
@@ -154,10 +175,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int s = 0; s < p.S; ++s) {
             for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.a_bytes + Cfg::B_BYTES));
+              mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES)));
               tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + s, yin0 + r, b0);
-              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, n_tile * BN);
-              if (++stage == Cfg::STAGES) {
+              if (!p.wres) tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, n_tile * BN);
+              if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -177,6 +198,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.wres) mbar_wait(wfull, 0);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -185,7 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + (p.wres ? kb : stage) * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
@@ -193,7 +215,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       static_cast<uint32_t>((kb | k) != 0));
           }
           umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
-          if (++stage == Cfg::STAGES) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
@@ -415,8 +437,21 @@ struct vd_conv_plan {
   ConvKParams kp;
   int BN;
   int grid;
+  int smem_bytes;
   vd_conv_desc_t desc;
 };
+
+template <int BN, bool RES>
+static void plan_smem(vd_conv_plan* pl) {
+  using Cfg = ConvCfg<BN, RES>;
+  ConvKParams& k = pl->kp;
+  const int KB = k.R * k.S * k.cin_blocks;
+  const int w_bytes = KB * Cfg::B_BYTES;
+  k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && k.num_tiles > pl->grid) ? 1 : 0;
+  k.w_bytes = k.wres ? w_bytes : 0;
+  k.stages = Cfg::stages_for(k.wres, k.w_bytes);
+  pl->smem_bytes = Cfg::smem_for(k.stages, k.wres, k.w_bytes);
+}
 
 static void choose_tile(int Wout, int Hout, int B, int sw, int sh, int* TW, int* TH, int* NB) {
   long best_tiles = -1;
@@ -617,6 +652,20 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
+  {
+    const bool res = (d->flags & VD_CONV_RESIDUAL) != 0;
+    switch (BN) {
+      case 32: plan_smem<32, false>(pl); break;
+      case 64: res ? plan_smem<64, true>(pl) : plan_smem<64, false>(pl); break;
+      case 128: res ? plan_smem<128, true>(pl) : plan_smem<128, false>(pl); break;
+      default: res ? plan_smem<256, true>(pl) : plan_smem<256, false>(pl); break;
+    }
+    if (k.stages < 2) {
+      vd_set_error("vd_conv_plan_create: shared memory budget too small");
+      delete pl;
+      return VD_ERR_UNSUPPORTED;
+    }
+  }
   *out = pl;
   return VD_OK;
 }
@@ -641,15 +690,14 @@ extern "C" int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, i
 template <int BN, bool RES>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, RES>;
-  static_assert(Cfg::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+                                       kSmemBudget));
     attr_set = true;
   }
-  conv_igemm_kernel<BN, RES><<<pl->grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
-                                                                               pl->kp);
+  conv_igemm_kernel<BN, RES><<<pl->grid, Cfg::THREADS, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
+                                                                              pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
