@@ -94,6 +94,17 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[6] == 3 and c[7] == 1] + [
+    ("3x3_256_128_p",   2, 40,  56, 256,  128, 3, 1, 1, True, False, False),
+    ("3x3_128_res_p",   3, 33,  47, 128,  128, 3, 1, 1, True, True, False),
+], ids=lambda c: c[0] + "_patch")
+def test_conv_halo_patch_mode(ops, case, monkeypatch):
+    """3x3 stride-1 convs forced through the halo-patch path (A tile fetched once per 64-channel slice,
+    nine taps read it through row-shifted UMMA descriptors)."""
+    monkeypatch.setenv("VD_CONV_PATCH", "2")
+    test_conv_vs_torch(ops, case)
+
+
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_vs_torch(ops, case):
     name, B, H, W, Cin, Cout, k, s, p, relu, use_res, use_up = case

@@ -21,6 +21,7 @@
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 #include <cuda.h>
+#include <cstdlib>
 #include <new>
 
 #include "common.cuh"
@@ -37,6 +38,13 @@ struct ConvKParams {
   int stride_h, stride_w, pad_h, pad_w;
   int dst_C, dst_coff;
   int up_H, up_W;
+  int patch;              // 1: 3x3 stride-1 "halo patch" mode — the (TH+2)x(TW+2) input patch of a 64-channel
+                          //    slice is loaded ONCE and the nine taps read it through row-shifted descriptors
+  int PW, PH;             // patch extent in pixels
+  int a_slots, a_slot_bytes;
+  int kps;                // K blocks (generic) / filter taps (patch mode) fetched and issued per pipeline stage:
+                          //    one mbarrier round trip costs the single issuing warp ~450 clk, a 64-wide MMA
+                          //    K block only 128 clk, so narrow layers batch several blocks per stage
   int stages;             // operand pipeline depth (<= kMaxStages), chosen on the host from the smem budget
   int wres;               // 1: the whole weight matrix of the (single) N tile stays resident in shared memory
   int w_bytes;            // wres: KB * BN * 128
@@ -58,7 +66,7 @@ struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 384;
   static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
   static constexpr int RES_SLOTS = 3;
   static constexpr int RES_BYTES = RES ? RES_SLOTS * 128 * 128 : 0;
@@ -81,11 +89,14 @@ constexpr int kEpiThreads = 256;
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows*128B)
 // | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+// The hardware applies the 128-byte swizzle to ABSOLUTE shared-memory address bits (csrc/probe_umma.cu,
+// measured on B200): a descriptor may start at any 128-byte row of a TMA-written tile and use any
+// multiple of 128 as group stride, with base_offset = 0.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
@@ -100,9 +111,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;             // B stages, or the resident weight matrix (wres)
-  uint8_t* sOut = sB + (p.wres ? p.w_bytes : STAGES * Cfg::B_BYTES);
+  uint8_t* sA = smem;                                     // A stages (or the ring of halo patches)
+  const int KPS = p.kps;
+  uint8_t* sB = smem + (p.patch ? p.a_slots * p.a_slot_bytes : STAGES * KPS * Cfg::A_BYTES);   // B stages / resident W
+  uint8_t* sOut = sB + (p.wres ? p.w_bytes : STAGES * KPS * Cfg::B_BYTES);
   uint8_t* sRes = sOut + Cfg::OUT_BYTES;
   float* sBias = reinterpret_cast<float*>(sRes + Cfg::RES_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
@@ -112,7 +124,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* rfull = tempty + 2;
   uint64_t* rempty = rfull + Cfg::RES_SLOTS;
   uint64_t* wfull = rempty + Cfg::RES_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* afull = wfull + 1;                            // patch ring (<= 4 slots)
+  uint64_t* aempty = afull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,6 +144,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_init(&empty[i], 1);
       }
       mbar_init(wfull, 1);
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(&afull[i], 1);
+        mbar_init(&aempty[i], 1);
+      }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8);
@@ -152,78 +170,167 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int KB = p.R * p.S * p.cin_blocks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      if (p.wres) {                                   // weights: loaded once, reused by every tile
-        mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * 64, 0);
-      }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
-        const int tx = m % p.tiles_x;
-        m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tb = m / p.tiles_y;
-        const int xin0 = tx * p.TW * p.stride_w - p.pad_w;
-        const int yin0 = ty * p.TH * p.stride_h - p.pad_h;
-        const int b0 = tb * p.NB;
-        int kb = 0;
-        for (int r = 0; r < p.R; ++r) {
-          for (int s = 0; s < p.S; ++s) {
-            for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-              mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES)));
-              tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + s, yin0 + r, b0);
-              if (!p.wres) tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, n_tile * BN);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1u;
-              }
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) ==========
+    int stage = 0;
+    uint32_t phase = 0;
+    int aslot = 0;
+    uint32_t aphase = 0;
+    if (p.wres && elect_one()) {                      // weights: loaded once, reused by every tile
+      mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * 64, 0);
+    }
+    __syncwarp();
+    const uint32_t stage_tx = static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES));
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int tb = m / p.tiles_y;
+      const int xin0 = tx * p.TW * p.stride_w - p.pad_w;
+      const int yin0 = ty * p.TH * p.stride_h - p.pad_h;
+      const int b0 = tb * p.NB;
+      const int ncol = n_tile * BN;
+      if (p.patch) {
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait(&aempty[aslot], aphase ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&afull[aslot], static_cast<uint32_t>(p.PW * p.PH * 128));
+            tma_load_4d(sA + aslot * p.a_slot_bytes, &tmA, &afull[aslot], cb * 64, xin0, yin0, b0);
+          }
+          __syncwarp();
+          if (++aslot == p.a_slots) {
+            aslot = 0;
+            aphase ^= 1u;
+          }
+          for (int tap = 0; tap < 9; tap += KPS) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], static_cast<uint32_t>(KPS * Cfg::B_BYTES));
+              for (int j = 0; j < KPS; ++j)
+                tma_load_2d(sB + (stage * KPS + j) * Cfg::B_BYTES, &tmB, &full[stage],
+                            ((tap + j) * p.cin_blocks + cb) * 64, ncol);
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
+        }
+        continue;
+      }
+      int r = 0, sx = 0, cb = 0;
+      for (int kb = 0; kb < KB; kb += KPS) {
+        const int n = min(KPS, KB - kb);
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const bool leader = elect_one() != 0;
+        if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * stage_tx);
+        for (int j = 0; j < n; ++j) {
+          if (leader) {
+            tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + sx, yin0 + r, b0);
+            if (!p.wres)
+              tma_load_2d(sB + (stage * KPS + j) * Cfg::B_BYTES, &tmB, &full[stage], (kb + j) * 64, ncol);
+          }
+          if (++cb == p.cin_blocks) {            // K order (r, s, cin block): advance for every lane alike
+            cb = 0;
+            if (++sx == p.S) {
+              sx = 0;
+              ++r;
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
-      // a/b K-major, N>>3 [17,23), M>>4 [24,29)
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                                 (static_cast<uint32_t>(128 >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (p.wres) mbar_wait(wfull, 0);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < KB; ++kb) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =============
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+    // a/b K-major, N>>3 [17,23), M>>4 [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(128 >> 4) << 24);
+    // descriptor words: lo = start>>4 | LBO(1)<<16 ; hi = SBO>>4 | version(1)<<14 | SWIZZLE_128B(2)<<29
+    constexpr uint32_t hi_std = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int aslot = 0;
+    uint32_t aphase = 0;
+    if (p.wres) mbar_wait(wfull, 0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      if (p.patch) {
+        const uint32_t hi_patch = (static_cast<uint32_t>(p.PW * 128) >> 4) | (1u << 14) | (2u << 29);
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait(&afull[aslot], aphase);
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(aslot * (p.a_slot_bytes >> 4));
+          for (int tap0 = 0; tap0 < 9; tap0 += KPS) {
+            mbar_wait(&full[stage], phase);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              for (int j = 0; j < KPS; ++j) {
+                const int tap = tap0 + j;
+                const int r = tap / 3, sx = tap - 3 * r;
+                const uint32_t al = a_lo + static_cast<uint32_t>((r * p.PW + sx) * 8);     // 128 B rows, >>4
+                const uint32_t bl = b_lo0 + static_cast<uint32_t>((stage * KPS + j) * (Cfg::B_BYTES >> 4));
+                umma_bf16_words(d_tmem, al, hi_patch, bl, hi_std, idesc, static_cast<uint32_t>((cb | tap) != 0));
+                umma_bf16_words(d_tmem, al + 2, hi_patch, bl + 2, hi_std, idesc, 1u);
+                umma_bf16_words(d_tmem, al + 4, hi_patch, bl + 4, hi_std, idesc, 1u);
+                umma_bf16_words(d_tmem, al + 6, hi_patch, bl + 6, hi_std, idesc, 1u);
+              }
+              umma_commit(&empty[stage]);
+              if (tap0 + KPS >= 9) umma_commit(&aempty[aslot]);   // patch slot free once all nine taps have read it
+              if (tap0 + KPS >= 9 && cb == p.cin_blocks - 1) umma_commit(&tfull[acc]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          if (++aslot == p.a_slots) {
+            aslot = 0;
+            aphase ^= 1u;
+          }
+        }
+      } else {
+        for (int kb = 0; kb < KB; kb += KPS) {
+          const int n = min(KPS, KB - kb);
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + (p.wres ? kb : stage) * Cfg::B_BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      static_cast<uint32_t>((kb | k) != 0));
+          if (elect_one()) {
+            for (int j = 0; j < n; ++j) {
+              const uint32_t al = a_lo0 + static_cast<uint32_t>((stage * KPS + j) * (Cfg::A_BYTES >> 4));
+              const uint32_t bl =
+                  b_lo0 + static_cast<uint32_t>((p.wres ? kb + j : stage * KPS + j) * (Cfg::B_BYTES >> 4));
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
+              umma_bf16_words(d_tmem, al, hi_std, bl, hi_std, idesc, static_cast<uint32_t>((kb + j) != 0));
+              umma_bf16_words(d_tmem, al + 2, hi_std, bl + 2, hi_std, idesc, 1u);
+              umma_bf16_words(d_tmem, al + 4, hi_std, bl + 4, hi_std, idesc, 1u);
+              umma_bf16_words(d_tmem, al + 6, hi_std, bl + 6, hi_std, idesc, 1u);
+            }
+            umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+            if (kb + KPS >= KB) umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
           }
-          umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else if (RES && warp == 10) {
     // ===================== residual producer =====================
@@ -446,11 +553,44 @@ static void plan_smem(vd_conv_plan* pl) {
   using Cfg = ConvCfg<BN, RES>;
   ConvKParams& k = pl->kp;
   const int KB = k.R * k.S * k.cin_blocks;
+  const int avail = kSmemBudget - Cfg::FIXED_BYTES;
+  const char* env = getenv("VD_CONV_KPS");
+  const int force_kps = env ? atoi(env) : 0;
+  if (k.patch) {
+    k.wres = 0;
+    k.w_bytes = 0;
+    k.a_slot_bytes = (k.PW * k.PH * 128 + 1023) & ~1023;
+    k.a_slots = 2;
+    k.kps = (BN <= 128) ? 3 : 1;                         // taps per stage (must divide 9)
+    if (force_kps == 1 || force_kps == 3) k.kps = force_kps;
+    int st = (avail - k.a_slots * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES);
+    if (st > 3 && k.cin_blocks >= 2 && (avail - 3 * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES) >= 3) {
+      k.a_slots = 3;
+      st = (avail - k.a_slots * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES);
+    }
+    k.stages = st > kMaxStages ? kMaxStages : st;
+    pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + k.stages * k.kps * Cfg::B_BYTES;
+    return;
+  }
   const int w_bytes = KB * Cfg::B_BYTES;
-  k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && k.num_tiles > pl->grid) ? 1 : 0;
+  k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && k.num_tiles > pl->grid && BN <= 64 && KB >= 4) ? 1 : 0;
   k.w_bytes = k.wres ? w_bytes : 0;
-  k.stages = Cfg::stages_for(k.wres, k.w_bytes);
-  pl->smem_bytes = Cfg::smem_for(k.stages, k.wres, k.w_bytes);
+  // K blocks per stage: narrow N tiles finish a 64-deep block in 128 (BN=64) / 256 (BN=128) clk, far less
+  // than one barrier round trip of the issuing warp
+  int kps = 1;
+  if (BN <= 64) kps = k.wres ? 4 : 2;
+  else if (BN == 128) kps = 2;
+  if (kps > KB) kps = KB;
+  if (force_kps > 0 && force_kps <= 4) kps = force_kps > KB ? KB : force_kps;
+  const int stage_bytes = kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES));
+  int st = (avail - k.w_bytes) / stage_bytes;
+  while (st < 2 && kps > 1) {
+    --kps;
+    st = (avail - k.w_bytes) / (kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES)));
+  }
+  k.kps = kps;
+  k.stages = st > kMaxStages ? kMaxStages : st;
+  pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES));
 }
 
 static void choose_tile(int Wout, int Hout, int B, int sw, int sh, int* TW, int* TH, int* NB) {
@@ -533,6 +673,21 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     R = d->R; S = d->S; cin_blocks = d->Cin / 64; sh = sw = d->stride; ph = pw = d->pad;
   }
   choose_tile(d->Wout, d->Hout, d->B, sw, sh, &k.TW, &k.TH, &k.NB);
+  {
+    // halo-patch mode: 3x3 stride-1 convs whose N tile is narrow are bound by the 9x re-fetch of the A tile
+    // from L2 (~25 B/clk/SM of unique data); an 8x16 pixel tile + halo is fetched once per 64-channel slice.
+    const char* env = getenv("VD_CONV_PATCH");
+    const int mode = env ? atoi(env) : 1;              // 0 = off, 1 = auto, 2 = force where legal
+    const bool legal = !x0 && d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1;
+    const long generic_tiles = static_cast<long>(vd_cdiv(d->Wout, k.TW)) * vd_cdiv(d->Hout, k.TH) * vd_cdiv(d->B, k.NB);
+    const long patch_tiles = static_cast<long>(vd_cdiv(d->Wout, 8)) * vd_cdiv(d->Hout, 16) * d->B;
+    const bool worth = BN <= 128 && patch_tiles * 4 <= generic_tiles * 5;      // <= 25 % more tiles
+    if (legal && (mode == 2 || (mode == 1 && worth))) {
+      k.patch = 1;
+      k.TW = 8; k.TH = 16; k.NB = 1;
+      k.PW = 10; k.PH = 18;
+    }
+  }
   k.tiles_x = vd_cdiv(d->Wout, k.TW);
   k.tiles_y = vd_cdiv(d->Hout, k.TH);
   k.tiles_b = vd_cdiv(d->B, k.NB);
@@ -570,6 +725,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   }
   box[0] = 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
   box[3] = static_cast<cuuint32_t>(k.NB);
+  if (k.patch) { box[1] = static_cast<cuuint32_t>(k.PW); box[2] = static_cast<cuuint32_t>(k.PH); }
   estr[0] = 1; estr[1] = static_cast<cuuint32_t>(sw); estr[2] = static_cast<cuuint32_t>(sh); estr[3] = 1;
   CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
