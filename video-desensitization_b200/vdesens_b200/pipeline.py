@@ -91,6 +91,7 @@ class StreamingAnonymizer:
         self.mode, self.mosaic_level, self.ksize, self.sigma = mode, int(mosaic_level), int(ksize), float(sigma)
         self.depth = max(2, int(depth))
         self.slots = None
+        self.stats = {"submit_s": 0.0, "collect_wait_s": 0.0, "collect_host_s": 0.0, "batches": 0}
         self.s_in = torch.cuda.Stream(device=engine.device)
         self.s_out = torch.cuda.Stream(device=engine.device)
 
@@ -99,6 +100,13 @@ class StreamingAnonymizer:
             self.slots = [_Slot(self.eng, h, w) for _ in range(self.depth)]
 
     def _submit(self, slot, batch, ext):
+        import time
+        t0 = time.perf_counter()
+        self._submit_impl(slot, batch, ext)
+        self.stats["submit_s"] += time.perf_counter() - t0
+        self.stats["batches"] += 1
+
+    def _submit_impl(self, slot, batch, ext):
         eng = self.eng
         if isinstance(batch, torch.Tensor):                       # (n,h,w,3) uint8, ideally pinned
             n = batch.shape[0]
@@ -136,12 +144,21 @@ class StreamingAnonymizer:
             self.s_out.wait_event(slot.ev_done)
             slot.pin_out.copy_(slot.dev, non_blocking=True)       # D2H of the processed frames
             slot.ev_out.record(self.s_out)
-        # the next H2D into this slot must not overtake this D2H
-        self.s_in.wait_event(slot.ev_out)
+        # (the slot is only refilled after _collect() has synchronised on ev_out, so the next H2D into it
+        #  cannot overtake this D2H; no wait is queued on s_in — it would also stall the OTHER slot's H2D)
         slot.busy = True
 
     def _collect(self, slot, copy_out):
+        import time
+        t0 = time.perf_counter()
         slot.ev_out.synchronize()
+        t1 = time.perf_counter()
+        out = self._collect_impl(slot, copy_out)
+        self.stats["collect_wait_s"] += t1 - t0
+        self.stats["collect_host_s"] += time.perf_counter() - t1
+        return out
+
+    def _collect_impl(self, slot, copy_out):
         slot.busy = False
         self.eng.check_status(int(slot.status[0]))
         n = slot.n
