@@ -273,7 +273,7 @@ def run_ours(args):
                 "steps": e2e_steps, "host_ms_per_batch": e2e_host, "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step (double-buffered), max over ranks"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (76 launches + maxpool per step)",
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3; + maxpool)" % (len(eng.plans) - 1),
                      "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
                      "peak_source": peak_src + " bf16_tflops_sustained", "traffic": None,
                      "algorithmic_flops_per_step": CONV_GFLOP_PER_FRAME * 1e9 * BATCH, "segment_ms": net_ms},

@@ -95,6 +95,8 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
 #define VD_CONV_UPADD 4u       /* + nearest-upsampled half-resolution tensor AFTER ReLU     */
 #define VD_CONV_OUT_F32 8u     /* store fp32 instead of bf16 (head GEMM)                    */
 #define VD_CONV_IN_X0 16u      /* input is the ingest layout (conv1: 7x7 s2 p3, 3->64)       */
+#define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
+                                  the same output (bottleneck conv3 + downsample projection fused) */
 
 typedef struct vd_conv_desc {
   int32_t B;                 /* frames */
@@ -111,6 +113,9 @@ typedef struct vd_conv_desc {
   const void* residual;      /* [dev] bf16 [B][Hout][Wout][Cout] or NULL */
   const void* upadd;         /* [dev] bf16 [B][up_H][up_W][Cout] or NULL */
   void* y;                   /* [dev] output */
+  /* VD_CONV_DUAL: y += conv1x1_stride2(x2); weights are [Cout][R*S*Cin + Cin2], bias is the sum */
+  const void* x2;            /* [dev] bf16 NHWC [B][Hin2][Win2][Cin2] or NULL */
+  int32_t Cin2, Hin2, Win2, stride2;
 } vd_conv_desc_t;
 
 typedef struct vd_conv_plan vd_conv_plan_t;

@@ -294,9 +294,15 @@ def forward_bf16_emulated(packed, x, capture=None):
                 wp, b = packed[c.name]
                 if c.name == "body.conv1":
                     w = wp.float().view(c.cout, 7, 8, 8)[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()
+                    y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad)
+                elif c.wkey2:       # fused projection: both GEMMs share the fp32 accumulator on the device
+                    k1 = c.k * c.k * c.cin
+                    w = wp.float()[:, :k1].reshape(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
+                    w2 = wp.float()[:, k1:].reshape(c.cout, c.cin2, 1, 1)
+                    y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad) + F.conv2d(bufs[op.src2], w2, None, c.stride2, 0)
                 else:
                     w = wp.float().view(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
-                y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad)
+                    y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad)
                 if op.residual:
                     y = y + bufs[op.residual]
                 if c.relu:

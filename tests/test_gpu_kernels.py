@@ -133,6 +133,29 @@ def test_conv_vs_torch(ops, case):
         pytest.fail("\n".join(msg))
 
 
+@pytest.mark.parametrize("stride2,shape", [(1, (2, 24, 32)), (2, (2, 17, 31)), (2, (4, 68, 120))])
+def test_conv_dual_projection(ops, stride2, shape):
+    """bottleneck conv3 with the downsample projection fused as a second K segment:
+    relu(conv1x1(t2) + conv1x1_stride(x) + bias)."""
+    B, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(11 + stride2)
+    Hi, Wi = (H * stride2 - (stride2 - 1), W * stride2 - (stride2 - 1)) if stride2 == 2 else (H, W)   # odd extents too
+    t2 = torch.randn((B, H, W, 128), generator=g).to(torch.bfloat16).to(DEV)
+    x = torch.randn((B, Hi, Wi, 256), generator=g).to(torch.bfloat16).to(DEV)
+    w3 = (torch.randn((512, 128, 1, 1), generator=g) / 11.0).to(torch.bfloat16).to(DEV)
+    wd = (torch.randn((512, 256, 1, 1), generator=g) / 16.0).to(torch.bfloat16).to(DEV)
+    bias = torch.randn((512,), generator=g).to(DEV)
+    wp = torch.cat([w3.reshape(512, 128), wd.reshape(512, 256)], dim=1).contiguous()
+    got = ops.conv2d(t2, wp, bias, 1, 1, 0, relu=True, x2=x, stride2=stride2)
+    torch.cuda.synchronize()
+    want = torch.relu(torch.nn.functional.conv2d(t2.float().permute(0, 3, 1, 2), w3.float(), bias) +
+                      torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wd.float(), None, stride2))
+    want = want.permute(0, 2, 3, 1)
+    assert got.shape == want.shape
+    err = (got.float() - want).abs()
+    assert bool((err <= 2.0 ** -7 * want.abs().clamp_min(1.0)).all()), float(err.max())
+
+
 def test_conv_channel_slice_and_f32(ops):
     g = torch.Generator(device="cpu").manual_seed(5)
     x = torch.randn((2, 10, 12, 256), generator=g).to(torch.bfloat16).to(DEV)

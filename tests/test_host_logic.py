@@ -42,8 +42,10 @@ def test_host_only_entry_points():
 
 def test_graph_bookkeeping():
     from vdesens_b200 import arch, synth, weights
-    convs, ops, bufs = arch.build_graph()
+    convs, ops, bufs = arch.build_graph(fuse_downsample=False)
     assert len(convs) == 73 and sum(1 for o in ops if o.kind == "heads") == 3        # 73 + 9 head convs = 82
+    convs, ops, bufs = arch.build_graph()                                             # 4 projections fused away
+    assert len(convs) == 69 and sum(1 for c in convs if c.wkey2) == 4
     spec = arch.state_dict_spec()
     assert len(spec) == 456
     assert sum(int(np.prod(s)) for _, s, k in spec if k not in ("bn_mean", "bn_var", "bn_count")) == 27293600
@@ -51,14 +53,14 @@ def test_graph_bookkeeping():
     written = {"x0"}
     for o in ops:
         assert o.src in written, o
-        for extra in (o.residual, o.upsample_add):
+        for extra in (o.residual, o.upsample_add, o.src2):
             assert not extra or extra in written
         written.add(o.dst)
     flops = 0
     for o in ops:
         if o.kind == "conv":
             h, w = arch.feature_hw(1080, 1920, next(b.stride for b in bufs if b.name == o.dst))
-            flops += 2 * o.conv.cin * o.conv.cout * o.conv.k ** 2 * h * w
+            flops += 2 * (o.conv.cin * o.conv.k ** 2 + o.conv.cin2) * o.conv.cout * h * w
     for lvl, s in enumerate((8, 16, 32)):
         h, w = arch.feature_hw(1080, 1920, s)
         flops += 2 * 256 * 32 * h * w

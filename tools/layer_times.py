@@ -23,7 +23,7 @@ eng.set_frames(frames)
 eng.forward()
 eng.stream.synchronize()
 convs, _, _ = arch.build_graph()
-flops = {c.name: 2.0 * c.cout * c.cin * c.k * c.k for c in convs}
+flops = {c.name: 2.0 * c.cout * (c.cin * c.k * c.k + c.cin2) for c in convs}
 info = {p[0]: p[1:] for p in eng.plan_info()}
 s = C.c_void_p(eng.stream.cuda_stream)
 rows = []

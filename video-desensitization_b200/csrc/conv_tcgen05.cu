@@ -38,6 +38,9 @@ struct ConvKParams {
   int stride_h, stride_w, pad_h, pad_w;
   int dst_C, dst_coff;
   int up_H, up_W;
+  int kb2;                // DUAL: K blocks (Cin2 / 64) of the second input
+  int kb1;                // K blocks of the main convolution; blocks >= kb1 come from the second input (DUAL)
+  int stride2;            // DUAL: spatial stride of the 1x1 projection of x2
   int patch;              // 1: 3x3 stride-1 "halo patch" mode — the (TH+2)x(TW+2) input patch of a 64-channel
                           //    slice is loaded ONCE and the nine taps read it through row-shifted descriptors
   int PW, PH;             // patch extent in pixels
@@ -106,7 +109,7 @@ template <int BN, bool RES>
 __global__ void __launch_bounds__((ConvCfg<BN, RES>::THREADS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                  const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmA2, const ConvKParams p) {
   using Cfg = ConvCfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -136,6 +139,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
     if (RES) tma_prefetch_desc(&tmR);
+    if (p.flags & VD_CONV_DUAL) tma_prefetch_desc(&tmA2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -167,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int KB = p.R * p.S * p.cin_blocks;
+  const int KB = p.patch ? p.R * p.S * p.cin_blocks : p.kb1 + ((p.flags & VD_CONV_DUAL) ? p.kb2 : 0);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) ==========
@@ -229,7 +233,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * stage_tx);
         for (int j = 0; j < n; ++j) {
           if (leader) {
-            tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + sx, yin0 + r, b0);
+            if (kb + j < p.kb1)
+              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + sx, yin0 + r, b0);
+            else        // second K segment: 1x1 projection of x2 at (x*stride2, y*stride2)
+              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA2, &full[stage], (kb + j - p.kb1) * 64,
+                          tx * p.TW * p.stride2, ty * p.TH * p.stride2, b0);
             if (!p.wres)
               tma_load_2d(sB + (stage * KPS + j) * Cfg::B_BYTES, &tmB, &full[stage], (kb + j) * 64, ncol);
           }
@@ -541,6 +549,7 @@ struct vd_conv_plan {
   CUtensorMap tmB;
   CUtensorMap tmY;
   CUtensorMap tmR;
+  CUtensorMap tmA2;
   ConvKParams kp;
   int BN;
   int grid;
@@ -552,7 +561,7 @@ template <int BN, bool RES>
 static void plan_smem(vd_conv_plan* pl) {
   using Cfg = ConvCfg<BN, RES>;
   ConvKParams& k = pl->kp;
-  const int KB = k.R * k.S * k.cin_blocks;
+  const int KB = k.R * k.S * k.cin_blocks + k.kb2;
   const int avail = kSmemBudget - Cfg::FIXED_BYTES;
   const char* env = getenv("VD_CONV_KPS");
   const int force_kps = env ? atoi(env) : 0;
@@ -697,6 +706,21 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.a_bytes = k.rows_used * 128;
   k.B = d->B; k.Hout = d->Hout; k.Wout = d->Wout; k.Cout = d->Cout;
   k.R = R; k.S = S; k.cin_blocks = cin_blocks;
+  k.kb1 = R * S * cin_blocks;
+  k.kb2 = 0;
+  k.stride2 = 1;
+  const bool dual = (d->flags & VD_CONV_DUAL) != 0;
+  if (dual) {
+    if (x0 || !d->x2 || d->Cin2 <= 0 || d->Cin2 % 64 != 0 || d->stride2 < 1 || d->R != 1 || d->S != 1 ||
+        (reinterpret_cast<uintptr_t>(d->x2) & 15) != 0 || (d->Hin2 + d->stride2 - 1) / d->stride2 != d->Hout ||
+        (d->Win2 + d->stride2 - 1) / d->stride2 != d->Wout) {
+      vd_set_error("vd_conv_plan_create: bad second input for VD_CONV_DUAL");
+      delete pl;
+      return VD_ERR_INVALID;
+    }
+    k.kb2 = d->Cin2 / 64;
+    k.stride2 = d->stride2;
+  }
   k.stride_h = sh; k.stride_w = sw; k.pad_h = ph; k.pad_w = pw;
   k.dst_C = d->dst_C; k.dst_coff = d->dst_coff;
   k.up_H = d->up_H; k.up_W = d->up_W;
@@ -737,8 +761,26 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     delete pl;
     return VD_ERR_CUDA;
   }
+  pl->tmA2 = pl->tmA;
+  if (dual) {
+    cuuint64_t g2[4] = {static_cast<cuuint64_t>(d->Cin2), static_cast<cuuint64_t>(d->Win2),
+                        static_cast<cuuint64_t>(d->Hin2), static_cast<cuuint64_t>(d->B)};
+    cuuint64_t s2[3] = {static_cast<cuuint64_t>(d->Cin2) * 2, static_cast<cuuint64_t>(d->Cin2) * 2 * d->Win2,
+                        static_cast<cuuint64_t>(d->Cin2) * 2 * d->Win2 * d->Hin2};
+    cuuint32_t b2[4] = {64, static_cast<cuuint32_t>(k.TW * d->stride2), static_cast<cuuint32_t>(k.TH * d->stride2),
+                        static_cast<cuuint32_t>(k.NB)};
+    cuuint32_t e2[4] = {1, static_cast<cuuint32_t>(d->stride2), static_cast<cuuint32_t>(d->stride2), 1};
+    r = enc(&pl->tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x2), g2, s2, b2, e2,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vd_set_error("cuTensorMapEncodeTiled(A2) failed: CUresult %d", (int)r);
+      delete pl;
+      return VD_ERR_CUDA;
+    }
+  }
   // ---- B: weights [Cout][Ktot] ----
-  const cuuint64_t Ktot = static_cast<cuuint64_t>(R) * S * cin_blocks * 64;
+  const cuuint64_t Ktot = (static_cast<cuuint64_t>(R) * S * cin_blocks + static_cast<cuuint64_t>(k.kb2)) * 64;
   cuuint64_t wdim[2] = {Ktot, static_cast<cuuint64_t>(d->Cout)};
   cuuint64_t wstr[1] = {Ktot * 2};
   cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(BN)};
@@ -853,7 +895,7 @@ static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
     attr_set = true;
   }
   conv_igemm_kernel<BN, RES><<<pl->grid, Cfg::THREADS, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
-                                                                              pl->kp);
+                                                                              pl->tmA2, pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }

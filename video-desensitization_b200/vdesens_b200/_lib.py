@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdesens.so")
 
-VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0 = 1, 2, 4, 8, 16
+VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0, VD_CONV_DUAL = 1, 2, 4, 8, 16, 32
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
 VD_NMS_MAX_CAND = 8192
@@ -26,7 +26,9 @@ class VdConvDesc(C.Structure):
                 ("dst_C", C.c_int32), ("dst_coff", C.c_int32), ("up_H", C.c_int32), ("up_W", C.c_int32),
                 ("flags", C.c_uint32),
                 ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
-                ("upadd", C.c_void_p), ("y", C.c_void_p)]
+                ("upadd", C.c_void_p), ("y", C.c_void_p),
+                ("x2", C.c_void_p), ("Cin2", C.c_int32), ("Hin2", C.c_int32), ("Win2", C.c_int32),
+                ("stride2", C.c_int32)]
 
 
 _SIGS = {

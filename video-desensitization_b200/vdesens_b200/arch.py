@@ -40,6 +40,11 @@ class ConvSpec:
     stride: int
     pad: int
     relu: bool                # ReLU applied in the epilogue (after residual add when there is one)
+    # fused second K segment (bottleneck block 0: conv3 + downsample projection share one accumulator)
+    wkey2: Optional[str] = None
+    bnkey2: Optional[str] = None
+    cin2: int = 0
+    stride2: int = 1
 
 
 @dataclass
@@ -49,6 +54,7 @@ class Op:
     src: str = ""             # input buffer name
     dst: str = ""             # output buffer name
     dst_coff: int = 0         # channel offset inside dst (SSH concat slices)
+    src2: str = ""            # input of the fused 1x1 projection (conv.wkey2), read with conv.stride2
     residual: str = ""        # buffer added before ReLU (bottleneck identity), same shape as dst
     upsample_add: str = ""    # buffer (half resolution) nearest-upsampled and added AFTER ReLU (FPN top-down)
     level: int = -1           # heads: pyramid level 0..2
@@ -89,8 +95,11 @@ def level_offsets(h: int, w: int) -> List[int]:
     return offs
 
 
-def build_graph():
-    """Returns (convs, ops, bufs).  Buffer 'x0' is the ingested frame (3 real channels)."""
+def build_graph(fuse_downsample: bool = True):
+    """Returns (convs, ops, bufs).  Buffer 'x0' is the ingested frame (3 real channels).
+    With fuse_downsample the projection shortcut of each stage's first bottleneck (torchvision
+    Bottleneck.downsample) is not a separate convolution: its 1x1 GEMM accumulates into conv3's
+    accumulator (same output pixels), which removes one write and one read of the widest tensors."""
     convs: List[ConvSpec] = []
     ops: List[Op] = []
     bufs: List[BufSpec] = []
@@ -100,10 +109,13 @@ def build_graph():
         return name
 
     def conv(name, wkey, bnkey, cin, cout, k, stride, pad, relu, src, dst, biaskey=None,
-             dst_coff=0, residual="", upsample_add=""):
+             dst_coff=0, residual="", upsample_add="", second=None):
         c = ConvSpec(name, wkey, bnkey, biaskey, cin, cout, k, stride, pad, relu)
+        src2 = ""
+        if second is not None:
+            c.wkey2, c.bnkey2, c.cin2, c.stride2, src2 = second
         convs.append(c)
-        ops.append(Op("conv", c, src, dst, dst_coff, residual, upsample_add))
+        ops.append(Op("conv", c, src, dst, dst_coff, src2, residual, upsample_add))
 
     buf("x0", 3, 1)
     buf("c1", 64, 2)
@@ -124,14 +136,18 @@ def build_graph():
             out = buf(f"{lname}.{b}.out", planes * 4, out_stride)
             conv(f"{p}.conv1", f"{p}.conv1.weight", f"{p}.bn1", cur_ch, planes, 1, 1, 0, True, cur, t1)
             conv(f"{p}.conv2", f"{p}.conv2.weight", f"{p}.bn2", planes, planes, 3, s, 1, True, t1, t2)
-            if b == 0:
-                idn = buf(f"{lname}.{b}.ds", planes * 4, out_stride)
-                conv(f"{p}.downsample", f"{p}.downsample.0.weight", f"{p}.downsample.1", cur_ch,
-                     planes * 4, 1, s, 0, False, cur, idn)
+            if b == 0 and fuse_downsample:
+                conv(f"{p}.conv3", f"{p}.conv3.weight", f"{p}.bn3", planes, planes * 4, 1, 1, 0, True, t2, out,
+                     second=(f"{p}.downsample.0.weight", f"{p}.downsample.1", cur_ch, s, cur))
             else:
-                idn = cur
-            conv(f"{p}.conv3", f"{p}.conv3.weight", f"{p}.bn3", planes, planes * 4, 1, 1, 0, True,
-                 t2, out, residual=idn)
+                if b == 0:
+                    idn = buf(f"{lname}.{b}.ds", planes * 4, out_stride)
+                    conv(f"{p}.downsample", f"{p}.downsample.0.weight", f"{p}.downsample.1", cur_ch,
+                         planes * 4, 1, s, 0, False, cur, idn)
+                else:
+                    idn = cur
+                conv(f"{p}.conv3", f"{p}.conv3.weight", f"{p}.bn3", planes, planes * 4, 1, 1, 0, True,
+                     t2, out, residual=idn)
             cur, cur_ch, cur_stride = out, planes * 4, out_stride
         feats[lname] = cur
 
@@ -186,7 +202,7 @@ def state_dict_spec():
     """[(key, shape, kind)] for every tensor of the reference state_dict (456 entries, 27,293,600
     parameters).  kind in {conv_backbone, conv_neck, bn_weight, bn_bias, bn_mean, bn_var,
     bn_count, head_weight, head_bias}."""
-    convs, _, _ = build_graph()
+    convs, _, _ = build_graph(fuse_downsample=False)
     spec = []
     for c in convs:
         kind = "conv_backbone" if c.name.startswith("body.") else "conv_neck"

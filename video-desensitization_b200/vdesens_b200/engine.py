@@ -92,6 +92,11 @@ class DetectorEngine:
                     flags |= _lib.VD_CONV_RESIDUAL
                     res = self.buf[op.residual]
                     assert tuple(res.shape) == (B, hout, wout, c.cout)
+                if op.src2:
+                    flags |= _lib.VD_CONV_DUAL
+                    x2 = self.buf[op.src2]
+                    d.x2 = x2.data_ptr()
+                    d.Hin2, d.Win2, d.Cin2, d.stride2 = x2.shape[1], x2.shape[2], x2.shape[3], c.stride2
                 if op.upsample_add:
                     flags |= _lib.VD_CONV_UPADD
                     up = self.buf[op.upsample_add]

@@ -62,7 +62,7 @@ def ingest_nchw_f32(frames, H, W):
 
 
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None):
+           out_f32=False, x0_hw=None, x2=None, stride2=1):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: bf16 (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout)."""
     lib = _lib.lib()
@@ -93,6 +93,10 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
         d.up_H, d.up_W = upadd.shape[1], upadd.shape[2]
     if out_f32:
         flags |= _lib.VD_CONV_OUT_F32
+    if x2 is not None:        # fused 1x1 projection of a second tensor (weights concatenated along K)
+        flags |= _lib.VD_CONV_DUAL
+        d.x2 = x2.data_ptr()
+        d.Hin2, d.Win2, d.Cin2, d.stride2 = x2.shape[1], x2.shape[2], x2.shape[3], stride2
     d.flags = flags
     d.x, d.w, d.bias = x.data_ptr(), w_packed.data_ptr(), bias.data_ptr()
     d.residual = residual.data_ptr() if residual is not None else None

@@ -10,19 +10,20 @@ import torch
 from . import arch
 
 
-def _fold(sd, c: arch.ConvSpec):
-    w = np.asarray(sd[c.wkey], np.float64)
-    if c.bnkey:
-        g = np.asarray(sd[c.bnkey + ".weight"], np.float64)
-        beta = np.asarray(sd[c.bnkey + ".bias"], np.float64)
-        mean = np.asarray(sd[c.bnkey + ".running_mean"], np.float64)
-        var = np.asarray(sd[c.bnkey + ".running_var"], np.float64)
+def _fold(sd, c: arch.ConvSpec, second: bool = False):
+    wkey, bnkey = (c.wkey2, c.bnkey2) if second else (c.wkey, c.bnkey)
+    w = np.asarray(sd[wkey], np.float64)
+    if bnkey:
+        g = np.asarray(sd[bnkey + ".weight"], np.float64)
+        beta = np.asarray(sd[bnkey + ".bias"], np.float64)
+        mean = np.asarray(sd[bnkey + ".running_mean"], np.float64)
+        var = np.asarray(sd[bnkey + ".running_var"], np.float64)
         scale = g / np.sqrt(var + arch.BN_EPS)
         w = w * scale[:, None, None, None]
         b = beta - mean * scale
     else:
         b = np.zeros(w.shape[0], np.float64)
-    if c.biaskey:
+    if c.biaskey and not second:
         b = b + np.asarray(sd[c.biaskey], np.float64)
     return w.astype(np.float32), b.astype(np.float32)
 
@@ -52,6 +53,10 @@ def pack_all(sd):
             mat = wp.reshape(c.cout, -1)
         else:
             mat = np.transpose(w, (0, 2, 3, 1)).reshape(c.cout, -1)
+        if c.wkey2:      # fused projection: [conv3 K | downsample K], biases add
+            w2, b2 = _fold(sd, c, second=True)
+            mat = np.concatenate([mat, w2.reshape(c.cout, -1)], axis=1)
+            b = b + b2
         packed[c.name] = (torch.from_numpy(np.ascontiguousarray(mat)).to(torch.bfloat16),
                           torch.from_numpy(b.copy()))
     for lvl in range(3):
