@@ -32,12 +32,19 @@ def make_bn_calib():
     frames = synth.synthetic_clip(4, 480, 640, base_seed=7000)
     x, _ = ro.preprocess(frames, (480, 640))
     ro.forward(sd, x, calibrate=True)
-    _, cls, _ = ro.forward(sd, x, softmax=False)
-    d = cls[..., 1] - cls[..., 0]
-    offs = arch.level_offsets(480, 640) + [arch.num_anchors(480, 640)]
     out = {k: v.numpy() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    # class-bias shifts: quantiles of the face-vs-background logit difference per pyramid level, estimated on
+    # eight 1080p frames (the coarse level has only 4080 anchors per frame, so small samples are too noisy)
+    ds = [[], [], []]
+    offs = arch.level_offsets(1080, 1920) + [arch.num_anchors(1080, 1920)]
+    for i in range(8):
+        xf, _ = ro.preprocess([synth.synthetic_frame(1080, 1920, 7100 + i)], (1080, 1920))
+        _, cls, _ = ro.forward(sd, xf, softmax=False)
+        d = (cls[..., 1] - cls[..., 0])[0]
+        for l in range(3):
+            ds[l].append(d[offs[l]:offs[l + 1]])
     for name, rate in RATES.items():
-        sh = [-float(torch.quantile(d[:, offs[l]:offs[l + 1]].flatten(), 1 - rate)) for l in range(3)]
+        sh = [-float(np.quantile(torch.cat(ds[l]).numpy().astype(np.float64), 1 - rate)) for l in range(3)]
         out["shift." + name] = np.array(sh, np.float32)
     os.makedirs(os.path.dirname(synth.BN_CALIB_FILE), exist_ok=True)
     np.savez_compressed(synth.BN_CALIB_FILE, **out)

@@ -517,3 +517,53 @@ def test_streaming_pipeline_matches_oracle_compositing(sd_np):
         for i in range(len(batches[k])):
             allb = [tuple(int(v) for v in b) for b in boxes[i]] + plates[k][i]
             assert np.array_equal(out[i], co.composite(batches[k][i], allb, "gauss", ksize=15)), (k, i)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs as parity cases
+# ------------------------------------------------------------------------------------------------
+def test_config5_dense_rois_mosaic():
+    """C5: 1080p, ~200 faces + 50 injected plate boxes per frame, mosaic mode.  The boxes the detector returns
+    (+ plates, in reference order: faces then plates) composited on the device == the reference loop on CPU."""
+    from vdesens_b200.engine import DetectorEngine
+    from vdesens_b200.pipeline import Anonymizer
+    H, W, B = 1080, 1920, 2
+    sd = synth.synthetic_state_dict(0, face_rate="dense")
+    eng = DetectorEngine(sd, B, H, W, device=DEV, confidence=0.5, nms_iou=0.4)
+    frames = [synth.synthetic_frame(H, W, 3000 + i) for i in range(B)]
+    plates = [synth.synthetic_boxes(50, H, W, seed=60 + i) for i in range(B)]
+    out, boxes = Anonymizer(eng, "mosaic", mosaic_level=8).process_batch(frames, plates)
+    for i in range(B):
+        assert 60 <= len(boxes[i]) <= 600, len(boxes[i])
+        allb = [tuple(int(v) for v in b) for b in boxes[i]] + plates[i]
+        want = co.composite(frames[i], allb, "mosaic", 8)
+        assert np.array_equal(out[i], want), f"frame {i}: {(out[i] != want).sum()} bytes differ"
+        # descending score order is part of the contract (sequential compositing depends on it)
+    rows, counts = eng.fetch_results()
+    for i in range(B):
+        sc = rows[i, :counts[i], 4]
+        assert np.all(sc[:-1] >= sc[1:])
+
+
+def test_config3_4k_large_roi_blur(sd_np):
+    """C3: 4K input (multi-scale FPN at 270x480 / 135x240 / 68x120), Gaussian k = 99 on >= 512^2 ROIs."""
+    from vdesens_b200 import weights
+    from vdesens_b200.engine import DetectorEngine
+    H, W = 2160, 3840
+    frame = synth.synthetic_frame(H, W, 4000)
+    eng = DetectorEngine(sd_np, 1, H, W, device=DEV, confidence=0.5, nms_iou=0.4, cand_cap=8192, max_det=4096)
+    dev = torch.from_numpy(frame[None]).to(DEV)
+    eng.set_frames(dev)
+    eng.forward()
+    loc, cls, ldm = (t.cpu() for t in eng.head_tensors())
+    assert loc.shape[1] == arch.num_anchors(H, W) == 340320
+    x, _ = ro.preprocess([frame], (H, W))
+    eloc, ecls, eldm = ro.forward_bf16_emulated(weights.pack_all(sd_np), x)
+    assert float((loc - eloc).abs().max()) <= 0.08 and float((cls - ecls).abs().max()) <= 0.08
+    assert float((loc - eloc).pow(2).mean().sqrt()) <= 0.01
+    # large-ROI blur, k = 99, boxes crossing the border and overlapping
+    big = [(100, 200, 900, 1000), (600, 500, 1500, 1300), (-50, 1500, 700, 2300), (3300, -20, 3900, 700)]
+    f2 = torch.from_numpy(frame.copy()).to(DEV)
+    from vdesens_b200 import ops as _ops
+    _ops.composite([f2], [big], "gauss", ksize=99)
+    assert np.array_equal(f2.cpu().numpy(), co.composite(frame, big, "gauss", ksize=99))

@@ -102,7 +102,8 @@ __host__ Ws carve(void* p0, int B, int maxb, size_t total_bytes, size_t* flag_by
 }
 
 // ---------------------------------------------------------------------------------------------
-// plan: clip boxes, count tiles, prefix sums.  One CTA; frames are walked sequentially.
+// plan: clip boxes, count tiles, prefix sums.  One CTA per frame; frame_prefix[f+1] holds the item COUNT of
+// frame f (the run kernel only needs per-frame counts).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float* __restrict__ det_rows,
@@ -115,11 +116,14 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_total = 0;
-    ws.hdr->ticket = 0;
-    ws.hdr->frame_prefix[0] = 0;
+    if (blockIdx.x == 0) {
+      ws.hdr->ticket = 0;
+      ws.hdr->frame_prefix[0] = 0;
+    }
   }
   __syncthreads();
-  for (int f = 0; f < B; ++f) {
+  {
+    const int f = blockIdx.x;
     const vd_frame_t fr = frames[f];
     const int nd = det_rows ? min(det_count[f], max_det) : 0;
     const int ne = ext_boxes ? min(ext_count[f], max_ext) : 0;
@@ -198,12 +202,9 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
     }
     if (tid == 0) {
       if (overflow || nd + ne > maxb) atomicOr(status, VD_STAT_WORK_OVERFLOW);
-      s_total += overflow ? 0u : item_carry;
-      ws.hdr->frame_prefix[f + 1] = s_total;
+      ws.hdr->frame_prefix[f + 1] = overflow ? 0u : item_carry;       // item count of this frame
     }
-    __syncthreads();
   }
-  if (tid == 0) ws.hdr->total_items = s_total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -276,21 +277,30 @@ __device__ __forceinline__ void wait_writers(const BoxMeta* fm, const int* done,
 template <int M>
 __device__ __forceinline__ void dp4a_run(const uint32_t* __restrict__ S, const uint32_t* __restrict__ qa, int kw,
                                          uint32_t (&acc)[M]) {
-  uint32_t win[M];
+  // register window of M + 3 words, advanced four tap-words per iteration (the tap vectors are zero padded
+  // up to KW_MAX, so running kw up to the next multiple of four is harmless)
+  uint32_t win[M + 3];
 #pragma unroll
-  for (int i = 0; i < M; ++i) { acc[i] = 0; win[i] = S[i]; }
-  for (int j = 0; j < kw; ++j) {
-    const uint32_t q = qa[j];
+  for (int i = 0; i < M; ++i) acc[i] = 0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) acc[i] = __dp4a(win[i], q, acc[i]);
-    // slide the window by one word
+  for (int i = 0; i < M + 3; ++i) win[i] = S[i];
+  for (int j = 0; j < kw; j += 4) {
+    const uint32_t q0 = qa[j], q1 = qa[j + 1], q2 = qa[j + 2], q3 = qa[j + 3];
 #pragma unroll
-    for (int i = 0; i + 1 < M; ++i) win[i] = win[i + 1];
-    win[M - 1] = S[M + j];
+    for (int i = 0; i < M; ++i) {
+      acc[i] = __dp4a(win[i], q0, acc[i]);
+      acc[i] = __dp4a(win[i + 1], q1, acc[i]);
+      acc[i] = __dp4a(win[i + 2], q2, acc[i]);
+      acc[i] = __dp4a(win[i + 3], q3, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i + 4 < M + 3; ++i) win[i] = win[i + 4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) win[M - 1 + i] = S[M + 3 + j + i];
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int mode, int ksize, Taps taps,
                      uint32_t* __restrict__ status, Ws ws) {
   extern __shared__ __align__(16) uint8_t dsm[];
@@ -300,12 +310,12 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
   __shared__ uint16_t s_q[256];
   __shared__ uint32_t s_qa[4][KW_MAX];
   const int tid = threadIdx.x;
-  for (int i = tid; i <= B; i += kThreads) s_fprefix[i] = ws.hdr->frame_prefix[i];
+  for (int i = tid; i < B; i += kThreads) s_fprefix[i] = ws.hdr->frame_prefix[i + 1];   // items of frame i
   s_q[tid] = taps.q[tid];
   if (tid < 4 * KW_MAX) s_qa[tid / KW_MAX][tid % KW_MAX] = taps.qa[tid / KW_MAX][tid % KW_MAX];
   __syncthreads();
   unsigned int max_items = 0;
-  for (int i = 0; i < B; ++i) max_items = max(max_items, s_fprefix[i + 1] - s_fprefix[i]);
+  for (int i = 0; i < B; ++i) max_items = max(max_items, s_fprefix[i]);
   const unsigned int total = max_items * static_cast<unsigned int>(B);
   const int r = ksize >> 1;
   const int kw = taps.kw;
@@ -318,7 +328,7 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     if (t >= total) break;
     const int f = static_cast<int>(t % static_cast<unsigned int>(B));
     const unsigned int local = t / static_cast<unsigned int>(B);
-    if (local >= s_fprefix[f + 1] - s_fprefix[f]) continue;      // this frame has fewer items
+    if (local >= s_fprefix[f]) continue;                           // this frame has fewer items
     const BoxMeta* fm = ws.meta + static_cast<size_t>(f) * maxb;
     int* done = ws.done + static_cast<size_t>(f) * ws.items_cap;
     // owner box of the item: warp-parallel search over the (non-decreasing) item_base array — the last
@@ -472,13 +482,19 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         const int spanw = (span + 3 + 4 * KW_MAX) / 4;       // words per row incl. slack read by the last window
         uint32_t* planes = reinterpret_cast<uint32_t*>(dsm); // [3][GA_H][spanw]
         uint8_t* pb = dsm;
-        for (int i = tid; i < rows * span; i += kThreads) {
-          const int ly = i / span, c = i - ly * span;
-          const int xs = reflect101(x0 - r + c, bw);
-          const uint8_t* p = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + (m.x1 + xs) * 3;
-          pb[((0 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p);
-          pb[((1 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p + 1);
-          pb[((2 * GA_H + ly) * spanw) * 4 + c] = __ldcg(p + 2);
+        for (int ly = 0; ly < rows; ++ly) {
+          const uint8_t* rowp = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + m.x1 * 3;
+          uint8_t* d0 = pb + (0 * GA_H + ly) * spanw * 4;
+          uint8_t* d1 = pb + (1 * GA_H + ly) * spanw * 4;
+          uint8_t* d2 = pb + (2 * GA_H + ly) * spanw * 4;
+          for (int c = tid; c < span; c += kThreads) {
+            int xs = x0 - r + c;
+            if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
+            const uint8_t* p = rowp + xs * 3;
+            d0[c] = __ldcg(p);
+            d1[c] = __ldcg(p + 1);
+            d2[c] = __ldcg(p + 2);
+          }
         }
         __syncthreads();
         // thread -> (channel, a, row, half): 16 outputs x = 64*half + 4m + a
@@ -530,12 +546,19 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         colw |= 1;
         uint8_t* hi = dsm;                                  // [GB_E][colw*4]
         uint8_t* lo = dsm + GB_E * colw * 4;
-        for (int i = tid; i < span * ne; i += kThreads) {
-          const int ly = i / ne, e = i - ly * ne;
-          const int ys = reflect101(y0 - r + ly, bh);
-          const uint16_t v = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
-          hi[e * colw * 4 + ly] = static_cast<uint8_t>(v >> 8);
-          lo[e * colw * 4 + ly] = static_cast<uint8_t>(v & 0xFF);
+        {
+          const int e = tid & (GB_E - 1);
+          if (e < ne) {
+            uint8_t* hcol = hi + e * colw * 4;
+            uint8_t* lcol = lo + e * colw * 4;
+            for (int ly = tid / GB_E; ly < span; ly += kThreads / GB_E) {
+              int ys = y0 - r + ly;
+              if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+              const uint16_t v = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
+              hcol[ly] = static_cast<uint8_t>(v >> 8);
+              lcol[ly] = static_cast<uint8_t>(v & 0xFF);
+            }
+          }
         }
         __syncthreads();
         // thread -> (e, a): 16 outputs y = 4m + a
@@ -663,7 +686,7 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   size_t flag_bytes = 0;
   const Ws ws = carve(workspace, B, maxb, workspace_bytes, &flag_bytes);
   VD_CHECK_CUDA(cudaMemsetAsync(ws.done, 0, flag_bytes, st));
-  composite_plan_kernel<<<1, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
+  composite_plan_kernel<<<B, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
                                             maxb, mode, mosaic_level, status, ws);
   VD_LAUNCH_CHECK();
   const int r = ksize >> 1;
