@@ -66,9 +66,9 @@ typedef struct vd_frame {
   int32_t reserved;
 } vd_frame_t;
 
-/* Layout of the ingested tensor "x0": [B][H][Wp][8] bf16, channels 0..2 = pixel - mean,
- * channels 3..7 = 0, pixel column x stored at column x+3, columns outside [3, W+3) are zero.
- * Wp = vd_x0_pitch(W).  conv1 reads it through a sliding-window tensor map (8 taps x 8 ch). */
+/* Layout of the ingested tensor "x0": [B][H][Wp][4] bf16, channels 0..2 = pixel - mean,
+ * channel 3 = 0, pixel column x stored at column x+3, columns outside [3, W+3) are zero.
+ * Wp = vd_x0_pitch(W).  conv1 reads it through a sliding-window tensor map (8 taps x 4 ch = 64 B). */
 int vd_x0_pitch(int W);
 
 /* Letterboxes each frame to HxW (cv2 INTER_LINEAR uint8 fixed-point arithmetic, grey 128 pad,
@@ -108,7 +108,7 @@ typedef struct vd_conv_desc {
   int32_t up_H, up_W;        /* extent of the UPADD source (half resolution) */
   uint32_t flags;
   const void* x;             /* [dev] input activations, bf16 NHWC (or x0) */
-  const void* w;             /* [dev] packed weights bf16 [Cout][R][S][Cin] (BN folded) */
+  const void* w;             /* [dev] packed weights bf16 [Cout][R][S][Cin] (BN folded); IN_X0: [64][7][8 taps][4 ch] */
   const float* bias;         /* [dev] fp32 [Cout] (BN folded / conv bias) */
   const void* residual;      /* [dev] bf16 [B][Hout][Wout][Cout] or NULL */
   const void* upadd;         /* [dev] bf16 [B][up_H][up_W][Cout] or NULL */

@@ -293,7 +293,7 @@ def forward_bf16_emulated(packed, x, capture=None):
                 c = op.conv
                 wp, b = packed[c.name]
                 if c.name == "body.conv1":
-                    w = wp.float().view(c.cout, 7, 8, 8)[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()
+                    w = wp.float().view(c.cout, 7, 8, 4)[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()
                     y = F.conv2d(bufs[op.src], w, b, c.stride, c.pad)
                 elif c.wkey2:       # fused projection: both GEMMs share the fp32 accumulator on the device
                     k1 = c.k * c.k * c.cin

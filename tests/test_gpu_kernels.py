@@ -186,7 +186,7 @@ def test_conv1_on_ingest_layout(ops, hw):
     g = torch.Generator(device="cpu").manual_seed(9)
     w = (torch.randn((64, 3, 7, 7), generator=g) / 12.0)
     bias = torch.randn((64,), generator=g).to(DEV)
-    wp = torch.zeros((64, 7, 8, 8))
+    wp = torch.zeros((64, 7, 8, 4))
     wp[:, :, :7, :3] = w.permute(0, 2, 3, 1)
     wp = wp.reshape(64, -1).to(torch.bfloat16).to(DEV)
     got = ops.conv2d(x0, wp, bias, 7, 2, 3, relu=True, x0_hw=(H, W))

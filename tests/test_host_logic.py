@@ -67,8 +67,8 @@ def test_graph_bookkeeping():
     assert abs(flops / 1e9 - 449.71) < 0.2
     sd = synth.synthetic_state_dict(0)
     packed = weights.pack_all(sd)
-    assert packed["body.conv1"][0].shape == (64, 448) and packed["heads.1"][0].shape == (32, 256)
-    w0 = packed["body.conv1"][0].float().view(64, 7, 8, 8)
+    assert packed["body.conv1"][0].shape == (64, 224) and packed["heads.1"][0].shape == (32, 256)
+    w0 = packed["body.conv1"][0].float().view(64, 7, 8, 4)
     assert float(w0[:, :, 7].abs().max()) == 0 and float(w0[..., 3:].abs().max()) == 0
     # BN fold: folded conv == conv + BN on a random input (fp32 check of the algebra, not of the device)
     c = next(c for c in convs if c.name == "body.layer2.0.conv2")

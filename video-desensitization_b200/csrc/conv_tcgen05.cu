@@ -64,10 +64,12 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 232448;        // 227 KB per CTA on sm_100
 constexpr int kWresMaxBytes = 72 * 1024;   // resident-weight limit (3x3 64->64 = 72 KB)
 
-template <int BN, bool RES>
+// ROWB = bytes of one operand row (one K block): 128 (64 bf16, SWIZZLE_128B) everywhere except the stem conv1,
+// whose K block is one filter row of 8 taps x 4 channels = 64 bytes (SWIZZLE_64B).
+template <int BN, bool RES, int ROWB = 128>
 struct ConvCfg {
-  static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = BN * ROWB;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 384;
   static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
@@ -105,12 +107,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
-template <int BN, bool RES>
-__global__ void __launch_bounds__((ConvCfg<BN, RES>::THREADS), 1)
+template <int BN, bool RES, int ROWB>
+__global__ void __launch_bounds__((ConvCfg<BN, RES, ROWB>::THREADS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ CUtensorMap tmA2, const ConvKParams p) {
-  using Cfg = ConvCfg<BN, RES>;
+  using Cfg = ConvCfg<BN, RES, ROWB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
@@ -181,7 +183,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aphase = 0;
     if (p.wres && elect_one()) {                      // weights: loaded once, reused by every tile
       mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * 64, 0);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * (ROWB / 2), 0);
     }
     __syncwarp();
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES));
@@ -239,7 +241,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA2, &full[stage], (kb + j - p.kb1) * 64,
                           tx * p.TW * p.stride2, ty * p.TH * p.stride2, b0);
             if (!p.wres)
-              tma_load_2d(sB + (stage * KPS + j) * Cfg::B_BYTES, &tmB, &full[stage], (kb + j) * 64, ncol);
+              tma_load_2d(sB + (stage * KPS + j) * Cfg::B_BYTES, &tmB, &full[stage], (kb + j) * (ROWB / 2), ncol);
           }
           if (++cb == p.cin_blocks) {            // K order (r, s, cin block): advance for every lane alike
             cb = 0;
@@ -263,7 +265,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                (static_cast<uint32_t>(128 >> 4) << 24);
     // descriptor words: lo = start>>4 | LBO(1)<<16 ; hi = SBO>>4 | version(1)<<14 | SWIZZLE_128B(2)<<29
-    constexpr uint32_t hi_std = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t hi_std = (static_cast<uint32_t>(8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    constexpr int MMAS = ROWB / 32;             // K = 16 bf16 = 32 bytes per tcgen05.mma
     const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
     int stage = 0;
@@ -323,9 +326,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   b_lo0 + static_cast<uint32_t>((p.wres ? kb + j : stage * KPS + j) * (Cfg::B_BYTES >> 4));
               // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
               umma_bf16_words(d_tmem, al, hi_std, bl, hi_std, idesc, static_cast<uint32_t>((kb + j) != 0));
-              umma_bf16_words(d_tmem, al + 2, hi_std, bl + 2, hi_std, idesc, 1u);
-              umma_bf16_words(d_tmem, al + 4, hi_std, bl + 4, hi_std, idesc, 1u);
-              umma_bf16_words(d_tmem, al + 6, hi_std, bl + 6, hi_std, idesc, 1u);
+#pragma unroll
+              for (int q = 1; q < MMAS; ++q)
+                umma_bf16_words(d_tmem, al + 2 * q, hi_std, bl + 2 * q, hi_std, idesc, 1u);
             }
             umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
             if (kb + KPS >= KB) umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
@@ -355,7 +358,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tb = m / p.tiles_y;
         for (int ch = 0; ch < NCHUNK_R; ++ch) {
           mbar_wait(&rempty[slot], rphase ^ 1u);
-          mbar_expect_tx(&rfull[slot], static_cast<uint32_t>(p.a_bytes));
+          mbar_expect_tx(&rfull[slot], static_cast<uint32_t>(p.rows_used * 128));
           tma_load_4d(sRes + slot * (128 * 128), &tmR, &rfull[slot], n_tile * BN + ch * 64, tx * p.TW, ty * p.TH,
                       tb * p.NB);
           if (++slot == Cfg::RES_SLOTS) {
@@ -557,9 +560,9 @@ struct vd_conv_plan {
   vd_conv_desc_t desc;
 };
 
-template <int BN, bool RES>
+template <int BN, bool RES, int ROWB = 128>
 static void plan_smem(vd_conv_plan* pl) {
-  using Cfg = ConvCfg<BN, RES>;
+  using Cfg = ConvCfg<BN, RES, ROWB>;
   ConvKParams& k = pl->kp;
   const int KB = k.R * k.S * k.cin_blocks + k.kb2;
   const int avail = kSmemBudget - Cfg::FIXED_BYTES;
@@ -674,7 +677,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
 
   int sw, sh, pw, ph, R, S, cin_blocks;
   if (x0) {
-    // conv1 7x7/2 p3 on the ingest layout: each filter row is one K block of 8 taps x 8 channels;
+    // conv1 7x7/2 p3 on the ingest layout: each filter row is one K block of 8 taps x 4 channels (64 bytes);
     // the x stride/pad are baked into the sliding-window tensor map.
     R = 7; S = 1; cin_blocks = 1; sh = 2; ph = 3; sw = 1; pw = 0;
     VD_REQUIRE(d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3, "IN_X0 conv must be 7x7 s2 p3");
@@ -703,7 +706,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.n_tiles = d->Cout / BN;
   k.num_tiles = k.tiles_x * k.tiles_y * k.tiles_b * k.n_tiles;
   k.rows_used = k.TW * k.TH * k.NB;
-  k.a_bytes = k.rows_used * 128;
+  k.a_bytes = k.rows_used * (x0 ? 64 : 128);
   k.B = d->B; k.Hout = d->Hout; k.Wout = d->Wout; k.Cout = d->Cout;
   k.R = R; k.S = S; k.cin_blocks = cin_blocks;
   k.kb1 = R * S * cin_blocks;
@@ -735,11 +738,11 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   cuuint32_t box[4], estr[4];
   if (x0) {
     const int Wp = vd_x0_pitch(d->Win);
-    gdim[0] = 64; gdim[1] = static_cast<cuuint64_t>(d->Wout); gdim[2] = static_cast<cuuint64_t>(d->Hin);
+    gdim[0] = 32; gdim[1] = static_cast<cuuint64_t>(d->Wout); gdim[2] = static_cast<cuuint64_t>(d->Hin);
     gdim[3] = static_cast<cuuint64_t>(d->B);
-    gstr[0] = 32;                                         // next output column = 2 pixels * 16 B
-    gstr[1] = static_cast<cuuint64_t>(Wp) * 16;
-    gstr[2] = static_cast<cuuint64_t>(Wp) * 16 * d->Hin;
+    gstr[0] = 16;                                         // next output column = 2 pixels * 8 B
+    gstr[1] = static_cast<cuuint64_t>(Wp) * 8;
+    gstr[2] = static_cast<cuuint64_t>(Wp) * 8 * d->Hin;
   } else {
     gdim[0] = static_cast<cuuint64_t>(d->Cin); gdim[1] = static_cast<cuuint64_t>(d->Win);
     gdim[2] = static_cast<cuuint64_t>(d->Hin); gdim[3] = static_cast<cuuint64_t>(d->B);
@@ -747,12 +750,13 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     gstr[1] = gstr[0] * d->Win;
     gstr[2] = gstr[1] * d->Hin;
   }
-  box[0] = 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
+  box[0] = x0 ? 32 : 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
   box[3] = static_cast<cuuint32_t>(k.NB);
   if (k.patch) { box[1] = static_cast<cuuint32_t>(k.PW); box[2] = static_cast<cuuint32_t>(k.PH); }
   estr[0] = 1; estr[1] = static_cast<cuuint32_t>(sw); estr[2] = static_cast<cuuint32_t>(sh); estr[3] = 1;
   CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vd_set_error("cuTensorMapEncodeTiled(A) failed: CUresult %d (dims %llu %llu %llu %llu, box %u %u %u %u)", (int)r,
@@ -780,13 +784,15 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     }
   }
   // ---- B: weights [Cout][Ktot] ----
-  const cuuint64_t Ktot = (static_cast<cuuint64_t>(R) * S * cin_blocks + static_cast<cuuint64_t>(k.kb2)) * 64;
+  const cuuint64_t kelems = x0 ? 32 : 64;               // elements per K block
+  const cuuint64_t Ktot = (static_cast<cuuint64_t>(R) * S * cin_blocks + static_cast<cuuint64_t>(k.kb2)) * kelems;
   cuuint64_t wdim[2] = {Ktot, static_cast<cuuint64_t>(d->Cout)};
   cuuint64_t wstr[1] = {Ktot * 2};
-  cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(BN)};
+  cuuint32_t wbox[2] = {static_cast<cuuint32_t>(kelems), static_cast<cuuint32_t>(BN)};
   cuuint32_t wes[2] = {1, 1};
   r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), wdim, wstr, wbox, wes,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vd_set_error("cuTensorMapEncodeTiled(B) failed: CUresult %d", (int)r);
@@ -852,7 +858,8 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
   {
     const bool res = (d->flags & VD_CONV_RESIDUAL) != 0;
-    switch (BN) {
+    if (x0) plan_smem<64, false, 64>(pl);
+    else switch (BN) {
       case 32: plan_smem<32, false>(pl); break;
       case 64: res ? plan_smem<64, true>(pl) : plan_smem<64, false>(pl); break;
       case 128: res ? plan_smem<128, true>(pl) : plan_smem<128, false>(pl); break;
@@ -885,16 +892,16 @@ extern "C" int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, i
   return VD_OK;
 }
 
-template <int BN, bool RES>
+template <int BN, bool RES, int ROWB = 128>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, RES>;
+  using Cfg = ConvCfg<BN, RES, ROWB>;
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBudget));
     attr_set = true;
   }
-  conv_igemm_kernel<BN, RES><<<pl->grid, Cfg::THREADS, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
+  conv_igemm_kernel<BN, RES, ROWB><<<pl->grid, Cfg::THREADS, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->tmR,
                                                                               pl->tmA2, pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
@@ -904,6 +911,7 @@ extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
   VD_REQUIRE(plan, "vd_conv_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool res = (plan->kp.flags & VD_CONV_RESIDUAL) != 0;
+  if (plan->kp.flags & VD_CONV_IN_X0) return launch_conv<64, false, 64>(plan, st);
   switch (plan->BN) {
     case 32: return launch_conv<32, false>(plan, st);
     case 64: return res ? launch_conv<64, true>(plan, st) : launch_conv<64, false>(plan, st);

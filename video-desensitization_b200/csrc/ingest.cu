@@ -8,7 +8,7 @@
 //
 // The bilinear resize restates cv2's fixed-point path bit-for-bit: coefficients
 // rint(f*2048), horizontal sums in int32, vertical (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
-// HBM-bound: 3 B read + 16 B written per output pixel (x0 layout), coalesced 16-byte stores.
+// HBM-bound: 3 B read + 8 B written per output pixel (x0 layout), coalesced vector stores.
 #include "common.cuh"
 
 namespace {
@@ -68,37 +68,35 @@ __device__ __forceinline__ void letter_pixel(const vd_frame_t& fr, const LetterG
   }
 }
 
-// x0 layout: [B][H][Wp][8] bf16, pixel x at column x+3.  One thread = one output pixel = one 16 B store.
+// x0 layout: [B][H][Wp][4] bf16, pixel x at column x+3.  One thread = one output pixel = one 8 B store.
 __global__ void __launch_bounds__(256)
-ingest_x0_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp, float m0,
+ingest_x0_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__ x0, int H, int W, int Wp, float m0,
                  float m1, float m2) {
   const int b = blockIdx.z;
   const int y = blockIdx.y;
   const vd_frame_t fr = frames[b];
   const LetterGeom g = letter_geom(fr.h, fr.w, H, W);
-  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * Wp;
+  uint2* row = x0 + (static_cast<size_t>(b) * H + y) * Wp;
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
     int v[3];
     letter_pixel(fr, g, y, x, v);
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16x2(static_cast<float>(v[0]) - m0, static_cast<float>(v[1]) - m1);
     o.y = pack_bf16x2(static_cast<float>(v[2]) - m2, 0.f);
-    o.z = 0u;
-    o.w = 0u;
     row[x + 3] = o;
   }
 }
 
 // fast path: frame size == network input (BASELINE configs 2-5): no resize, no pad.
-// Each thread converts 4 pixels: 12 B in (3 x u32), 64 B out (4 x uint4).
+// Each thread converts 4 pixels: 12 B in (3 x u32), 32 B out (4 x uint2).
 __global__ void __launch_bounds__(256)
-ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp,
+ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__ x0, int H, int W, int Wp,
                           float m0, float m1, float m2) {
   const int b = blockIdx.z;
   const int y = blockIdx.y;
   const vd_frame_t fr = frames[b];
   const uint8_t* src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
-  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * Wp + 3;
+  uint2* row = x0 + (static_cast<size_t>(b) * H + y) * Wp + 3;
   const int groups = W >> 2;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
@@ -114,22 +112,18 @@ ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint4* __restri
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      uint4 o;
+      uint2 o;
       o.x = pack_bf16x2(static_cast<float>(px[3 * i]) - m0, static_cast<float>(px[3 * i + 1]) - m1);
       o.y = pack_bf16x2(static_cast<float>(px[3 * i + 2]) - m2, 0.f);
-      o.z = 0u;
-      o.w = 0u;
       row[gi * 4 + i] = o;
     }
   }
   // tail pixels (W % 4)
   if (blockIdx.x == 0 && threadIdx.x < (W & 3)) {
     const int x = (groups << 2) + threadIdx.x;
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16x2(static_cast<float>(src[x * 3]) - m0, static_cast<float>(src[x * 3 + 1]) - m1);
     o.y = pack_bf16x2(static_cast<float>(src[x * 3 + 2]) - m2, 0.f);
-    o.z = 0u;
-    o.w = 0u;
     row[x] = o;
   }
 }
@@ -161,7 +155,7 @@ extern "C" int vd_ingest_u8hwc(const vd_frame_t* frames, int B, void* x0, int H,
   VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc: bad extent");
   const int Wp = vd_x0_pitch(W);
   dim3 grid(vd_cdiv(W, 256), H, B);
-  ingest_x0_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, static_cast<uint4*>(x0), H, W, Wp,
+  ingest_x0_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, static_cast<uint2*>(x0), H, W, Wp,
                                                                          mean[0], mean[1], mean[2]);
   VD_LAUNCH_CHECK();
   return VD_OK;
@@ -175,7 +169,7 @@ extern "C" int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x
   const int Wp = vd_x0_pitch(W);
   dim3 grid(vd_cdiv(vd_cdiv(W, 4), 256), H, B);
   ingest_x0_identity_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
+      frames, static_cast<uint2*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }

@@ -58,7 +58,7 @@ class DetectorEngine:
             h, w = arch.feature_hw(H, W, bs.stride)
             self.buf_hw[bs.name] = (h, w, bs.channels)
             if bs.name == "x0":
-                self.buf["x0"] = torch.zeros((B, H, self.Wp, 8), dtype=torch.bfloat16, device=dev)
+                self.buf["x0"] = torch.zeros((B, H, self.Wp, 4), dtype=torch.bfloat16, device=dev)
             else:
                 self.buf[bs.name] = torch.empty((B, h, w, bs.channels), dtype=torch.bfloat16, device=dev)
         self.heads = []

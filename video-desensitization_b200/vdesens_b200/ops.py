@@ -38,11 +38,11 @@ def x0_pitch(W):
 
 
 def ingest(frames, H, W, identity=None):
-    """-> x0 bf16 (B,H,Wp,8).  reference: Retinaface.preprocess (face.py:65-88)."""
+    """-> x0 bf16 (B,H,Wp,4).  reference: Retinaface.preprocess (face.py:65-88)."""
     lib = _lib.lib()
     B = len(frames)
     desc = frame_descriptors(frames)
-    x0 = torch.zeros((B, H, x0_pitch(W), 8), dtype=torch.bfloat16, device=frames[0].device)
+    x0 = torch.zeros((B, H, x0_pitch(W), 4), dtype=torch.bfloat16, device=frames[0].device)
     if identity is None:
         identity = all(f.shape[0] == H and f.shape[1] == W for f in frames)
     fn = lib.vd_ingest_u8hwc_identity if identity else lib.vd_ingest_u8hwc

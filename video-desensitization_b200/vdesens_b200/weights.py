@@ -46,9 +46,9 @@ def pack_all(sd):
     for c in convs:
         w, b = _fold(sd, c)
         if c.name == "body.conv1":
-            # conv1 on the ingest layout: K = 7 filter rows x (8 taps x 8 channels); tap 7 and
-            # channels 3..7 are zero padding
-            wp = np.zeros((c.cout, 7, 8, 8), np.float32)
+            # conv1 on the ingest layout: K = 7 filter rows x (8 taps x 4 channels); tap 7 and
+            # channel 3 are zero padding
+            wp = np.zeros((c.cout, 7, 8, 4), np.float32)
             wp[:, :, :7, :3] = np.transpose(w, (0, 2, 3, 1))
             mat = wp.reshape(c.cout, -1)
         else:
