@@ -108,7 +108,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 }
 
 template <int BN, bool RES, int ROWB>
-__global__ void __launch_bounds__((ConvCfg<BN, RES, ROWB>::THREADS), 1)
+__global__ void __launch_bounds__((ConvCfg<BN, RES, ROWB>::THREADS), (BN <= 128 && !RES) ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ CUtensorMap tmA2, const ConvKParams p) {
@@ -560,12 +560,17 @@ struct vd_conv_plan {
   vd_conv_desc_t desc;
 };
 
+// Chooses the shared-memory layout of a plan.  occ = CTAs meant to co-reside on one SM: narrow layers are bound
+// by the latency of the single issuing warp, so two half-size CTAs per SM (two producers, two MMA issuers,
+// sixteen epilogue warps; TMEM 2 x 2*BN columns <= 512) beat one big one.  Returns false if the budget of
+// `occ` CTAs per SM leaves fewer than `min_stages` pipeline stages.
 template <int BN, bool RES, int ROWB = 128>
-static void plan_smem(vd_conv_plan* pl) {
+static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   using Cfg = ConvCfg<BN, RES, ROWB>;
   ConvKParams& k = pl->kp;
   const int KB = k.R * k.S * k.cin_blocks + k.kb2;
-  const int avail = kSmemBudget - Cfg::FIXED_BYTES;
+  const int budget = occ > 1 ? (kSmemBudget / occ - 1024) : kSmemBudget;
+  const int avail = budget - Cfg::FIXED_BYTES;
   const char* env = getenv("VD_CONV_KPS");
   const int force_kps = env ? atoi(env) : 0;
   if (k.patch) {
@@ -576,16 +581,21 @@ static void plan_smem(vd_conv_plan* pl) {
     k.kps = (BN <= 128) ? 3 : 1;                         // taps per stage (must divide 9)
     if (force_kps == 1 || force_kps == 3) k.kps = force_kps;
     int st = (avail - k.a_slots * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES);
+    if (st < min_stages && k.kps == 3 && !force_kps) {   // tight budget (two CTAs per SM): one tap per stage
+      k.kps = 1;
+      st = (avail - k.a_slots * k.a_slot_bytes) / Cfg::B_BYTES;
+    }
     if (st > 3 && k.cin_blocks >= 2 && (avail - 3 * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES) >= 3) {
       k.a_slots = 3;
       st = (avail - k.a_slots * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES);
     }
     k.stages = st > kMaxStages ? kMaxStages : st;
     pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + k.stages * k.kps * Cfg::B_BYTES;
-    return;
+    return k.stages >= min_stages;
   }
   const int w_bytes = KB * Cfg::B_BYTES;
-  k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && k.num_tiles > pl->grid && BN <= 64 && KB >= 4) ? 1 : 0;
+  k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && w_bytes * 2 <= avail && k.num_tiles > pl->grid &&
+            BN <= 64 && KB >= 4) ? 1 : 0;
   k.w_bytes = k.wres ? w_bytes : 0;
   // K blocks per stage: narrow N tiles finish a 64-deep block in 128 (BN=64) / 256 (BN=128) clk, far less
   // than one barrier round trip of the issuing warp
@@ -594,15 +604,30 @@ static void plan_smem(vd_conv_plan* pl) {
   else if (BN == 128) kps = 2;
   if (kps > KB) kps = KB;
   if (force_kps > 0 && force_kps <= 4) kps = force_kps > KB ? KB : force_kps;
-  const int stage_bytes = kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES));
-  int st = (avail - k.w_bytes) / stage_bytes;
-  while (st < 2 && kps > 1) {
+  const int per_block = Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES);
+  int st = (avail - k.w_bytes) / (kps * per_block);
+  while (st < min_stages && kps > 1) {
     --kps;
-    st = (avail - k.w_bytes) / (kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES)));
+    st = (avail - k.w_bytes) / (kps * per_block);
   }
   k.kps = kps;
   k.stages = st > kMaxStages ? kMaxStages : st;
-  pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * kps * (Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES));
+  pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * kps * per_block;
+  return k.stages >= min_stages;
+}
+
+// occupancy policy: variants compiled with two CTAs per SM (see __launch_bounds__) try occ = 2 first
+template <int BN, bool RES, int ROWB = 128>
+static bool plan_occ(vd_conv_plan* pl, int sms) {
+  constexpr bool kTwo = (BN <= 128 && !RES);
+  const char* env = getenv("VD_CONV_OCC");
+  const int want = env ? atoi(env) : 2;
+  if (kTwo && want >= 2 && pl->kp.num_tiles > sms) {
+    pl->grid = pl->kp.num_tiles < 2 * sms ? pl->kp.num_tiles : 2 * sms;
+    if (plan_smem<BN, RES, ROWB>(pl, 2, 3)) return true;
+  }
+  pl->grid = pl->kp.num_tiles < sms ? pl->kp.num_tiles : sms;
+  return plan_smem<BN, RES, ROWB>(pl, 1, 2);
 }
 
 static void choose_tile(int Wout, int Hout, int B, int sw, int sh, int* TW, int* TH, int* NB) {
@@ -858,14 +883,15 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
   {
     const bool res = (d->flags & VD_CONV_RESIDUAL) != 0;
-    if (x0) plan_smem<64, false, 64>(pl);
+    bool ok;
+    if (x0) ok = plan_occ<64, false, 64>(pl, sms);
     else switch (BN) {
-      case 32: plan_smem<32, false>(pl); break;
-      case 64: res ? plan_smem<64, true>(pl) : plan_smem<64, false>(pl); break;
-      case 128: res ? plan_smem<128, true>(pl) : plan_smem<128, false>(pl); break;
-      default: res ? plan_smem<256, true>(pl) : plan_smem<256, false>(pl); break;
+      case 32: ok = plan_occ<32, false>(pl, sms); break;
+      case 64: ok = res ? plan_occ<64, true>(pl, sms) : plan_occ<64, false>(pl, sms); break;
+      case 128: ok = res ? plan_occ<128, true>(pl, sms) : plan_occ<128, false>(pl, sms); break;
+      default: ok = res ? plan_occ<256, true>(pl, sms) : plan_occ<256, false>(pl, sms); break;
     }
-    if (k.stages < 2) {
+    if (!ok) {
       vd_set_error("vd_conv_plan_create: shared memory budget too small");
       delete pl;
       return VD_ERR_UNSUPPORTED;
