@@ -51,6 +51,9 @@ enum vd_status {
 #define VD_STAT_WATCHDOG 8u        /* a device-side wait timed out */
 
 int vd_abi_version(void);
+/* storage type of activations and weights this build computes in: 0 = bf16 (libvdesens.so),
+ * 1 = fp16 (libvdesens_fp16.so, same sources built with -DVD_ACT_FP16) */
+int vd_act_is_fp16(void);
 const char* vd_build_info(void);
 int vd_last_error(char* buf, size_t n);
 /* fills SM count and compute capability of the current device */

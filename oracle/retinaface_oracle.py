@@ -273,7 +273,7 @@ def detect_images(sd, images, input_hw, confidence=0.5, nms_iou=0.45, return_row
 # bf16 emulation of the device network (same packed weights, same rounding points, fp32 math):
 # separates "the CUDA pipeline computes the right function" from "bf16 differs from fp32".
 # ----------------------------------------------------------------------------------------------
-def forward_bf16_emulated(packed, x, capture=None):
+def forward_bf16_emulated(packed, x, capture=None, dtype=torch.bfloat16):
     """packed: vdesens_b200.weights.pack_all(sd) (BN-folded bf16 GEMM operands).  x: (B,3,H,W) fp32
     mean-subtracted (exact integers).  Activations are rounded to bf16 where the device stores them."""
     from vdesens_b200 import arch
@@ -281,7 +281,7 @@ def forward_bf16_emulated(packed, x, capture=None):
     cap = capture if capture is not None else {}
 
     def bf(t):
-        return t.to(torch.bfloat16).float()
+        return t.to(dtype).float()
 
     bufs = {"x0": x}
     heads = [None, None, None]

@@ -567,3 +567,50 @@ def test_config3_4k_large_roi_blur(sd_np):
     from vdesens_b200 import ops as _ops
     _ops.composite([f2], [big], "gauss", ksize=99)
     assert np.array_equal(f2.cpu().numpy(), co.composite(frame, big, "gauss", ksize=99))
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16-storage build (libvdesens_fp16.so): meets north_star's IoU >= 0.99 on EVERY anchor
+# ------------------------------------------------------------------------------------------------
+def test_fp16_conv_kernel(ops):
+    g = torch.Generator(device="cpu").manual_seed(21)
+    x = torch.randn((2, 17, 31, 128), generator=g).to(torch.float16).to(DEV)
+    w = (torch.randn((128, 128, 3, 3), generator=g) / 34.0).to(torch.float16).to(DEV)
+    bias = torch.randn((128,), generator=g).to(DEV)
+    res = torch.randn((2, 17, 31, 128), generator=g).to(torch.float16).to(DEV)
+    got = ops.conv2d(x, w.permute(0, 2, 3, 1).reshape(128, -1).contiguous(), bias, 3, 1, 1, relu=True, residual=res)
+    torch.cuda.synchronize()
+    want = _ref_conv(x, w, bias, 1, 1, True, res, None)
+    assert got.dtype == torch.float16
+    assert bool(((got.float() - want).abs() <= 2.0 ** -10 * want.abs().clamp_min(1.0)).all())
+    xm = torch.randn((1, 45, 77, 64), generator=g).to(torch.float16).to(DEV)
+    assert torch.equal(ops.maxpool3x3s2(xm).float(),
+                       torch.nn.functional.max_pool2d(xm.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("case", ["native", "odd"])
+def test_fp16_network_vs_reference_fp32(det_gold, sd_np, case):
+    """fp16 storage, fp32 accumulation: vs the EXECUTED fp32 reference every decoded box has IoU >= 0.99
+    (north_star's reduced-precision tolerance), |score| error <= 0.01, |loc| error <= 0.03."""
+    from vdesens_b200.engine import DetectorEngine
+    fr = det_gold[case + ".frames"]
+    H, W = (int(v) for v in det_gold[case + ".input_shape"][:2])
+    frames = [synth.synthetic_frame(int(h), int(w), int(s)) for h, w, s in fr]
+    eng = DetectorEngine(sd_np, len(frames), H, W, device=DEV, confidence=0.5, nms_iou=0.4, precision="fp16")
+    eng.set_frames(_dev_frames(frames))
+    eng.forward()
+    loc, cls, ldm = (t.cpu() for t in eng.head_tensors())
+    conf = torch.softmax(cls, -1).numpy()
+    dl = np.abs(loc.numpy() - det_gold[case + ".loc"]).max()
+    dc = np.abs(conf - det_gold[case + ".conf"]).max()
+    pri = ro.anchors(H, W).unsqueeze(0)
+    iou = _box_iou_pairs(ro.decode(loc, pri).numpy(), ro.decode(torch.from_numpy(det_gold[case + ".loc"]), pri).numpy())
+    print(f"fp16: loc {dl:.4f} conf {dc:.4f} IoU min {iou.min():.4f}")
+    assert dl <= 0.03 and dc <= 0.01 and iou.min() >= 0.99
+    # and the kept boxes: every reference row away from the threshold is reproduced with IoU >= 0.99
+    rows, counts = eng.fetch_results()
+    for i in range(len(frames)):
+        want = det_gold[f"{case}.rows{i}"]
+        got = rows[i, :counts[i], :15]
+        strong = want[np.abs(want[:, 4] - 0.5) > 0.01]
+        assert all(_iou(r[:4], got[:, :4]).max(initial=0) >= 0.99 for r in strong)

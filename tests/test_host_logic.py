@@ -19,8 +19,11 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(vd_[a-z0-9_]+)\s*\(", hdr))
     declared -= {"vd_frame", "vd_status"}
     lib = _lib.lib()                       # raises if the .so is missing: there is no fallback
+    lib16 = _lib.lib("fp16")
     for name in sorted(declared):
         assert hasattr(lib, name), f"libvdesens.so does not export {name}"
+        assert hasattr(lib16, name), f"libvdesens_fp16.so does not export {name}"
+    assert lib.vd_act_is_fp16() == 0 and lib16.vd_act_is_fp16() == 1
     assert set(_lib.EXPORTED) == declared, (set(_lib.EXPORTED) ^ declared)
     assert lib.vd_abi_version() == 1
     assert b"sm_100a" in lib.vd_build_info()

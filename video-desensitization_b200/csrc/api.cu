@@ -27,8 +27,11 @@ int vd_num_sms() {
 
 extern "C" int vd_abi_version(void) { return VD_ABI_VERSION; }
 
+// 0 = bf16 activations/weights (libvdesens.so), 1 = fp16 (libvdesens_fp16.so)
+extern "C" int vd_act_is_fp16(void) { return VD_ACT_IS_FP16; }
+
 extern "C" const char* vd_build_info(void) {
-  return "libvdesens sm_100a (tcgen05/TMEM/TMA), built " __DATE__ " " __TIME__;
+  return "libvdesens sm_100a (tcgen05/TMEM/TMA), activations " VD_ACT_NAME ", built " __DATE__ " " __TIME__;
 }
 
 extern "C" int vd_last_error(char* buf, size_t n) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -213,10 +214,35 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- misc ----
+// Activation / weight storage type: bf16 (default, BASELINE's dtype) or, when the library is built with
+// -DVD_ACT_FP16 (libvdesens_fp16.so), IEEE half — same tensor-core rate, 3 more mantissa bits.
+#ifdef VD_ACT_FP16
+#define VD_ACT_NAME "fp16"
+#define VD_ACT_IS_FP16 1
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);               // .x = lo (low 16 bits), .y = hi
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu))); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
+__device__ __forceinline__ uint32_t act2_max(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+#define VD_ACT2_NEG_INF 0xFC00FC00u
+#else
+#define VD_ACT_NAME "bf16"
+#define VD_ACT_IS_FP16 0
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t act2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+#define VD_ACT2_NEG_INF 0xFF80FF80u
+#endif
 #endif  // __CUDACC__

@@ -60,6 +60,8 @@ struct ConvKParams {
 
 // RES = the layer adds a residual tensor: it is prefetched by a dedicated TMA warp into a ring of
 // RES_SLOTS 16 KB tiles (one per 64-channel chunk), paid for with fewer operand stages.
+constexpr CUtensorMapDataType kActTmapType =
+    VD_ACT_IS_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 232448;        // 227 KB per CTA on sm_100
 constexpr int kWresMaxBytes = 72 * 1024;   // resident-weight limit (3x3 64->64 = 72 KB)
@@ -262,7 +264,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =============
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
     // a/b K-major, N>>3 [17,23), M>>4 [24,29)
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+    constexpr uint32_t kFmt = VD_ACT_IS_FP16 ? 0u : 1u;      // a/b format: 0 = F16, 1 = BF16
+    constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                (static_cast<uint32_t>(128 >> 4) << 24);
     // descriptor words: lo = start>>4 | LBO(1)<<16 ; hi = SBO>>4 | version(1)<<14 | SWIZZLE_128B(2)<<29
     constexpr uint32_t hi_std = (static_cast<uint32_t>(8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
@@ -779,7 +782,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   box[3] = static_cast<cuuint32_t>(k.NB);
   if (k.patch) { box[1] = static_cast<cuuint32_t>(k.PW); box[2] = static_cast<cuuint32_t>(k.PH); }
   estr[0] = 1; estr[1] = static_cast<cuuint32_t>(sw); estr[2] = static_cast<cuuint32_t>(sh); estr[3] = 1;
-  CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
+  CUresult r = enc(&pl->tmA, kActTmapType, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -799,7 +802,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     cuuint32_t b2[4] = {64, static_cast<cuuint32_t>(k.TW * d->stride2), static_cast<cuuint32_t>(k.TH * d->stride2),
                         static_cast<cuuint32_t>(k.NB)};
     cuuint32_t e2[4] = {1, static_cast<cuuint32_t>(d->stride2), static_cast<cuuint32_t>(d->stride2), 1};
-    r = enc(&pl->tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x2), g2, s2, b2, e2,
+    r = enc(&pl->tmA2, kActTmapType, 4, const_cast<void*>(d->x2), g2, s2, b2, e2,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -815,7 +818,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   cuuint64_t wstr[1] = {Ktot * 2};
   cuuint32_t wbox[2] = {static_cast<cuuint32_t>(kelems), static_cast<cuuint32_t>(BN)};
   cuuint32_t wes[2] = {1, 1};
-  r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), wdim, wstr, wbox, wes,
+  r = enc(&pl->tmB, kActTmapType, 2, const_cast<void*>(d->w), wdim, wstr, wbox, wes,
           CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -845,7 +848,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     cuuint32_t ybox[4] = {static_cast<cuuint32_t>(f32 ? 32 : 64), static_cast<cuuint32_t>(k.TW),
                           static_cast<cuuint32_t>(k.TH), static_cast<cuuint32_t>(k.NB)};
     cuuint32_t yes[4] = {1, 1, 1, 1};
-    r = enc(&pl->tmY, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->y, ydim, ystr,
+    r = enc(&pl->tmY, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : kActTmapType, 4, d->y, ydim, ystr,
             ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -869,7 +872,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     cuuint32_t rbox[4] = {64, static_cast<cuuint32_t>(k.TW), static_cast<cuuint32_t>(k.TH),
                           static_cast<cuuint32_t>(k.NB)};
     cuuint32_t res1[4] = {1, 1, 1, 1};
-    r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->residual), rdim, rstr, rbox, res1,
+    r = enc(&pl->tmR, kActTmapType, 4, const_cast<void*>(d->residual), rdim, rstr, rbox, res1,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

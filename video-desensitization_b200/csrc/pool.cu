@@ -4,10 +4,6 @@
 #include "common.cuh"
 
 namespace {
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
 
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int C8, int Ho, int Wo) {
@@ -20,7 +16,7 @@ maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, i
     t /= Wo;
     const int yo = static_cast<int>(t % Ho);
     const int b = static_cast<int>(t / Ho);
-    uint4 m = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // -inf bf16 pairs
+    uint4 m = make_uint4(VD_ACT2_NEG_INF, VD_ACT2_NEG_INF, VD_ACT2_NEG_INF, VD_ACT2_NEG_INF);   // -inf pairs
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int yi = yo * 2 - 1 + dy;
@@ -30,10 +26,10 @@ maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, i
         const int xi = xo * 2 - 1 + dx;
         if (xi < 0 || xi >= W) continue;
         const uint4 v = __ldg(x + ((static_cast<size_t>(b) * H + yi) * W + xi) * C8 + c);
-        m.x = bf16x2_max(m.x, v.x);
-        m.y = bf16x2_max(m.y, v.y);
-        m.z = bf16x2_max(m.z, v.z);
-        m.w = bf16x2_max(m.w, v.w);
+        m.x = act2_max(m.x, v.x);
+        m.y = act2_max(m.y, v.y);
+        m.z = act2_max(m.z, v.z);
+        m.w = act2_max(m.w, v.w);
       }
     }
     y[i] = m;

@@ -7,7 +7,9 @@ Same constructor kwargs/defaults, attributes and methods; same return types; sam
   * `backbone="mobilenet"` raises NotImplementedError (outside BASELINE.json's hot path);
   * multi-GPU is one process per GPU (vdesens_b200.shard), not nn.DataParallel (face.py:56);
   * extra optional kwargs: `state_dict` (weights given in memory instead of `model_path`),
-    `batch_size` (engine batch, default = first batch seen), `cand_cap`, `max_det`, `device_index`.
+    `batch_size` (engine batch, default = first batch seen), `cand_cap`, `max_det`, `device_index`,
+    `precision` ("bf16" default; "fp16" = same kernels with half storage: boxes agree with the fp32
+    reference to IoU >= 0.99 on every anchor).
 """
 import time
 
@@ -47,7 +49,7 @@ class _NetHandle(object):
         x0 = eng.buf["x0"]
         with torch.cuda.stream(eng.stream):
             eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
-            x0[:, :, 3:3 + W, :3] = x.to(eng.device).permute(0, 2, 3, 1).to(torch.bfloat16)
+            x0[:, :, 3:3 + W, :3] = x.to(eng.device).permute(0, 2, 3, 1).to(eng.act_dtype)
             eng.enqueue_network()
         loc, cls, ldm = eng.head_tensors()
         return loc, torch.softmax(cls, dim=-1), ldm
@@ -75,6 +77,7 @@ class Retinaface(object):
         self.cand_cap = 4096
         self.max_det = 2048
         self.device_index = None
+        self.precision = "bf16"
         for name, value in kwargs.items():
             setattr(self, name, value)
         if self.backbone == "mobilenet":
@@ -105,7 +108,7 @@ class Retinaface(object):
         if b not in self._engines:
             self._engines[b] = DetectorEngine(self._sd, b, self.input_shape[0], self.input_shape[1], device=self.device,
                                               confidence=self.confidence, nms_iou=self.nms_iou, cand_cap=self.cand_cap,
-                                              max_det=self.max_det)
+                                              max_det=self.max_det, precision=self.precision)
         eng = self._engines[b]
         eng.confidence, eng.nms_iou = float(self.confidence), float(self.nms_iou)
         return eng

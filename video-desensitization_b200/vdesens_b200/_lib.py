@@ -6,6 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdesens.so")
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libvdesens_fp16.so")}
 
 VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0, VD_CONV_DUAL = 1, 2, 4, 8, 16, 32
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
@@ -33,6 +34,7 @@ class VdConvDesc(C.Structure):
 
 _SIGS = {
     "vd_abi_version": (C.c_int, []),
+    "vd_act_is_fp16": (C.c_int, []),
     "vd_build_info": (C.c_char_p, []),
     "vd_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
     "vd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
@@ -61,24 +63,38 @@ _SIGS = {
 
 EXPORTED = tuple(_SIGS)
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    """Loads libvdesens.so once.  Raises if it has not been built (see __graft_entry__.build())."""
-    global _lib
-    if _lib is None:
-        if not os.path.isfile(LIB_PATH):
+def lib(precision: str = "bf16"):
+    """Loads libvdesens.so (bf16 activations, BASELINE's dtype) or libvdesens_fp16.so (same sources, fp16
+    storage) once.  Raises if it has not been built (see __graft_entry__.build()); there is no fallback."""
+    if precision not in LIB_PATHS:
+        raise ValueError(f"precision must be 'bf16' or 'fp16', got {precision!r}")
+    if precision not in _libs:
+        path = LIB_PATHS[precision]
+        if not os.path.isfile(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                f"{path} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
                 f"g.build()' or make -C video-desensitization_b200/csrc). There is no CPU fallback.")
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)       # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
-        _lib = l
-    return _lib
+        assert l.vd_act_is_fp16() == (1 if precision == "fp16" else 0)
+        _libs[precision] = l
+    return _libs[precision]
+
+
+def torch_dtype(precision: str):
+    import torch
+    return torch.float16 if precision == "fp16" else torch.bfloat16
+
+
+def precision_of(dtype) -> str:
+    import torch
+    return "fp16" if dtype == torch.float16 else "bf16"
 
 
 def last_error() -> str:

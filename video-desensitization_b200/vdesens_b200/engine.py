@@ -26,10 +26,12 @@ def _ptr(t):
 
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
-                 cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0):
+                 cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
-        self.lib = _lib.lib()
+        self.precision = precision            # "bf16" (BASELINE's dtype) or "fp16" (libvdesens_fp16.so)
+        self.act_dtype = _lib.torch_dtype(precision)
+        self.lib = _lib.lib(precision)
         self.device = torch.device(device)
         self.B, self.H, self.W = int(batch), int(in_h), int(in_w)
         self.confidence, self.nms_iou = float(confidence), float(nms_iou)
@@ -50,7 +52,7 @@ class DetectorEngine:
     def _build(self, state_dict, scratch_frames):
         dev, B, H, W = self.device, self.B, self.H, self.W
         convs, ops, bufs = arch.build_graph()
-        packed = weights.pack_all(state_dict)
+        packed = weights.pack_all(state_dict, self.act_dtype)
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
         self.Wp = self.lib.vd_x0_pitch(W)
         self.buf, self.buf_hw = {}, {}
@@ -58,9 +60,9 @@ class DetectorEngine:
             h, w = arch.feature_hw(H, W, bs.stride)
             self.buf_hw[bs.name] = (h, w, bs.channels)
             if bs.name == "x0":
-                self.buf["x0"] = torch.zeros((B, H, self.Wp, 4), dtype=torch.bfloat16, device=dev)
+                self.buf["x0"] = torch.zeros((B, H, self.Wp, 4), dtype=self.act_dtype, device=dev)
             else:
-                self.buf[bs.name] = torch.empty((B, h, w, bs.channels), dtype=torch.bfloat16, device=dev)
+                self.buf[bs.name] = torch.empty((B, h, w, bs.channels), dtype=self.act_dtype, device=dev)
         self.heads = []
         for lvl, s in enumerate(arch.CFG_RE50["steps"]):
             h, w = arch.feature_hw(H, W, s)

@@ -37,12 +37,12 @@ def x0_pitch(W):
     return int(_lib.lib().vd_x0_pitch(int(W)))
 
 
-def ingest(frames, H, W, identity=None):
-    """-> x0 bf16 (B,H,Wp,4).  reference: Retinaface.preprocess (face.py:65-88)."""
-    lib = _lib.lib()
+def ingest(frames, H, W, identity=None, precision="bf16"):
+    """-> x0 (B,H,Wp,4) in the library's activation type.  reference: Retinaface.preprocess (face.py:65-88)."""
+    lib = _lib.lib(precision)
     B = len(frames)
     desc = frame_descriptors(frames)
-    x0 = torch.zeros((B, H, x0_pitch(W), 4), dtype=torch.bfloat16, device=frames[0].device)
+    x0 = torch.zeros((B, H, x0_pitch(W), 4), dtype=_lib.torch_dtype(precision), device=frames[0].device)
     if identity is None:
         identity = all(f.shape[0] == H and f.shape[1] == W for f in frames)
     fn = lib.vd_ingest_u8hwc_identity if identity else lib.vd_ingest_u8hwc
@@ -64,8 +64,10 @@ def ingest_nchw_f32(frames, H, W):
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
            out_f32=False, x0_hw=None, x2=None, stride2=1):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
-    w_packed: bf16 (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout)."""
-    lib = _lib.lib()
+    w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
+    The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
+    lib = _lib.lib(_lib.precision_of(x.dtype))
+    assert w_packed.dtype == x.dtype
     B = x.shape[0]
     cout = w_packed.shape[0]
     d = _lib.VdConvDesc()
@@ -78,7 +80,7 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     hout = (hin + 2 * pad - k) // stride + 1
     wout = (win + 2 * pad - k) // stride + 1
     if out is None:
-        out = torch.empty((B, hout, wout, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        out = torch.empty((B, hout, wout, cout), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
     d.B, d.Hin, d.Win, d.Cin = B, hin, win, cin
     d.Hout, d.Wout, d.Cout = hout, wout, cout
     d.R = d.S = k
@@ -112,9 +114,9 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
 
 
 def maxpool3x3s2(x):
-    lib = _lib.lib()
+    lib = _lib.lib(_lib.precision_of(x.dtype))
     B, H, W, Cc = x.shape
-    y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, Cc), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, Cc), dtype=x.dtype, device=x.device)
     _lib.check(lib.vd_maxpool3x3s2(_p(x), _p(y), B, H, W, Cc, _stream()), "vd_maxpool3x3s2")
     return y
 

@@ -37,7 +37,7 @@ def to_numpy_sd(sd):
     return out
 
 
-def pack_all(sd):
+def pack_all(sd, dtype=torch.bfloat16):
     """Returns {layer name: (w_packed bf16 CPU tensor [Cout, K], bias fp32 CPU tensor [Cout])} for every
     conv of the graph plus 'heads.{0,1,2}' (the three 1x1 heads of a level fused to one N=32 GEMM)."""
     sd = to_numpy_sd(sd)
@@ -57,7 +57,7 @@ def pack_all(sd):
             w2, b2 = _fold(sd, c, second=True)
             mat = np.concatenate([mat, w2.reshape(c.cout, -1)], axis=1)
             b = b + b2
-        packed[c.name] = (torch.from_numpy(np.ascontiguousarray(mat)).to(torch.bfloat16),
+        packed[c.name] = (torch.from_numpy(np.ascontiguousarray(mat)).to(dtype),
                           torch.from_numpy(b.copy()))
     for lvl in range(3):
         ws, bs = [], []
@@ -66,5 +66,5 @@ def pack_all(sd):
             bs.append(np.asarray(sd[hk + ".bias"], np.float32))
         mat = np.concatenate(ws, 0)
         assert mat.shape == (arch.HEAD_ROWS, 256)
-        packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(torch.bfloat16), torch.from_numpy(np.concatenate(bs)))
+        packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(dtype), torch.from_numpy(np.concatenate(bs)))
     return packed
