@@ -614,3 +614,31 @@ def test_fp16_network_vs_reference_fp32(det_gold, sd_np, case):
         got = rows[i, :counts[i], :15]
         strong = want[np.abs(want[:, 4] - 0.5) > 0.01]
         assert all(_iou(r[:4], got[:, :4]).max(initial=0) >= 0.99 for r in strong)
+
+
+def test_facade_mixed_frame_sizes_vs_reference(det_gold, sd_np):
+    """frames of different sizes in one batch (reference face.py:73-80 letterboxes each one): the façade's
+    boxes against the executed reference's boxes for the golden "letterbox" case."""
+    from detect_face.face import Retinaface
+    fr = det_gold["letterbox.frames"]
+    frames = [synth.synthetic_frame(int(h), int(w), int(s)) for h, w, s in fr]
+    det = Retinaface(state_dict=sd_np, input_shape=[128, 128, 3], confidence=0.5, nms_iou=0.4, precision="fp16")
+    res = det.detect_images(frames)
+    for i, (img, boxes) in enumerate(res):
+        want = det_gold[f"letterbox.boxes{i}"]
+        rows = det_gold[f"letterbox.rows{i}"]
+        got = np.array(boxes, np.float64).reshape(-1, 4)
+        assert np.array_equal(img, frames[i])
+        strong = want[np.abs(rows[:, 4] - 0.5) > 0.02]
+        assert len(strong) > 0
+        for r in strong:
+            assert _iou(r, got).max(initial=0) >= 0.98, (i, r)
+        assert abs(len(got) - len(want)) <= max(2, len(want) // 10)
+    # preprocess() returns the reference's tensor bit for bit; postprocess() on the reference's head tensors
+    # returns the reference's rows
+    x, shapes = det.preprocess(frames)
+    assert np.array_equal(x.cpu().numpy(), det_gold["letterbox.x"])
+    out = det.postprocess(torch.from_numpy(det_gold["letterbox.loc"]).to(DEV), torch.from_numpy(det_gold["letterbox.conf"]).to(DEV),
+                          torch.from_numpy(det_gold["letterbox.landms"]).to(DEV), shapes, len(frames))
+    for i, r in enumerate(out):
+        np.testing.assert_allclose(r.cpu().numpy(), det_gold[f"letterbox.rows{i}"], atol=1e-5, rtol=0)
