@@ -642,3 +642,32 @@ def test_facade_mixed_frame_sizes_vs_reference(det_gold, sd_np):
                           torch.from_numpy(det_gold["letterbox.landms"]).to(DEV), shapes, len(frames))
     for i, r in enumerate(out):
         np.testing.assert_allclose(r.cpu().numpy(), det_gold[f"letterbox.rows{i}"], atol=1e-5, rtol=0)
+
+
+def test_fp16_is_as_close_to_fp32_as_the_references_own_tf32_gpu_path(det_gold, sd_np):
+    """the reference's "fp32" GPU run is TF32 inside cuDNN (torch default allow_tf32=True), which has the
+    same 10-bit mantissa as fp16.  Run the oracle network (the reference's own torch ops) on THIS GPU with cuDNN TF32 and
+    measure its distance to the executed fp32 CPU reference; the fp16 tcgen05 path must not be further away than 2x."""
+    from vdesens_b200.engine import DetectorEngine
+    case = "odd"
+    fr = det_gold[case + ".frames"]
+    H, W = (int(v) for v in det_gold[case + ".input_shape"][:2])
+    frames = [synth.synthetic_frame(int(h), int(w), int(s)) for h, w, s in fr]
+    x, _ = ro.preprocess(frames, (H, W))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        sd_gpu = {k: v.to(DEV) for k, v in ro.to_torch_sd(sd_np).items()}
+        tloc, tconf, _ = ro.forward(sd_gpu, x.to(DEV))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    tf32_loc = float(np.abs(tloc.cpu().numpy() - det_gold[case + ".loc"]).max())
+    tf32_conf = float(np.abs(tconf.cpu().numpy() - det_gold[case + ".conf"]).max())
+    eng = DetectorEngine(sd_np, len(frames), H, W, device=DEV, confidence=0.5, nms_iou=0.4, precision="fp16")
+    eng.set_frames(_dev_frames(frames))
+    eng.forward()
+    loc, cls, _ = (t.cpu() for t in eng.head_tensors())
+    our_loc = float(np.abs(loc.numpy() - det_gold[case + ".loc"]).max())
+    our_conf = float(np.abs(torch.softmax(cls, -1).numpy() - det_gold[case + ".conf"]).max())
+    print(f"vs fp32 CPU reference: cuDNN-TF32 oracle loc {tf32_loc:.5f} conf {tf32_conf:.5f} | fp16 tcgen05 loc {our_loc:.5f} conf {our_conf:.5f}")
+    assert our_loc <= max(2 * tf32_loc, 5e-3) and our_conf <= max(2 * tf32_conf, 2e-3)
