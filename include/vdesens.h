@@ -98,6 +98,11 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
 #define VD_CONV_UPADD 4u       /* + nearest-upsampled half-resolution tensor AFTER ReLU     */
 #define VD_CONV_OUT_F32 8u     /* store fp32 instead of bf16 (head GEMM)                    */
 #define VD_CONV_IN_X0 16u      /* input is the ingest layout (conv1: 7x7 s2 p3, 3->64)       */
+#define VD_CONV_SPLIT 64u      /* split-precision tensors ("fp32-class" mode): every activation tensor has 3 planes of
+                                  C channels [hi | lo | hi] with value = hi + lo; Cin counts all three planes, weights
+                                  are [w_hi | w_hi | w_lo] per tap, so x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulates
+                                  in fp32.  dst_C, the residual and the upadd tensor have 3*C channels; the epilogue
+                                  writes hi, lo and the hi copy.  Not combinable with VD_CONV_DUAL. */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 
@@ -133,6 +138,8 @@ int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, int* NB, int
 
 /* max-pool 3x3 stride 2 pad 1 on bf16 NHWC (torchvision resnet stem) */
 int vd_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
+/* same on split-precision tensors: [B][H][W][3*C] planes hi | lo | hi, maximum of hi + lo (VD_CONV_SPLIT) */
+int vd_maxpool3x3s2_split(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K3 decode + threshold + compaction                                                          */

@@ -243,7 +243,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < n; ++j) {
           if (leader) {
             if (kb + j < p.kb1)
-              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + sx, yin0 + r, b0);
+              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage],
+                          (p.flags & VD_CONV_IN_X0) ? 0 : cb * 64, xin0 + sx, yin0 + r, b0);
             else        // second K segment: 1x1 projection of x2 at (x*stride2, y*stride2)
               tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA2, &full[stage], (kb + j - p.kb1) * 64,
                           tx * p.TW * p.stride2, ty * p.TH * p.stride2, b0);
@@ -364,14 +365,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         m /= p.tiles_x;
         const int ty = m % p.tiles_y;
         const int tb = m / p.tiles_y;
+        const int nplanes = (p.flags & VD_CONV_SPLIT) ? 2 : 1;      // split residual = hi plane + lo plane
         for (int ch = 0; ch < NCHUNK_R; ++ch) {
-          mbar_wait(&rempty[slot], rphase ^ 1u);
-          mbar_expect_tx(&rfull[slot], static_cast<uint32_t>(p.rows_used * 128));
-          tma_load_4d(sRes + slot * (128 * 128), &tmR, &rfull[slot], n_tile * BN + ch * 64, tx * p.TW, ty * p.TH,
-                      tb * p.NB);
-          if (++slot == Cfg::RES_SLOTS) {
-            slot = 0;
-            rphase ^= 1u;
+          for (int pl = 0; pl < nplanes; ++pl) {
+            mbar_wait(&rempty[slot], rphase ^ 1u);
+            mbar_expect_tx(&rfull[slot], static_cast<uint32_t>(p.rows_used * 128));
+            tma_load_4d(sRes + slot * (128 * 128), &tmR, &rfull[slot], pl * p.Cout + n_tile * BN + ch * 64, tx * p.TW,
+                        ty * p.TH, tb * p.NB);
+            if (++slot == Cfg::RES_SLOTS) {
+              slot = 0;
+              rphase ^= 1u;
+            }
           }
         }
       }
@@ -386,6 +390,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nb_ = row / (p.TW * p.TH);
     const bool issuer = (threadIdx.x == 64);        // lane 0 of warp 2 issues the TMA stores
     const bool f32out = (p.flags & VD_CONV_OUT_F32) != 0;
+    const bool split = (p.flags & VD_CONV_SPLIT) != 0;
+    const int up_C = split ? 3 * p.Cout : p.Cout;        // channels of the upadd tensor
     constexpr int NCHUNK = (BN >= 64) ? BN / 64 : 1;
     const bool active = (BN >= 64) || (half == 0);  // BN == 32 (head GEMM): one 32-column chunk
     int acc = 0;
@@ -429,19 +435,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                             static_cast<uint32_t>(acc * BN + ch * 64 + half * 32), v);
         }
-        uint4 rcur[4];
+        uint4 rcur[4], rlo[4];
         if (RES) {
-          // residual chunk staged by the residual-producer warp (SWIZZLE_128B tile, same geometry as the output)
-          mbar_wait(&rfull[rslot], rphase);
-          const uint8_t* rrow = sRes + rslot * (128 * 128) + row * 128;
+          // residual chunk staged by the residual-producer warp (SWIZZLE_128B tile, same geometry as the output);
+          // split mode: a second tile carries the lo plane
+          const int nplanes = split ? 2 : 1;
+          for (int pl = 0; pl < nplanes; ++pl) {
+            mbar_wait(&rfull[rslot], rphase);
+            const uint8_t* rrow = sRes + rslot * (128 * 128) + row * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            rcur[j] = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&rempty[rslot]);
-          if (++rslot == Cfg::RES_SLOTS) {
-            rslot = 0;
-            rphase ^= 1u;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
+              if (pl == 0) rcur[j] = t; else rlo[j] = t;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty[rslot]);
+            if (++rslot == Cfg::RES_SLOTS) {
+              rslot = 0;
+              rphase ^= 1u;
+            }
           }
         }
         float f[32];
@@ -465,22 +477,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
               f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
             }
+            if (split) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rv = rlo[j];
+                f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
+                f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
+                f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
+                f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+              }
+            }
           }
           if (p.flags & VD_CONV_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
           if ((p.flags & VD_CONV_UPADD) && valid) {
-            const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * p.Cout + n0);
+            for (int pl = 0; pl < (split ? 2 : 1); ++pl) {
+              const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * up_C + pl * p.Cout + n0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 rv = __ldg(up + j);
-              f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
-              f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
-              f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
-              f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rv = __ldg(up + j);
+                f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
+                f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
+                f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
+                f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+              }
             }
           }
+        }
+        if (split && !f32out) {
+          // split-precision output: hi = round(v), lo = round(v - hi); planes [hi | lo | hi] of dst_C / 3 channels.
+          // Both staging tiles are used per chunk (hi, lo), so the previous chunk's stores must have read them.
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1, kEpiThreads);
+          if (active) {
+            uint8_t* hrow = sOut + row * 128;
+            uint8_t* lrow = sOut + 128 * 128 + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 h, l;
+              h.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              h.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              h.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              h.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              l.x = pack_bf16x2(f[8 * j + 0] - bf16lo_to_f32(h.x), f[8 * j + 1] - bf16hi_to_f32(h.x));
+              l.y = pack_bf16x2(f[8 * j + 2] - bf16lo_to_f32(h.y), f[8 * j + 3] - bf16hi_to_f32(h.y));
+              l.z = pack_bf16x2(f[8 * j + 4] - bf16lo_to_f32(h.z), f[8 * j + 5] - bf16hi_to_f32(h.z));
+              l.w = pack_bf16x2(f[8 * j + 6] - bf16lo_to_f32(h.w), f[8 * j + 7] - bf16hi_to_f32(h.w));
+              const int off = (((half * 4 + j) ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(hrow + off) = h;
+              *reinterpret_cast<uint4*>(lrow + off) = l;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (issuer) {
+            const int plane = p.dst_C / 3;
+            const int cch = p.dst_coff + n_tile * BN + ch * 64;
+            tma_store_4d(&tmY, sOut, cch, tx * p.TW, ty * p.TH, tb * p.NB);
+            tma_store_4d(&tmY, sOut + 128 * 128, plane + cch, tx * p.TW, ty * p.TH, tb * p.NB);
+            tma_store_4d(&tmY, sOut, 2 * plane + cch, tx * p.TW, ty * p.TH, tb * p.NB);
+            tma_store_commit();
+          }
+          continue;
         }
         // staging tile `sbuf` is free once the TMA store issued two chunks ago has read it
         uint8_t* sbuf = sOut + (chunk_ctr & 1u) * (128 * 128);
@@ -671,8 +731,13 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   VD_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(d->y) & 15) == 0,
              "vd_conv_plan_create: tensors must be 16-byte aligned");
-  VD_REQUIRE(d->dst_coff % 32 == 0 && d->dst_C % 8 == 0 && d->dst_coff + d->Cout <= d->dst_C,
+  const bool split_mode = (d->flags & VD_CONV_SPLIT) != 0;
+  VD_REQUIRE(d->dst_coff % 32 == 0 && d->dst_C % 8 == 0 &&
+                 d->dst_coff + d->Cout <= ((split_mode && !(d->flags & VD_CONV_OUT_F32)) ? d->dst_C / 3 : d->dst_C),
              "vd_conv_plan_create: bad destination slice");
+  VD_REQUIRE(!split_mode || !(d->flags & VD_CONV_DUAL), "vd_conv_plan_create: SPLIT and DUAL cannot be combined");
+  VD_REQUIRE(!split_mode || (d->flags & VD_CONV_OUT_F32) || d->dst_C % 3 == 0,
+             "vd_conv_plan_create: split destination must have 3 planes");
   if (d->flags & VD_CONV_UPADD) {
     // the FPN's F.interpolate(mode="nearest") source index floor(dst*in/out) must equal dst>>1
     // (reference layers.py:102,110; true for every ceil(n/2) pyramid) — checked, not assumed
@@ -712,7 +777,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   if (x0) {
     // conv1 7x7/2 p3 on the ingest layout: each filter row is one K block of 8 taps x 4 channels (64 bytes);
     // the x stride/pad are baked into the sliding-window tensor map.
-    R = 7; S = 1; cin_blocks = 1; sh = 2; ph = 3; sw = 1; pw = 0;
+    R = 7; S = 1; cin_blocks = split_mode ? 2 : 1; sh = 2; ph = 3; sw = 1; pw = 0;   // split: [w_hi | w_lo] per row
     VD_REQUIRE(d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3, "IN_X0 conv must be 7x7 s2 p3");
   } else {
     R = d->R; S = d->S; cin_blocks = d->Cin / 64; sh = sw = d->stride; ph = pw = d->pad;
@@ -870,10 +935,10 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
       delete pl;
       return VD_ERR_INVALID;
     }
-    cuuint64_t rdim[4] = {static_cast<cuuint64_t>(d->Cout), static_cast<cuuint64_t>(d->Wout),
-                          static_cast<cuuint64_t>(d->Hout), static_cast<cuuint64_t>(d->B)};
-    cuuint64_t rstr[3] = {static_cast<cuuint64_t>(d->Cout) * 2, static_cast<cuuint64_t>(d->Cout) * 2 * d->Wout,
-                          static_cast<cuuint64_t>(d->Cout) * 2 * d->Wout * d->Hout};
+    const cuuint64_t rC = static_cast<cuuint64_t>(d->Cout) * (split_mode ? 3 : 1);
+    cuuint64_t rdim[4] = {rC, static_cast<cuuint64_t>(d->Wout), static_cast<cuuint64_t>(d->Hout),
+                          static_cast<cuuint64_t>(d->B)};
+    cuuint64_t rstr[3] = {rC * 2, rC * 2 * d->Wout, rC * 2 * d->Wout * d->Hout};
     cuuint32_t rbox[4] = {64, static_cast<cuuint32_t>(k.TW), static_cast<cuuint32_t>(k.TH),
                           static_cast<cuuint32_t>(k.NB)};
     cuuint32_t res1[4] = {1, 1, 1, 1};

@@ -8,7 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdesens.so")
 LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libvdesens_fp16.so")}
 
-VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32, VD_CONV_IN_X0, VD_CONV_DUAL = 1, 2, 4, 8, 16, 32
+VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32 = 1, 2, 4, 8
+VD_CONV_IN_X0, VD_CONV_DUAL, VD_CONV_SPLIT = 16, 32, 64
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
 VD_NMS_MAX_CAND = 8192
@@ -47,6 +48,7 @@ _SIGS = {
     "vd_conv_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vd_conv_plan_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6),
     "vd_maxpool3x3s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vd_maxpool3x3s2_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vd_decode_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vd_decode_threshold_lcl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -29,9 +29,13 @@ class DetectorEngine:
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
-        self.precision = precision            # "bf16" (BASELINE's dtype) or "fp16" (libvdesens_fp16.so)
-        self.act_dtype = _lib.torch_dtype(precision)
-        self.lib = _lib.lib(precision)
+        # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
+        # planes for activations and weights, three tensor-core products per term (VD_CONV_SPLIT), ~1/3 of the speed
+        self.precision = precision
+        self.split = precision == "fp32x"
+        storage = "fp16" if self.split else precision
+        self.act_dtype = _lib.torch_dtype(storage)
+        self.lib = _lib.lib(storage)
         self.device = torch.device(device)
         self.B, self.H, self.W = int(batch), int(in_h), int(in_w)
         self.confidence, self.nms_iou = float(confidence), float(nms_iou)
@@ -51,8 +55,9 @@ class DetectorEngine:
     # ------------------------------------------------------------------------------------------
     def _build(self, state_dict, scratch_frames):
         dev, B, H, W = self.device, self.B, self.H, self.W
-        convs, ops, bufs = arch.build_graph()
-        packed = weights.pack_all(state_dict, self.act_dtype)
+        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split)
+        packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
+        P = 3 if self.split else 1            # channel planes per activation tensor
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
         self.Wp = self.lib.vd_x0_pitch(W)
         self.buf, self.buf_hw = {}, {}
@@ -62,7 +67,7 @@ class DetectorEngine:
             if bs.name == "x0":
                 self.buf["x0"] = torch.zeros((B, H, self.Wp, 4), dtype=self.act_dtype, device=dev)
             else:
-                self.buf[bs.name] = torch.empty((B, h, w, bs.channels), dtype=self.act_dtype, device=dev)
+                self.buf[bs.name] = torch.empty((B, h, w, P * bs.channels), dtype=self.act_dtype, device=dev)
         self.heads = []
         for lvl, s in enumerate(arch.CFG_RE50["steps"]):
             h, w = arch.feature_hw(H, W, s)
@@ -76,8 +81,11 @@ class DetectorEngine:
             if op.kind == "conv":
                 c = op.conv
                 flags = _lib.VD_CONV_RELU if c.relu else 0
+                if self.split:
+                    flags |= _lib.VD_CONV_SPLIT
                 hin, win, cin = self.buf_hw[op.src]
                 hout, wout, dst_c = self.buf_hw[op.dst]
+                cin, dst_c = P * cin, P * dst_c
                 d = _lib.VdConvDesc()
                 d.B, d.Hin, d.Win = B, hin, win
                 if op.src == "x0":
@@ -93,7 +101,7 @@ class DetectorEngine:
                 if op.residual:
                     flags |= _lib.VD_CONV_RESIDUAL
                     res = self.buf[op.residual]
-                    assert tuple(res.shape) == (B, hout, wout, c.cout)
+                    assert tuple(res.shape) == (B, hout, wout, P * c.cout)
                 if op.src2:
                     flags |= _lib.VD_CONV_DUAL
                     x2 = self.buf[op.src2]
@@ -115,12 +123,12 @@ class DetectorEngine:
             elif op.kind == "heads":
                 hin, win, cin = self.buf_hw[op.src]
                 d = _lib.VdConvDesc()
-                d.B, d.Hin, d.Win, d.Cin = B, hin, win, cin
+                d.B, d.Hin, d.Win, d.Cin = B, hin, win, P * cin
                 d.Hout, d.Wout, d.Cout = hin, win, arch.HEAD_ROWS
                 d.R = d.S = 1
                 d.stride, d.pad = 1, 0
                 d.dst_C, d.dst_coff = arch.HEAD_ROWS, 0
-                d.flags = _lib.VD_CONV_OUT_F32
+                d.flags = _lib.VD_CONV_OUT_F32 | (_lib.VD_CONV_SPLIT if self.split else 0)
                 wt, bt = self.w[f"heads.{op.level}"]
                 d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
                 d.y = self.heads[op.level].data_ptr()
@@ -243,8 +251,8 @@ class DetectorEngine:
             else:
                 src, dst = h
                 hh, ww, cc = self.buf_hw[src]
-                _lib.check(self.lib.vd_maxpool3x3s2(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s),
-                           "vd_maxpool3x3s2")
+                pool = self.lib.vd_maxpool3x3s2_split if self.split else self.lib.vd_maxpool3x3s2
+                _lib.check(pool(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s), "vd_maxpool3x3s2")
             if upto is not None and name == upto:
                 break
 
@@ -330,7 +338,11 @@ class DetectorEngine:
         self.stream.synchronize()
         if name == "x0":
             return self.buf["x0"][:, :, 3:3 + self.W, :3].permute(0, 3, 1, 2).float()
-        return self.buf[name].permute(0, 3, 1, 2).float()
+        t = self.buf[name]
+        if self.split:                         # value = hi plane + lo plane
+            C1 = t.shape[3] // 3
+            return (t[..., :C1].float() + t[..., C1:2 * C1].float()).permute(0, 3, 1, 2)
+        return t.permute(0, 3, 1, 2).float()
 
     def head_tensors(self):
         """(loc (B,A,4), cls logits (B,A,2), landms (B,A,10)) assembled from the fused head outputs in

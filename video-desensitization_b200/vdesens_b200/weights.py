@@ -37,11 +37,22 @@ def to_numpy_sd(sd):
     return out
 
 
-def pack_all(sd, dtype=torch.bfloat16):
-    """Returns {layer name: (w_packed bf16 CPU tensor [Cout, K], bias fp32 CPU tensor [Cout])} for every
+def _split(mat, dtype):
+    """fp32 matrix -> (hi, lo) in `dtype` with hi + lo ~= mat to ~2x the mantissa bits"""
+    t = torch.from_numpy(np.ascontiguousarray(mat))
+    hi = t.to(dtype)
+    lo = (t - hi.float()).to(dtype)
+    return hi, lo
+
+
+def pack_all(sd, dtype=torch.bfloat16, split=False):
+    """split=True (fp32-class mode, VD_CONV_SPLIT): activations are stored as planes [hi | lo | hi], so every tap's
+    weight slice becomes [w_hi | w_hi | w_lo] (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo); the stem, whose input is exact,
+    gets [w_hi | w_lo] per filter row.
+    Returns {layer name: (w_packed bf16 CPU tensor [Cout, K], bias fp32 CPU tensor [Cout])} for every
     conv of the graph plus 'heads.{0,1,2}' (the three 1x1 heads of a level fused to one N=32 GEMM)."""
     sd = to_numpy_sd(sd)
-    convs, _, _ = arch.build_graph()
+    convs, _, _ = arch.build_graph(fuse_downsample=not split)
     packed = {}
     for c in convs:
         w, b = _fold(sd, c)
@@ -54,9 +65,19 @@ def pack_all(sd, dtype=torch.bfloat16):
         else:
             mat = np.transpose(w, (0, 2, 3, 1)).reshape(c.cout, -1)
         if c.wkey2:      # fused projection: [conv3 K | downsample K], biases add
+            assert not split
             w2, b2 = _fold(sd, c, second=True)
             mat = np.concatenate([mat, w2.reshape(c.cout, -1)], axis=1)
             b = b + b2
+        if split:
+            if c.name == "body.conv1":
+                hi, lo = _split(mat.reshape(c.cout, 7, 32), dtype)
+                wt = torch.cat([hi, lo], dim=2).reshape(c.cout, -1).contiguous()
+            else:
+                hi, lo = _split(mat.reshape(c.cout, c.k * c.k, c.cin), dtype)
+                wt = torch.cat([hi, hi, lo], dim=2).reshape(c.cout, -1).contiguous()
+            packed[c.name] = (wt, torch.from_numpy(b.copy()))
+            continue
         packed[c.name] = (torch.from_numpy(np.ascontiguousarray(mat)).to(dtype),
                           torch.from_numpy(b.copy()))
     for lvl in range(3):
@@ -66,5 +87,9 @@ def pack_all(sd, dtype=torch.bfloat16):
             bs.append(np.asarray(sd[hk + ".bias"], np.float32))
         mat = np.concatenate(ws, 0)
         assert mat.shape == (arch.HEAD_ROWS, 256)
-        packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(dtype), torch.from_numpy(np.concatenate(bs)))
+        if split:
+            hi, lo = _split(mat, dtype)
+            packed[f"heads.{lvl}"] = (torch.cat([hi, hi, lo], dim=1).contiguous(), torch.from_numpy(np.concatenate(bs)))
+        else:
+            packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(dtype), torch.from_numpy(np.concatenate(bs)))
     return packed
