@@ -171,7 +171,8 @@ def run_ours(args):
 
     hbm_peak, tf_peak, peak_src = load_peaks()
     sd = synth.synthetic_state_dict(0, face_rate="r001")
-    eng = DetectorEngine(sd, BATCH, H, W, device=dev, confidence=0.5, nms_iou=0.4)
+    precision = os.environ.get("VD_BENCH_PRECISION", "bf16")        # bf16 = BASELINE's dtype; fp16 / fp32x for comparison
+    eng = DetectorEngine(sd, BATCH, H, W, device=dev, confidence=0.5, nms_iou=0.4, precision=precision)
     NB = 3                                   # distinct resident batches, cycled
     base = rank * 100000                     # every rank owns different frames (sharded stream)
     host_batches = [[synth.synthetic_frame(H, W, 1000 + base + b * BATCH + i) for i in range(BATCH)] for b in range(NB)]
@@ -267,7 +268,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32x": "f16x3 (split hi/lo, fp32-class)"}[precision],
+        "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BATCH * H * W * 3,
                 "d2h_bytes_per_step": BATCH * H * W * 3 + int(rows.nbytes) + int(counts.nbytes) + 4,
                 "steps": e2e_steps, "host_ms_per_batch": e2e_host, "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step (double-buffered), max over ranks"},
