@@ -33,6 +33,10 @@ H, W, BATCH = 1080, 1920, 16
 KSIZE = 31
 N_PLATES = 4
 CONV_GFLOP_PER_FRAME = 449.71          # 82 convs at 1080p, 2*MAC
+# average dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 16-frame step, from the ncu capture
+# summarised in profiles/r01_ncu_summary.md §2 (33.96 GB over the 73 captured launches); algorithmic activation traffic
+# is 2.085 GB/frame * 16 = 33.4 GB per step, i.e. no wasted re-reads
+CONV_DRAM_BYTES_PER_LAUNCH = 4.65e8
 METRIC = "1080p detect+blur frames/sec"
 
 
@@ -265,6 +269,7 @@ def run_ours(args):
     e2e_value = BATCH * e2e_steps * world / (e2e_ms / 1e3)
     launches_per_step = eng.launches_per_forward + 2          # + composite plan/run
     tflops = CONV_GFLOP_PER_FRAME * BATCH / net_ms            # GFLOP / ms = TFLOP/s
+    n_conv = sum(1 for kind, _, _ in eng.plans if kind == "conv")
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -277,7 +282,11 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3; + maxpool)" % (len(eng.plans) - 1),
                      "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
-                     "peak_source": peak_src + " bf16_tflops_sustained", "traffic": None,
+                     "peak_source": peak_src + " bf16_tflops_sustained",
+                     "traffic": CONV_DRAM_BYTES_PER_LAUNCH if precision == "bf16" else None,
+                     "traffic_note": "avg DRAM bytes per conv launch (ncu, profiles/r01_ncu_summary.md)",
+                     "launches_per_step": n_conv, "avg_launch_ms": net_ms / n_conv,
+                     "algorithmic_flops_per_launch": CONV_GFLOP_PER_FRAME * 1e9 * BATCH / n_conv,
                      "algorithmic_flops_per_step": CONV_GFLOP_PER_FRAME * 1e9 * BATCH, "segment_ms": net_ms},
         "segments_ms": {"network": net_ms, "decode_nms": post_ms, "composite": comp_ms,
                         "copy_ingest": ms_total / args.steps - net_ms - post_ms - comp_ms},
