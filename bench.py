@@ -50,17 +50,18 @@ def load_peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    """samples nvidia-smi clocks / throttle reasons; started before the warm-up (nvidia-smi needs a moment to come
+    up) and evaluated over the wall-clock windows of the timed regions"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -69,29 +70,36 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for s in self.samples:
+        sm, mx, reasons, n_in = [], None, set(), 0
+        for ts, s in self.samples:
+            inside = any(t0 - 0.05 <= ts <= t1 + 0.1 for t0, t1 in self.windows)
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                clk, mx = float(f[0]), float(f[1])
             except ValueError:
                 continue
+            if not inside:
+                continue
+            n_in += 1
+            sm.append(clk)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        busy = [v for v in sm if mx and v > 0.3 * mx] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": n_in, "samples_total": len(self.samples),
+                "windows": "device-timed steps + end-to-end steps"}
 
 
 def dist_env():
@@ -204,6 +212,9 @@ def run_ours(args):
             if ev is not None:
                 ev[3].record(st)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
     st.synchronize()
@@ -214,10 +225,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    if sampler:
-        sampler.start()
+    tw0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seg = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e0.record(st)
@@ -226,7 +235,8 @@ def run_ours(args):
     e1.record(st)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
+    if sampler:
+        sampler.window(tw0, time.time())
     rows, counts = eng.fetch_results()
     net_ms = sum(s[0].elapsed_time(s[1]) for s in seg) / args.steps
     post_ms = sum(s[1].elapsed_time(s[2]) for s in seg) / args.steps
@@ -250,6 +260,9 @@ def run_ours(args):
         checksum += int(out[0, 0, 0, 0])                # the result is host-visible here
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    if sampler:
+        sampler.window(time.time() - e2e_ms / 1e3, time.time())
+    clocks = sampler.stop() if sampler else None
     e2e_host = {k: (v * 1e3 / max(1, sa.stats["batches"]) if k != "batches" else v) for k, v in sa.stats.items()}
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
