@@ -738,3 +738,32 @@ def test_fp32x_network_within_1e3_of_reference(det_gold, sd_np, case):
         # identical kept sets unless a score sits within 1e-3 of the threshold (none in these fixtures)
         assert got.shape == want.shape
         np.testing.assert_allclose(got, want, atol=1e-3, rtol=0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_composite_randomized_against_oracle(ops, seed):
+    """randomised property check: any mix of box sizes / positions / kernel sizes / modes on frames of odd sizes
+    equals the sequential reference semantics byte for byte (includes degenerate, 1-pixel, frame-sized and
+    off-frame boxes, and kernels wider than the box)."""
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(40, 260)), int(rng.integers(40, 400))
+    nfr = int(rng.integers(1, 4))
+    frames = [synth.synthetic_frame(H, W, 9000 + 10 * seed + i) for i in range(nfr)]
+    mode = "mosaic" if seed % 2 else "gauss"
+    ksize = int(rng.choice([3, 9, 21, 31, 61, 127]))
+    level = int(rng.integers(2, 17))
+    boxes = []
+    for i in range(nfr):
+        bl = []
+        for _ in range(int(rng.integers(0, 60))):
+            x1, y1 = int(rng.integers(-40, W + 10)), int(rng.integers(-40, H + 10))
+            bw, bh = int(rng.integers(-3, W)), int(rng.integers(-3, H))
+            bl.append((x1, y1, x1 + bw, y1 + bh))
+        bl += [(0, 0, W, H), (W // 2, H // 2, W // 2 + 1, H // 2 + 1)]
+        boxes.append(bl)
+    want = [co.composite(f, b, mode, level, ksize) for f, b in zip(frames, boxes)]
+    dfr = _dev_frames([f.copy() for f in frames])
+    ops.composite(dfr, boxes, mode, mosaic_level=level, ksize=ksize)
+    for i in range(nfr):
+        got = dfr[i].cpu().numpy()
+        assert np.array_equal(got, want[i]), (seed, mode, ksize, level, i, int((got != want[i]).sum()))

@@ -95,11 +95,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trap (-> CUDA error on the host), never as a
-// hung GPU.  ~2^28 polls of a HW-suspended try_wait is several seconds.
+// hung GPU.  try_wait suspends the thread in hardware for up to a few microseconds per poll, so 2^24 polls is
+// tens of seconds — far beyond any legitimate wait in these kernels (< 1 ms).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

@@ -80,15 +80,6 @@ struct ConvCfg {
   static constexpr int BIAS_BYTES = 1024;
   static constexpr int FIXED_BYTES = OUT_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // +1024: alignment
   static constexpr int THREADS = RES ? 352 : 320;                             // +1 warp: residual producer
-  // operand region: `stages` A tiles, then either `stages` B tiles or the resident weight matrix
-  static int stages_for(int wres, int w_bytes) {
-    const int avail = kSmemBudget - FIXED_BYTES - (wres ? w_bytes : 0);
-    int st = avail / (wres ? A_BYTES : A_BYTES + B_BYTES);
-    return st > kMaxStages ? kMaxStages : st;
-  }
-  static int smem_for(int stages, int wres, int w_bytes) {
-    return FIXED_BYTES + stages * A_BYTES + (wres ? w_bytes : stages * B_BYTES);
-  }
 };
 
 constexpr int kEpiThreads = 256;
