@@ -767,3 +767,28 @@ def test_composite_randomized_against_oracle(ops, seed):
     for i in range(nfr):
         got = dfr[i].cpu().numpy()
         assert np.array_equal(got, want[i]), (seed, mode, ksize, level, i, int((got != want[i]).sum()))
+
+
+def test_detector_called_from_pool_threads_like_the_reference(sd_np):
+    """reference combine_detect.py:214-217: detect_images runs on a ThreadPoolExecutor worker while a sibling
+    thread drives another model on the same GPU.  Results must equal the main-thread results."""
+    from concurrent.futures import ThreadPoolExecutor
+    from detect_face.face import Retinaface
+    det = Retinaface(state_dict=sd_np, input_shape=[160, 224, 3], confidence=0.5, nms_iou=0.4, batch_size=2)
+    frames = [synth.synthetic_frame(160, 224, 77 + i) for i in range(2)]
+    want = det.detect_images(frames)
+
+    def other_model(batch, verbose=False, conf=0.5):
+        a = torch.randn(512, 512, device=DEV)
+        for _ in range(20):
+            a = a @ a / 512.0
+        torch.cuda.synchronize()
+        return [(None, [[1, 2, 30, 40]]) for _ in batch]
+
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        for _ in range(3):
+            f1 = ex.submit(det.detect_images, list(frames))
+            f2 = ex.submit(other_model, list(frames), verbose=False, conf=0.5)
+            got, plates = f1.result(), f2.result()
+            assert [b for _, b in got] == [b for _, b in want]
+            assert len(plates) == 2

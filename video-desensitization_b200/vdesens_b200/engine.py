@@ -24,6 +24,20 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _on_device(fn):
+    """run the method with the engine's GPU as the current CUDA device: the reference calls the detector from
+    pool threads (combine_detect.py:214-217), whose current device is 0 regardless of where the engine lives"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16"):
@@ -37,6 +51,8 @@ class DetectorEngine:
         self.act_dtype = _lib.torch_dtype(storage)
         self.lib = _lib.lib(storage)
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.B, self.H, self.W = int(batch), int(in_h), int(in_w)
         self.confidence, self.nms_iou = float(confidence), float(nms_iou)
         assert cand_cap >= 64 and (cand_cap & (cand_cap - 1)) == 0 and cand_cap <= _lib.VD_NMS_MAX_CAND
@@ -164,6 +180,7 @@ class DetectorEngine:
         self._plan_handles.append(h)
         return h
 
+    @_on_device
     def plan_info(self):
         out = []
         for kind, h, name in self.plans:
@@ -182,6 +199,7 @@ class DetectorEngine:
             pass
 
     # ------------------------------------------------------------------------------------------
+    @_on_device
     def set_frames(self, frames_u8, shapes=None):
         """frames_u8: device uint8 tensor (B,h,w,3) or list of device tensors (h_i,w_i,3).
         Fills the frame descriptors and the un-letterbox parameters (fp32 arithmetic of reference
@@ -212,6 +230,7 @@ class DetectorEngine:
         self.identity = identity
         return identity
 
+    @_on_device
     def frame_records(self, frames_dev):
         """(desc (B,6) int32 device tensor of vd_frame_t records, unlb (B,4) fp32 device tensor, identity)
         for a resident frame tensor/list — built once per buffer and re-bound with bind_frames_async."""
@@ -219,6 +238,7 @@ class DetectorEngine:
         self.stream.synchronize()
         return self.frame_desc.clone(), self.unlb.clone(), self.identity
 
+    @_on_device
     def bind_frames_async(self, desc_dev, unlb_dev, identity, shapes=None):
         """stream-ordered switch of the frame set (device-to-device copies of the small records)."""
         with torch.cuda.stream(self.stream):
@@ -226,11 +246,13 @@ class DetectorEngine:
             self.unlb.copy_(unlb_dev, non_blocking=True)
         self.identity = identity
 
+    @_on_device
     def upload_ext_async(self, eb_pinned, ec_pinned):
         with torch.cuda.stream(self.stream):
             self.ext_boxes.copy_(eb_pinned, non_blocking=True)
             self.ext_count.copy_(ec_pinned, non_blocking=True)
 
+    @_on_device
     def download_results_async(self, rows_host, count_host, status_host):
         with torch.cuda.stream(self.stream):
             rows_host.copy_(self.out_rows, non_blocking=True)
@@ -238,11 +260,13 @@ class DetectorEngine:
             status_host.copy_(self.status, non_blocking=True)
 
     # ------------------------------------------------------------------------------------------
+    @_on_device
     def enqueue_ingest(self):
         s = C.c_void_p(self.stream.cuda_stream)
         fn = self.lib.vd_ingest_u8hwc_identity if self.identity else self.lib.vd_ingest_u8hwc
         _lib.check(fn(_ptr(self.frame_desc), self.B, _ptr(self.buf["x0"]), self.H, self.W, self._mean, s), "vd_ingest")
 
+    @_on_device
     def enqueue_network(self, upto=None):
         s = C.c_void_p(self.stream.cuda_stream)
         for kind, h, name in self.plans:
@@ -256,6 +280,7 @@ class DetectorEngine:
             if upto is not None and name == upto:
                 break
 
+    @_on_device
     def enqueue_postprocess(self):
         s = C.c_void_p(self.stream.cuda_stream)
         _lib.check(self.lib.vd_decode_threshold(_ptr(self.heads[0]), _ptr(self.heads[1]), _ptr(self.heads[2]),
@@ -263,12 +288,14 @@ class DetectorEngine:
                                                 _ptr(self.cand_count), _ptr(self.status), s), "vd_decode_threshold")
         self.enqueue_nms()
 
+    @_on_device
     def enqueue_nms(self):
         s = C.c_void_p(self.stream.cuda_stream)
         _lib.check(self.lib.vd_nms_batched(_ptr(self.cand), _ptr(self.cand_count), self.B, self.cap, self.nms_iou,
                                            _ptr(self.unlb), self.max_det, _ptr(self.out_rows), _ptr(self.out_count),
                                            _ptr(self.status), _ptr(self.nms_ws), self.nms_ws_bytes, s), "vd_nms_batched")
 
+    @_on_device
     def enqueue_composite(self, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, use_faces=True, use_ext=True):
         s = C.c_void_p(self.stream.cuda_stream)
         m = _lib.VD_MODE_MOSAIC if mode == "mosaic" else _lib.VD_MODE_GAUSS
@@ -293,6 +320,7 @@ class DetectorEngine:
         self.enqueue_network()
         self.enqueue_postprocess()
 
+    @_on_device
     def set_ext_boxes(self, boxes_per_frame):
         """externally supplied (plate) boxes: list (len B) of lists of (x1,y1,x2,y2) ints."""
         eb = np.zeros((self.B, self.max_ext, 4), np.int32)
@@ -309,6 +337,7 @@ class DetectorEngine:
             self.ext_count.copy_(torch.from_numpy(ec).pin_memory(), non_blocking=True)
         self.stream.synchronize()
 
+    @_on_device
     def fetch_results(self):
         """one D2H per batch + status check.  Returns (rows (B,max_det,16) numpy, counts (B,))."""
         with torch.cuda.stream(self.stream):
