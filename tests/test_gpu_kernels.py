@@ -490,6 +490,43 @@ def test_facade_detect_images_and_frame_loop(sd_np):
         Retinaface(state_dict=sd_np, input_shape=[160, 224, 3], letterbox_image=False).detect_images(frames)
 
 
+def test_directory_frame_loop_like_the_reference(sd_np, tmp_path):
+    """combine_detect.batch_process_images (reference :183-277) on a directory of lossless frames: same
+    return tuple, one processed_<name> file per input, pixels identical to the in-memory loop; the sequence
+    has a size change and one batch with mixed sizes, and an empty directory returns zeros."""
+    cv2 = pytest.importorskip("cv2")
+    from detect_face.face import Retinaface
+    import combine_detect
+    det = Retinaface(state_dict=sd_np, input_shape=[160, 224, 3], confidence=0.5, nms_iou=0.4, letterbox_image=True,
+                     cuda=True, batch_size=2)
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    sizes = [(160, 224)] * 5 + [(120, 200)] * 4          # batches of 2: aa aa a|b(mixed) bb b
+    frames = [synth.synthetic_frame(h, w, 3100 + i) for i, (h, w) in enumerate(sizes)]
+    for i, f in enumerate(frames):
+        cv2.imwrite(str(src / f"f{i:03d}.png"), cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    (src / "notes.txt").write_text("ignored")
+
+    def plates(batch, verbose=False, conf=0.5):
+        return [(None, [[3, 4, 50, 30]]) if k % 2 == 0 else [[9, 9, 20, 20]] for k, _ in enumerate(batch)]
+
+    n, nf, npl = combine_detect.batch_process_images(str(src), str(dst), det, plates, batch_size=2)
+    want, wf, wpl = [], 0, 0
+    for s in range(0, len(frames), 2):
+        o, a, b = combine_detect.batch_process_frames(frames[s:s + 2], det, plates, batch_size=2)
+        want += o
+        wf += a
+        wpl += b
+    assert (n, nf, npl) == (len(frames), wf, wpl) and npl == 5
+    assert sorted(os.listdir(dst)) == [f"processed_f{i:03d}.png" for i in range(len(frames))]
+    for i, w in enumerate(want):
+        got = cv2.cvtColor(cv2.imread(str(dst / f"processed_f{i:03d}.png")), cv2.COLOR_BGR2RGB)
+        assert np.array_equal(got, w), i
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    assert combine_detect.batch_process_images(str(empty), str(tmp_path / "o2"), det, None, batch_size=2) == (0, 0, 0)
+
+
 def test_streaming_pipeline_matches_oracle_compositing(sd_np):
     """the pipelined public path (double-buffered H2D / compute / D2H): results come back in order,
     frames are anonymised exactly as the oracle does with the boxes the detector returned, and the

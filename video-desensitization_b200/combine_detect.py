@@ -100,22 +100,113 @@ def save_output_image(image_array, output_path):
     cv2.imwrite(output_path, cv2.cvtColor(image_array, cv2.COLOR_RGB2BGR))
 
 
-def batch_process_images(input_dir, output_dir, face_detector, plate_detector, batch_size=16, mode="mosaic"):
-    """Same signature and return value as the reference (:183-277): (n_frames, n_faces, n_plates)."""
-    paths = [os.path.join(input_dir, f) for f in os.listdir(input_dir) if f.lower().endswith((".png", ".jpg", ".jpeg"))]
+class _Lookahead:
+    """iterator with a one-item peek (the frame loop decides per batch which path takes it)"""
+    _END = object()
+
+    def __init__(self, it):
+        self._it, self._head = iter(it), self._END
+        self._advance()
+
+    def _advance(self):
+        self._head = next(self._it, self._END)
+
+    def more(self):
+        return self._head is not self._END
+
+    def peek(self):
+        return self._head
+
+    def pop(self):
+        h = self._head
+        self._advance()
+        return h
+
+
+def _decoded_batches(groups, workers=6):
+    """yields (files, RGB frames) per group; group i+1 is decoded by a thread pool while group i is consumed"""
+    with ThreadPoolExecutor(max_workers=workers) as dec, ThreadPoolExecutor(max_workers=1) as ahead:
+        def load(files):
+            return list(dec.map(load_image_rgb, files))
+        fut = ahead.submit(load, groups[0]) if groups else None
+        for i, files in enumerate(groups):
+            frames = fut.result()
+            if i + 1 < len(groups):
+                fut = ahead.submit(load, groups[i + 1])
+            yield files, frames
+
+
+def _one_shape(frames):
+    shapes = {f.shape[:2] for f in frames}
+    return next(iter(shapes)) if len(shapes) == 1 else None
+
+
+def batch_process_images(input_dir, output_dir, face_detector, plate_detector, batch_size=16, mode="mosaic",
+                         mosaic_level=8, ksize=31, sigma=0.0):
+    """Same signature and return value as the reference (:183-277): (n_frames, n_faces, n_plates).
+
+    What changes is the schedule: the reference loads a batch, waits for both detectors,
+    mosaics on the CPU and only then loads the next batch.  Here batch i+1 is decoded by a thread pool while the
+    GPU processes batch i through the pipelined StreamingAnonymizer (H2D / compute / D2H overlapped) and the
+    saver pool encodes batch i-1.  Files are taken in sorted order, a failing batch raises instead of being
+    dropped silently (reference :226-228), and only tuple results of the plate provider are honoured (:239)."""
+    from collections import deque
+    from vdesens_b200.pipeline import StreamingAnonymizer
+    paths = sorted(os.path.join(input_dir, f) for f in os.listdir(input_dir)
+                   if f.lower().endswith((".png", ".jpg", ".jpeg")))
     os.makedirs(output_dir, exist_ok=True)
-    total, faces, plates = 0, 0, 0
-    with ThreadPoolExecutor(max_workers=6) as pool:
+    groups = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
+    n_frames = n_faces = n_plates = 0
+
+    def plates_of(frames):
+        res = plate_detector(list(frames), verbose=False, conf=0.5) if plate_detector is not None else None
+        return [[tuple(int(v) for v in b) for b in _plate_boxes(res, j)] for j in range(len(frames))]
+
+    with ThreadPoolExecutor(max_workers=6) as savers:
         saves = []
-        for i in range(0, len(paths), batch_size):
-            files = paths[i:i + batch_size]
-            batch = list(pool.map(load_image_rgb, files))
-            out, nf, npl = batch_process_frames(batch, face_detector, plate_detector, batch_size, mode)
+
+        def emit(files, out):
             for pth, img in zip(files, out):
-                saves.append(pool.submit(save_output_image, img, os.path.join(output_dir, "processed_" + os.path.basename(pth))))
-            total += len(files)
-            faces += nf
-            plates += npl
-        for s in saves:
-            s.result()
-    return total, faces, plates
+                saves.append(savers.submit(save_output_image, img,
+                                           os.path.join(output_dir, "processed_" + os.path.basename(pth))))
+
+        src = _Lookahead(_decoded_batches(groups))
+        while src.more():
+            shape = _one_shape(src.peek()[1])
+            if shape is None:
+                # mixed frame sizes inside one batch: every frame is letterboxed on its own (face.py:73-80)
+                files, frames = src.pop()
+                plates = plates_of(frames)
+                res = face_detector.detect_images(frames)
+                allb = [[tuple(int(v) for v in b) for b in r[1]] + plates[j] for j, r in enumerate(res)]
+                emit(files, composite_frames(frames, allb, mode, mosaic_level, ksize, sigma))
+                n_frames += len(files)
+                n_faces += sum(len(r[1]) for r in res)
+                n_plates += sum(len(p) for p in plates)
+                continue
+            # a run of consecutive batches of one frame size goes through the pipelined path
+            eng = face_detector._engine_for(min(batch_size, len(paths)))
+            sa = StreamingAnonymizer(eng, mode, mosaic_level, ksize, sigma)
+            inflight = deque()                       # (files, plate boxes) per submitted device batch
+
+            def device_batches():
+                while src.more() and _one_shape(src.peek()[1]) == shape:
+                    files, frames = src.pop()
+                    plates = plates_of(frames)
+                    for s in range(0, len(frames), eng.B):
+                        inflight.append((files[s:s + eng.B], plates[s:s + eng.B]))
+                        yield frames[s:s + eng.B]
+
+            def plate_boxes():                       # run() asks for these right after it took the batch
+                while True:
+                    yield inflight[-1][1]
+
+            for out, boxes in sa.run(device_batches(), plate_boxes(), copy_out=True):
+                files, plates = inflight.popleft()
+                emit(files, list(out))
+                n_frames += len(files)
+                n_faces += sum(len(b) for b in boxes)
+                n_plates += sum(len(p) for p in plates)
+        for f in saves:
+            f.result()
+    return n_frames, n_faces, n_plates
