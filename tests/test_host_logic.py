@@ -33,7 +33,7 @@ def test_host_only_entry_points():
     from vdesens_b200 import _lib
     from oracle import cv_oracle as co
     lib = _lib.lib()
-    assert lib.vd_x0_pitch(1920) == 1928 and lib.vd_x0_pitch(7) == 16 and lib.vd_x0_pitch(640) % 8 == 0
+    assert lib.vd_x0_pitch(1920) == 1936 and lib.vd_x0_pitch(7) == 16 and lib.vd_x0_pitch(640) % 16 == 0
     for k, s in [(1, 0), (3, 0), (7, 0), (9, 0), (31, 0), (99, 0), (15, 2.5), (255, 0)]:
         assert _lib.gaussian_taps_q8(k, s) == co.gaussian_taps_q8(k, s).tolist()
     assert lib.vd_gaussian_taps_q8(4, 0.0, (ctypes.c_uint16 * 256)()) != 0      # even ksize rejected

@@ -59,9 +59,10 @@ extern "C" int vd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return VD_OK;
 }
 
-// conv1 reads windows [2*xo, 2*xo+8) of the padded row; pixel x sits at column x+3.
+// conv1 reads windows [2*xo, 2*xo+8) of the padded row; pixel x sits at column x+3.  The pitch is a multiple of
+// 16 pixels (128 bytes) so that a row is a whole number of the 128-byte chunks conv1's tensor map is made of.
 extern "C" int vd_x0_pitch(int W) {
   const int Wout = (W + 1) / 2;
   const int need = 2 * Wout + 6;
-  return (need + 7) & ~7;
+  return (need + 15) & ~15;
 }

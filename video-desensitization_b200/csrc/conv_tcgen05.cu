@@ -31,6 +31,7 @@ namespace {
 struct ConvKParams {
   int TW, TH, NB;
   int tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;
+  uint32_t dv_n_mul, dv_n_shr, dv_x_mul, dv_x_shr, dv_y_mul, dv_y_shr;   // tile index -> (n, x, y, b) without IDIV
   int rows_used;          // TW*TH*NB
   int a_bytes;            // rows_used * 128
   int B, Hout, Wout, Cout;
@@ -70,7 +71,9 @@ constexpr int kWresMaxBytes = 72 * 1024;   // resident-weight limit (3x3 64->64 
 // whose K block is one filter row of 8 taps x 4 channels = 64 bytes (SWIZZLE_64B).
 template <int BN, bool RES, int ROWB = 128>
 struct ConvCfg {
-  static constexpr int A_BYTES = 128 * ROWB;
+  // operand slot of one K block; the stem's slot holds the seven raw row segments of one tile (each <= 17 chunks of
+  // 128 B, see hi_raw), fetched by ONE tensor-map box
+  static constexpr int A_BYTES = (ROWB == 64) ? 7 * 17 * 128 + 128 : 128 * ROWB;
   static constexpr int B_BYTES = BN * ROWB;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 384;
@@ -98,6 +101,25 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// q = n / d for n < 2^31 with a host-made (mul, shr) pair (d == 1 is encoded as mul = 0)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
+  return mul ? (__umulhi(n, mul) >> shr) : n;
+}
+
+struct TileCoord { int n_tile, tx, ty, tb; };
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) {
+  TileCoord c;
+  uint32_t m = fast_div(static_cast<uint32_t>(tile), p.dv_n_mul, p.dv_n_shr);
+  c.n_tile = tile - static_cast<int>(m) * p.n_tiles;
+  uint32_t m2 = fast_div(m, p.dv_x_mul, p.dv_x_shr);
+  c.tx = static_cast<int>(m) - static_cast<int>(m2) * p.tiles_x;
+  uint32_t m3 = fast_div(m2, p.dv_y_mul, p.dv_y_shr);
+  c.ty = static_cast<int>(m2) - static_cast<int>(m3) * p.tiles_y;
+  c.tb = static_cast<int>(m3);
+  return c;
 }
 
 template <int BN, bool RES, int ROWB>
@@ -186,12 +208,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES));
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
-      const int tx = m % p.tiles_x;
-      m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int tb = m / p.tiles_y;
+      const TileCoord tc = tile_coord(p, tile);
+      const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
       const int xin0 = tx * p.TW * p.stride_w - p.pad_w;
       const int yin0 = ty * p.TH * p.stride_h - p.pad_h;
       const int b0 = tb * p.NB;
@@ -225,6 +243,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (ROWB == 64) {
+        // stem: the RAW padded input rows 2y-3 .. 2y+3, pixels [2*X0, 2*X0 + 2*TW + 6) (8 B each) as whole 128-byte
+        // chunks — one box per tile; the MMAs read it as a sliding window (see hi_raw below)
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(7 * p.a_bytes));
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], 0, (tx * p.TW) >> 3, yin0, b0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        continue;
+      }
       int r = 0, sx = 0, cb = 0;
       for (int kb = 0; kb < KB; kb += KPS) {
         const int n = min(KPS, KB - kb);
@@ -234,8 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < n; ++j) {
           if (leader) {
             if (kb + j < p.kb1)
-              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage],
-                          (p.flags & VD_CONV_IN_X0) ? 0 : cb * 64, xin0 + sx, yin0 + r, b0);
+              tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, xin0 + sx, yin0 + r, b0);
             else        // second K segment: 1x1 projection of x2 at (x*stride2, y*stride2)
               tma_load_4d(sA + (stage * KPS + j) * Cfg::A_BYTES, &tmA2, &full[stage], (kb + j - p.kb1) * 64,
                           tx * p.TW * p.stride2, ty * p.TH * p.stride2, b0);
@@ -266,6 +298,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                (static_cast<uint32_t>(128 >> 4) << 24);
     // descriptor words: lo = start>>4 | LBO(1)<<16 ; hi = SBO>>4 | version(1)<<14 | SWIZZLE_128B(2)<<29
     constexpr uint32_t hi_std = (static_cast<uint32_t>(8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    // stem (ROWB == 64): A is the raw input row in shared memory, NO swizzle, read through the canonical K-major
+    // layout with LBO = 16 B (next 16-byte chunk along K) and SBO = 128 B (next 8 rows): row i,
+    // chunk c sits at 16*i + 16*c — output pixel i's window starts 2 input pixels (16 B) after pixel i-1's, so the
+    // overlapping windows are never materialised (one 2 KB row segment instead of a 128 x 64 B operand tile).
+    constexpr uint32_t hi_raw = (128u >> 4) | (1u << 14);
+    constexpr uint32_t hi_a = (ROWB == 64) ? hi_raw : hi_std;
     constexpr int MMAS = ROWB / 32;             // K = 16 bf16 = 32 bytes per tcgen05.mma
     const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -314,6 +352,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             aphase ^= 1u;
           }
         }
+      } else if (ROWB == 64) {
+        // stem: one stage = one tile; K block kb reads raw row kb / cin_blocks (split mode: [w_hi | w_lo] per row)
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_row = static_cast<uint32_t>(p.a_bytes >> 4);
+          uint32_t al = a_lo0 + static_cast<uint32_t>(stage * (Cfg::A_BYTES >> 4));
+          uint32_t bl = b_lo0;
+          for (int r = 0; r < 7; ++r, al += a_row) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb, bl += (Cfg::B_BYTES >> 4)) {
+              umma_bf16_words(d_tmem, al, hi_a, bl, hi_std, idesc, static_cast<uint32_t>((r | cb) != 0));
+              umma_bf16_words(d_tmem, al + 2, hi_a, bl + 2, hi_std, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
       } else {
         for (int kb = 0; kb < KB; kb += KPS) {
           const int n = min(KPS, KB - kb);
@@ -325,10 +385,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t bl =
                   b_lo0 + static_cast<uint32_t>((p.wres ? kb + j : stage * KPS + j) * (Cfg::B_BYTES >> 4));
               // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
-              umma_bf16_words(d_tmem, al, hi_std, bl, hi_std, idesc, static_cast<uint32_t>((kb + j) != 0));
+              umma_bf16_words(d_tmem, al, hi_a, bl, hi_std, idesc, static_cast<uint32_t>((kb + j) != 0));
 #pragma unroll
               for (int q = 1; q < MMAS; ++q)
-                umma_bf16_words(d_tmem, al + 2 * q, hi_std, bl + 2 * q, hi_std, idesc, 1u);
+                umma_bf16_words(d_tmem, al + 2 * q, hi_a, bl + 2 * q, hi_std, idesc, 1u);
             }
             umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
             if (kb + KPS >= KB) umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
@@ -350,12 +410,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int slot = 0;
       uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
-        const int tx = m % p.tiles_x;
-        m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tb = m / p.tiles_y;
+        const TileCoord tc = tile_coord(p, tile);
+        const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
         const int nplanes = (p.flags & VD_CONV_SPLIT) ? 2 : 1;      // split residual = hi plane + lo plane
         for (int ch = 0; ch < NCHUNK_R; ++ch) {
           for (int pl = 0; pl < nplanes; ++pl) {
@@ -393,12 +449,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int bias_tile = -1;
     const int etid = threadIdx.x - 64;               // 0..255 inside the epilogue group
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
-      const int tx = m % p.tiles_x;
-      m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int tb = m / p.tiles_y;
+      const TileCoord tc = tile_coord(p, tile);
+      const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
       const int x = tx * p.TW + tx_;
       const int y = ty * p.TH + ty_;
       const int b = tb * p.NB + nb_;
@@ -652,6 +704,16 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
     pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + k.stages * k.kps * Cfg::B_BYTES;
     return k.stages >= min_stages;
   }
+  if (ROWB == 64) {
+    // stem: weights resident, one pipeline stage = the raw rows of one tile
+    k.wres = 1;
+    k.w_bytes = KB * Cfg::B_BYTES;
+    k.kps = 1;
+    const int st = (avail - k.w_bytes) / Cfg::A_BYTES;
+    k.stages = st > kMaxStages ? kMaxStages : st;
+    pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * Cfg::A_BYTES;
+    return k.stages >= min_stages;
+  }
   const int w_bytes = KB * Cfg::B_BYTES;
   k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && w_bytes * 2 <= avail && k.num_tiles > pl->grid &&
             BN <= 64 && KB >= 4) ? 1 : 0;
@@ -662,7 +724,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   if (BN <= 64) kps = k.wres ? 4 : 2;
   else if (BN == 128) kps = 2;
   if (kps > KB) kps = KB;
-  if (force_kps > 0 && force_kps <= 4) kps = force_kps > KB ? KB : force_kps;
+  if (force_kps > 0 && force_kps <= 8) kps = force_kps > KB ? KB : force_kps;
   const int per_block = Cfg::A_BYTES + (k.wres ? 0 : Cfg::B_BYTES);
   int st = (avail - k.w_bytes) / (kps * per_block);
   while (st < min_stages && kps > 1) {
@@ -774,6 +836,14 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     R = d->R; S = d->S; cin_blocks = d->Cin / 64; sh = sw = d->stride; ph = pw = d->pad;
   }
   choose_tile(d->Wout, d->Hout, d->B, sw, sh, &k.TW, &k.TH, &k.NB);
+  if (x0) {
+    // stem tile = one run of TW output pixels of one row; TW is a multiple of 8 so that the run's first input
+    // pixel (2*X0) starts a 128-byte chunk; fewest tiles first, then the narrowest
+    int best = -1;
+    for (int tw = 8; tw <= 128; tw += 8)
+      if (best < 0 || vd_cdiv(d->Wout, tw) < vd_cdiv(d->Wout, best)) best = tw;
+    k.TW = best; k.TH = 1; k.NB = 1;
+  }
   {
     // halo-patch mode: 3x3 stride-1 convs whose N tile is narrow are bound by the 9x re-fetch of the A tile
     // from L2 (~25 B/clk/SM of unique data); an 8x16 pixel tile + halo is fetched once per 64-channel slice.
@@ -794,8 +864,22 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.tiles_b = vd_cdiv(d->B, k.NB);
   k.n_tiles = d->Cout / BN;
   k.num_tiles = k.tiles_x * k.tiles_y * k.tiles_b * k.n_tiles;
+  {
+    auto magic = [](int d, uint32_t* mul, uint32_t* shr) {
+      if (d <= 1) { *mul = 0; *shr = 0; return; }
+      int lg = 0;
+      while ((1u << lg) < static_cast<uint32_t>(d)) ++lg;
+      const int pw = 31 + lg;
+      *mul = static_cast<uint32_t>(((1ull << pw) + static_cast<unsigned long long>(d) - 1) / d);
+      *shr = static_cast<uint32_t>(pw - 32);
+    };
+    magic(k.n_tiles, &k.dv_n_mul, &k.dv_n_shr);
+    magic(k.tiles_x, &k.dv_x_mul, &k.dv_x_shr);
+    magic(k.tiles_y, &k.dv_y_mul, &k.dv_y_shr);
+  }
   k.rows_used = k.TW * k.TH * k.NB;
-  k.a_bytes = k.rows_used * (x0 ? 64 : 128);
+  const int x0_chunks = (2 * k.TW + 6 + 15) / 16;          // 128-byte chunks of one stem row segment
+  k.a_bytes = x0 ? x0_chunks * 128 : k.rows_used * 128;
   k.B = d->B; k.Hout = d->Hout; k.Wout = d->Wout; k.Cout = d->Cout;
   k.R = R; k.S = S; k.cin_blocks = cin_blocks;
   k.kb1 = R * S * cin_blocks;
@@ -826,10 +910,10 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t box[4], estr[4];
   if (x0) {
-    const int Wp = vd_x0_pitch(d->Win);
-    gdim[0] = 32; gdim[1] = static_cast<cuuint64_t>(d->Wout); gdim[2] = static_cast<cuuint64_t>(d->Hin);
+    const int Wp = vd_x0_pitch(d->Win);                   // multiple of 16 pixels
+    gdim[0] = 64; gdim[1] = static_cast<cuuint64_t>(Wp / 16); gdim[2] = static_cast<cuuint64_t>(d->Hin);
     gdim[3] = static_cast<cuuint64_t>(d->B);
-    gstr[0] = 16;                                         // next output column = 2 pixels * 8 B
+    gstr[0] = 128;                                        // one chunk = 16 pixels * 8 B
     gstr[1] = static_cast<cuuint64_t>(Wp) * 8;
     gstr[2] = static_cast<cuuint64_t>(Wp) * 8 * d->Hin;
   } else {
@@ -839,12 +923,13 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     gstr[1] = gstr[0] * d->Win;
     gstr[2] = gstr[1] * d->Hin;
   }
-  box[0] = x0 ? 32 : 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
+  box[0] = 64; box[1] = static_cast<cuuint32_t>(k.TW * sw); box[2] = static_cast<cuuint32_t>(k.TH * sh);
   box[3] = static_cast<cuuint32_t>(k.NB);
   if (k.patch) { box[1] = static_cast<cuuint32_t>(k.PW); box[2] = static_cast<cuuint32_t>(k.PH); }
   estr[0] = 1; estr[1] = static_cast<cuuint32_t>(sw); estr[2] = static_cast<cuuint32_t>(sh); estr[3] = 1;
+  if (x0) { box[1] = static_cast<cuuint32_t>(x0_chunks); box[2] = 7; estr[1] = estr[2] = 1; }
   CUresult r = enc(&pl->tmA, kActTmapType, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, x0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
