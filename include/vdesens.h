@@ -103,6 +103,10 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
                                   are [w_hi | w_hi | w_lo] per tap, so x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulates
                                   in fp32.  dst_C, the residual and the upadd tensor have 3*C channels; the epilogue
                                   writes hi, lo and the hi copy.  Not combinable with VD_CONV_DUAL. */
+#define VD_CONV_POOL 128u      /* with VD_CONV_IN_X0 | VD_CONV_RELU: torchvision's maxpool (3x3, stride 2, pad 1) is applied
+                                  to the convolution's output inside the kernel; Hout/Wout stay conv1's extents and y is
+                                  the POOLED tensor [B][(Hout+1)/2][(Wout+1)/2][64] (reference retinaface.py:71-73: the
+                                  conv1 -> bn1 -> relu -> maxpool head of the ResNet body) */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 

@@ -199,6 +199,50 @@ def test_conv1_on_ingest_layout(ops, hw):
     assert bool((err <= 2.0 ** -7 * want.abs().clamp_min(4.0)).all()), f"max err {float(err.max())}"
 
 
+@pytest.mark.parametrize("hw", [(32, 48), (45, 77), (96, 128), (135, 241), (270, 480), (540, 500)])
+@pytest.mark.parametrize("B", [1, 3])
+def test_conv1_with_fused_maxpool_is_bit_identical(ops, hw, B):
+    """VD_CONV_POOL: conv1+bn1+relu+maxpool (reference retinaface.py:71-73) as ONE kernel must give exactly the
+    bytes of the two-kernel form — same MMA sequence per output, and a max of bf16 values is exact.  Sizes cover
+    several column strips, ragged last strips / row runs, odd extents and the -inf padding rule of the pool."""
+    H, W = hw
+    frames = [synth.synthetic_frame(H, W, 170 + i) for i in range(B)]
+    x0 = ops.ingest(_dev_frames(frames), H, W)
+    g = torch.Generator(device="cpu").manual_seed(19)
+    w = (torch.randn((64, 3, 7, 7), generator=g) / 12.0)
+    bias = torch.randn((64,), generator=g).to(DEV)
+    wp = torch.zeros((64, 7, 8, 4))
+    wp[:, :, :7, :3] = w.permute(0, 2, 3, 1)
+    wp = wp.reshape(64, -1).to(torch.bfloat16).to(DEV)
+    c1 = ops.conv2d(x0, wp, bias, 7, 2, 3, relu=True, x0_hw=(H, W))
+    want = ops.maxpool3x3s2(c1)
+    got = ops.conv2d(x0, wp, bias, 7, 2, 3, relu=True, x0_hw=(H, W), pool=True)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert torch.equal(got, want), f"{int((got != want).sum())} of {got.numel()} values differ"
+    ref = torch.nn.functional.max_pool2d(c1.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(got.float(), ref)
+
+
+def test_fused_stem_pool_engine_matches_two_kernel_engine(sd_np):
+    """the engine's default graph (conv1+pool fused) against the explicit two-kernel graph: identical p1, heads,
+    detections."""
+    from vdesens_b200.engine import DetectorEngine
+    H, W = 160, 224
+    frames = [synth.synthetic_frame(H, W, 640 + i) for i in range(2)]
+    outs = []
+    for fuse in (True, False):
+        eng = DetectorEngine(sd_np, 2, H, W, device=DEV, confidence=0.5, nms_iou=0.4, fuse_stem_pool=fuse)
+        assert eng.fuse_stem_pool == fuse and (("c1" in eng.buf) != fuse)
+        eng.set_frames(_dev_frames(frames))
+        eng.forward()
+        rows, counts = eng.fetch_results()
+        outs.append((eng.activation("p1").cpu(), [h.cpu() for h in eng.heads], rows.copy(), counts.copy()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+    assert np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][2], outs[1][2])
+
+
 def test_maxpool_exact(ops):
     g = torch.Generator(device="cpu").manual_seed(3)
     for (B, H, W, Cc) in [(2, 48, 64, 64), (1, 45, 77, 64), (1, 7, 5, 128)]:
@@ -397,7 +441,7 @@ def test_network_vs_bf16_emulated_oracle(det_gold, sd_np, case):
     cap = {}
     eloc, ecls, eldm = ro.forward_bf16_emulated(weights.pack_all(sd_np), x, capture=cap)
     report = []
-    for name in ["c1", "p1", "layer1.0.out", "layer1.2.out", "layer2.3.out", "layer3.5.out", "layer4.2.out",
+    for name in (["c1"] if "c1" in eng.buf else []) + ["p1", "layer1.0.out", "layer1.2.out", "layer2.3.out", "layer3.5.out", "layer4.2.out",
                  "fpn.o3", "fpn.o2", "fpn.o1", "ssh1.out", "ssh2.out", "ssh3.out"]:
         a, b = eng.activation(name).cpu(), cap[name]
         mx = float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
@@ -408,7 +452,7 @@ def test_network_vs_bf16_emulated_oracle(det_gold, sd_np, case):
     # accumulation-order differences flip a bf16 rounding now and then; the flips propagate like any
     # other bf16 noise through this (chaotic, untrained) network: rms <= 3 %, max <= 8 % of the range
     assert all(m <= 0.08 and r <= 0.03 for _, m, r in report), msg
-    assert report[0][1] <= 0.004 and report[1][1] <= 0.004, msg          # conv1 / pool: first layer is tight
+    assert report[0][1] <= 0.004 and report[1][1] <= 0.008, msg          # conv1 / pool: first layers are tight
     assert float((loc - eloc).abs().max()) <= 0.06, msg
     assert float((cls - ecls).abs().max()) <= 0.06, msg
     assert float((ldm - eldm).abs().max()) <= 0.06, msg

@@ -52,7 +52,7 @@ with torch.cuda.stream(eng.stream):
         rows.append((name, ms))
 # flops per layer from output extents
 out_hw = {}
-_, ops_, _ = arch.build_graph()
+_, ops_, _ = arch.build_graph(fuse_stem_pool=eng.fuse_stem_pool)
 for op in ops_:
     if op.kind == "conv":
         hh, ww, _ = eng.buf_hw[op.dst]

@@ -25,6 +25,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "stem_pool.h"
 
 namespace {
 
@@ -485,10 +486,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int nplanes = split ? 2 : 1;
           for (int pl = 0; pl < nplanes; ++pl) {
             mbar_wait(&rfull[rslot], rphase);
-            const uint8_t* rrow = sRes + rslot * (128 * 128) + row * 128;
+            const uint32_t rrow = smem_u32(sRes) + rslot * (128 * 128) + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 t = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
+              const uint4 t = lds128(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
               if (pl == 0) rcur[j] = t; else rlo[j] = t;
             }
             __syncwarp();
@@ -502,14 +503,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float f[32];
         if (active) {
           tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(sBias + ch * 64 + half * 32);
+          const uint32_t bp = smem_u32(sBias) + static_cast<uint32_t>((ch * 64 + half * 32) * 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = bp[j];
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+            const uint4 bv = lds128(bp + j * 16);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + __uint_as_float(bv.x);
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bv.y);
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bv.z);
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bv.w);
           }
           if (RES) {
 #pragma unroll
@@ -555,8 +556,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiThreads);
           if (active) {
-            uint8_t* hrow = sOut + row * 128;
-            uint8_t* lrow = sOut + 128 * 128 + row * 128;
+            const uint32_t hrow = smem_u32(sOut) + row * 128;
+            const uint32_t lrow = hrow + 128 * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 h, l;
@@ -569,8 +570,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               l.z = pack_bf16x2(f[8 * j + 4] - bf16lo_to_f32(h.z), f[8 * j + 5] - bf16hi_to_f32(h.z));
               l.w = pack_bf16x2(f[8 * j + 6] - bf16lo_to_f32(h.w), f[8 * j + 7] - bf16hi_to_f32(h.w));
               const int off = (((half * 4 + j) ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(hrow + off) = h;
-              *reinterpret_cast<uint4*>(lrow + off) = l;
+              sts128(hrow + off, h);
+              sts128(lrow + off, l);
             }
           }
           fence_proxy_async_smem();
@@ -591,12 +592,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         named_bar_sync(1, kEpiThreads);
         if (active) {
           // SWIZZLE_128B staging: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
-          uint8_t* srow = sbuf + row * 128;
+          const uint32_t srow = smem_u32(sbuf) + row * 128;
           if (f32out) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) =
-                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              sts128(srow + ((j ^ (row & 7)) << 4),
+                     make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                __float_as_uint(f[4 * j + 3])));
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -605,7 +607,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = o;
+              sts128(srow + (((half * 4 + j) ^ (row & 7)) << 4), o);
             }
           }
         }
@@ -658,7 +660,10 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+void* vd_tensor_map_encoder() { return reinterpret_cast<void*>(get_encode_fn()); }
+
 struct vd_conv_plan {
+  vd_stem_pool_plan* fused = nullptr;      // VD_CONV_POOL: the plan lives in stem_pool.cu
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmY;
@@ -775,6 +780,27 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   VD_REQUIRE(d && out, "vd_conv_plan_create: null argument");
   const bool x0 = (d->flags & VD_CONV_IN_X0) != 0;
   VD_REQUIRE(d->B > 0 && d->Hout > 0 && d->Wout > 0, "vd_conv_plan_create: empty extent");
+  if (d->flags & VD_CONV_POOL) {
+    VD_REQUIRE(d->x && d->w && d->bias && d->y, "vd_conv_plan_create: null tensor pointer");
+    VD_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->y) & 15) == 0,
+               "vd_conv_plan_create: tensors must be 16-byte aligned");
+    vd_conv_plan* pl = new (std::nothrow) vd_conv_plan();
+    VD_REQUIRE(pl, "out of host memory");
+    pl->desc = *d;
+    memset(&pl->kp, 0, sizeof(pl->kp));
+    pl->kp.flags = d->flags;
+    pl->BN = 64;
+    const int rc = vd_stem_pool_create(d, &pl->fused);
+    if (rc != VD_OK) {
+      delete pl;
+      return rc;
+    }
+    vd_stem_pool_info(pl->fused, &pl->kp.num_tiles, &pl->grid);
+    pl->kp.TW = 120; pl->kp.TH = 1; pl->kp.NB = 1;
+    *out = pl;
+    return VD_OK;
+  }
   VD_REQUIRE(d->Cout % 32 == 0 && d->Cout >= 32, "vd_conv_plan_create: Cout=%d must be a multiple of 32", d->Cout);
   VD_REQUIRE(x0 || (d->Cin % 64 == 0), "vd_conv_plan_create: Cin=%d must be a multiple of 64", d->Cin);
   VD_REQUIRE(d->x && d->w && d->bias && d->y, "vd_conv_plan_create: null tensor pointer");
@@ -1051,6 +1077,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
 }
 
 extern "C" int vd_conv_plan_destroy(vd_conv_plan_t* plan) {
+  if (plan && plan->fused) vd_stem_pool_destroy(plan->fused);
   delete plan;
   return VD_OK;
 }
@@ -1102,6 +1129,7 @@ static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
 extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
   VD_REQUIRE(plan, "vd_conv_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->fused) return vd_stem_pool_run(plan->fused, st);
   const bool res = (plan->kp.flags & VD_CONV_RESIDUAL) != 0;
   if (plan->kp.flags & VD_CONV_IN_X0) return launch_conv<64, false, 64>(plan, st);
   switch (plan->BN) {

@@ -57,6 +57,7 @@ class Op:
     src2: str = ""            # input of the fused 1x1 projection (conv.wkey2), read with conv.stride2
     residual: str = ""        # buffer added before ReLU (bottleneck identity), same shape as dst
     upsample_add: str = ""    # buffer (half resolution) nearest-upsampled and added AFTER ReLU (FPN top-down)
+    pool: bool = False        # conv1 only: the 3x3/2 max-pool runs inside the convolution kernel, dst is the pooled tensor
     level: int = -1           # heads: pyramid level 0..2
 
 
@@ -95,8 +96,10 @@ def level_offsets(h: int, w: int) -> List[int]:
     return offs
 
 
-def build_graph(fuse_downsample: bool = True):
+def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False):
     """Returns (convs, ops, bufs).  Buffer 'x0' is the ingested frame (3 real channels).
+    With fuse_stem_pool conv1+bn1+relu+maxpool (retinaface.py:71-73) is one op writing 'p1' directly; the
+    half-resolution 64-channel tensor 'c1' (4x the size of either neighbour) is never materialised.
     With fuse_downsample the projection shortcut of each stage's first bottleneck (torchvision
     Bottleneck.downsample) is not a separate convolution: its 1x1 GEMM accumulates into conv3's
     accumulator (same output pixels), which removes one write and one read of the widest tensors."""
@@ -118,10 +121,15 @@ def build_graph(fuse_downsample: bool = True):
         ops.append(Op("conv", c, src, dst, dst_coff, src2, residual, upsample_add))
 
     buf("x0", 3, 1)
-    buf("c1", 64, 2)
-    conv("body.conv1", "body.conv1.weight", "body.bn1", 3, 64, 7, 2, 3, True, "x0", "c1")
-    buf("p1", 64, 4)
-    ops.append(Op("maxpool", None, "c1", "p1"))
+    if fuse_stem_pool:
+        buf("p1", 64, 4)
+        conv("body.conv1", "body.conv1.weight", "body.bn1", 3, 64, 7, 2, 3, True, "x0", "p1")
+        ops[-1].pool = True
+    else:
+        buf("c1", 64, 2)
+        conv("body.conv1", "body.conv1.weight", "body.bn1", 3, 64, 7, 2, 3, True, "x0", "c1")
+        buf("p1", 64, 4)
+        ops.append(Op("maxpool", None, "c1", "p1"))
 
     cur, cur_ch, cur_stride = "p1", 64, 4
     layer_cfg = [("layer1", 64, 3, 1), ("layer2", 128, 4, 2), ("layer3", 256, 6, 2), ("layer4", 512, 3, 2)]

@@ -8,6 +8,7 @@ of Retinaface.detect_images (reference detect_face/face.py:120-150) and nn.DataP
 (face.py:56): one process / engine per GPU, no per-forward weight broadcast.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -40,13 +41,18 @@ def _on_device(fn):
 
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
-                 cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16"):
+                 cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16",
+                 fuse_stem_pool=None):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
         # planes for activations and weights, three tensor-core products per term (VD_CONV_SPLIT), ~1/3 of the speed
         self.precision = precision
         self.split = precision == "fp32x"
+        # conv1+bn1+relu+maxpool as one kernel (VD_CONV_POOL); the split-precision mode keeps the two-kernel form
+        if fuse_stem_pool is None:
+            fuse_stem_pool = os.environ.get("VD_STEM_POOL", "1") != "0"
+        self.fuse_stem_pool = bool(fuse_stem_pool) and not self.split
         storage = "fp16" if self.split else precision
         self.act_dtype = _lib.torch_dtype(storage)
         self.lib = _lib.lib(storage)
@@ -71,7 +77,7 @@ class DetectorEngine:
     # ------------------------------------------------------------------------------------------
     def _build(self, state_dict, scratch_frames):
         dev, B, H, W = self.device, self.B, self.H, self.W
-        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split)
+        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool)
         packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
         P = 3 if self.split else 1            # channel planes per activation tensor
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
@@ -109,6 +115,9 @@ class DetectorEngine:
                     d.Cin = 3
                 else:
                     d.Cin = cin
+                if op.pool:                   # Hout/Wout are conv1's own extents; dst holds the pooled tensor
+                    flags |= _lib.VD_CONV_POOL
+                    hout, wout = (hin + 1) // 2, (win + 1) // 2
                 d.Hout, d.Wout, d.Cout = hout, wout, c.cout
                 d.R = d.S = c.k
                 d.stride, d.pad = c.stride, c.pad

@@ -62,7 +62,7 @@ def ingest_nchw_f32(frames, H, W):
 
 
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False):
+           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
     The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
@@ -81,7 +81,10 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     wout = (win + 2 * pad - k) // stride + 1
     if out is None:
         oc = cout if (out_f32 or not split) else 3 * cout      # split tensors carry [hi | lo | hi] planes
-        out = torch.empty((B, hout, wout, oc), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+        oh, ow = ((hout + 1) // 2, (wout + 1) // 2) if pool else (hout, wout)   # pool: conv1 + maxpool 3x3/2 fused
+        out = torch.empty((B, oh, ow, oc), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    if pool:
+        flags |= _lib.VD_CONV_POOL
     if split:
         flags |= _lib.VD_CONV_SPLIT
     d.B, d.Hin, d.Win, d.Cin = B, hin, win, cin
