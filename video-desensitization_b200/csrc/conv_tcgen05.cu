@@ -227,7 +227,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             aslot = 0;
             aphase ^= 1u;
           }
-          for (int tap = 0; tap < 9; tap += KPS) {
+          for (int tap = 0; tap < 9 && !p.wres; tap += KPS) {
             mbar_wait(&empty[stage], phase ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(&full[stage], static_cast<uint32_t>(KPS * Cfg::B_BYTES));
@@ -324,7 +324,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           mbar_wait(&afull[aslot], aphase);
           const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(aslot * (p.a_slot_bytes >> 4));
-          for (int tap0 = 0; tap0 < 9; tap0 += KPS) {
+          if (p.wres) {
+            // resident weights: the nine taps of this 64-channel slice issue back to back
+            tcgen05_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int r = tap / 3, sx = tap - 3 * r;
+                const uint32_t al = a_lo + static_cast<uint32_t>((r * p.PW + sx) * 8);
+                const uint32_t bl = b_lo0 + static_cast<uint32_t>((tap * p.cin_blocks + cb) * (Cfg::B_BYTES >> 4));
+                umma_bf16_words(d_tmem, al, hi_patch, bl, hi_std, idesc, static_cast<uint32_t>((cb | tap) != 0));
+                umma_bf16_words(d_tmem, al + 2, hi_patch, bl + 2, hi_std, idesc, 1u);
+                umma_bf16_words(d_tmem, al + 4, hi_patch, bl + 4, hi_std, idesc, 1u);
+                umma_bf16_words(d_tmem, al + 6, hi_patch, bl + 6, hi_std, idesc, 1u);
+              }
+              umma_commit(&aempty[aslot]);
+              if (cb == p.cin_blocks - 1) umma_commit(&tfull[acc]);
+            }
+            __syncwarp();
+          }
+          for (int tap0 = 0; tap0 < 9 && !p.wres; tap0 += KPS) {
             mbar_wait(&full[stage], phase);
             tcgen05_fence_after();
             if (elect_one()) {
@@ -690,9 +709,29 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   const char* env = getenv("VD_CONV_KPS");
   const int force_kps = env ? atoi(env) : 0;
   if (k.patch) {
+    k.a_slot_bytes = (k.PW * k.PH * 128 + 1023) & ~1023;
+    {
+      // narrow 3x3 layers whose whole filter bank fits (64 -> 64: 72 KB) keep it resident: streaming it costs
+      // 72 KB of L2 reads per 128-pixel tile, three times the patch itself
+      const char* we = getenv("VD_CONV_PATCH_WRES");
+      const int want = we ? atoi(we) : 1;
+      const int wb = KB * Cfg::B_BYTES;
+      if (want && occ == 1 && k.n_tiles == 1 && wb <= kWresMaxBytes && k.num_tiles > pl->grid) {
+        int slots = (avail - wb) / k.a_slot_bytes;
+        if (slots > 4) slots = 4;
+        if (slots >= 2) {
+          k.wres = 1;
+          k.w_bytes = wb;
+          k.a_slots = slots;
+          k.kps = 1;
+          k.stages = 1;
+          pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + wb;
+          return true;
+        }
+      }
+    }
     k.wres = 0;
     k.w_bytes = 0;
-    k.a_slot_bytes = (k.PW * k.PH * 128 + 1023) & ~1023;
     k.a_slots = 2;
     k.kps = (BN <= 128) ? 3 : 1;                         // taps per stage (must divide 9)
     if (force_kps == 1 || force_kps == 3) k.kps = force_kps;
@@ -748,6 +787,10 @@ static bool plan_occ(vd_conv_plan* pl, int sms) {
   constexpr bool kTwo = (BN <= 128 && !RES);
   const char* env = getenv("VD_CONV_OCC");
   const int want = env ? atoi(env) : 2;
+  if (pl->kp.patch) {                       // narrow 3x3: one CTA per SM with the filter bank resident, if it fits
+    pl->grid = pl->kp.num_tiles < sms ? pl->kp.num_tiles : sms;
+    if (plan_smem<BN, RES, ROWB>(pl, 1, 2) && pl->kp.wres) return true;
+  }
   if (kTwo && want >= 2 && pl->kp.num_tiles > sms) {
     pl->grid = pl->kp.num_tiles < 2 * sms ? pl->kp.num_tiles : 2 * sms;
     if (plan_smem<BN, RES, ROWB>(pl, 2, 3)) return true;
