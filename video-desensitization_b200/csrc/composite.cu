@@ -441,9 +441,22 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       // whole box in shared memory: u8 source [bh][bw*3], u16 horizontal result [bh][bw*3]
       uint8_t* src = dsm;
       uint16_t* mid = reinterpret_cast<uint16_t*>(dsm + ((bh * row3 + 15) & ~15));
-      for (int i = tid; i < bh * row3; i += kThreads) {
-        const int y = i / row3, e = i - y * row3;
-        src[i] = __ldcg(img + static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e);
+      // loads are issued in batches of 8 per thread before any of them is consumed: the item is latency-bound
+      for (int base = 0; base < bh * row3; base += 8 * kThreads) {
+        uint8_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * kThreads + tid;
+          if (i < bh * row3) {
+            const int y = i / row3, e = i - y * row3;
+            v[u] = __ldcg(img + static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * kThreads + tid;
+          if (i < bh * row3) src[i] = v[u];
+        }
       }
       __syncthreads();
       for (int i = tid; i < bh * row3; i += kThreads) {
@@ -482,18 +495,31 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         const int spanw = (span + 3 + 4 * KW_MAX) / 4;       // words per row incl. slack read by the last window
         uint32_t* planes = reinterpret_cast<uint32_t*>(dsm); // [3][GA_H][spanw]
         uint8_t* pb = dsm;
-        for (int ly = 0; ly < rows; ++ly) {
-          const uint8_t* rowp = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + m.x1 * 3;
-          uint8_t* d0 = pb + (0 * GA_H + ly) * spanw * 4;
-          uint8_t* d1 = pb + (1 * GA_H + ly) * spanw * 4;
-          uint8_t* d2 = pb + (2 * GA_H + ly) * spanw * 4;
-          for (int c = tid; c < span; c += kThreads) {
-            int xs = x0 - r + c;
-            if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
-            const uint8_t* p = rowp + xs * 3;
-            d0[c] = __ldcg(p);
-            d1[c] = __ldcg(p + 1);
-            d2[c] = __ldcg(p + 2);
+        const int total = rows * span;
+        for (int base = 0; base < total; base += 6 * kThreads) {       // 6 x 3 loads in flight per thread
+          uint8_t v[6][3];
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int i = base + u * kThreads + tid;
+            if (i < total) {
+              const int ly = i / span, c = i - ly * span;
+              int xs = x0 - r + c;
+              if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
+              const uint8_t* p = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + (m.x1 + xs) * 3;
+              v[u][0] = __ldcg(p);
+              v[u][1] = __ldcg(p + 1);
+              v[u][2] = __ldcg(p + 2);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int i = base + u * kThreads + tid;
+            if (i < total) {
+              const int ly = i / span, c = i - ly * span;
+              pb[(0 * GA_H + ly) * spanw * 4 + c] = v[u][0];
+              pb[(1 * GA_H + ly) * spanw * 4 + c] = v[u][1];
+              pb[(2 * GA_H + ly) * spanw * 4 + c] = v[u][2];
+            }
           }
         }
         __syncthreads();
@@ -551,12 +577,26 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           if (e < ne) {
             uint8_t* hcol = hi + e * colw * 4;
             uint8_t* lcol = lo + e * colw * 4;
-            for (int ly = tid / GB_E; ly < span; ly += kThreads / GB_E) {
-              int ys = y0 - r + ly;
-              if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
-              const uint16_t v = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
-              hcol[ly] = static_cast<uint8_t>(v >> 8);
-              lcol[ly] = static_cast<uint8_t>(v & 0xFF);
+            constexpr int LSTEP = kThreads / GB_E;
+            for (int l0 = tid / GB_E; l0 < span; l0 += 8 * LSTEP) {     // 8 loads in flight per thread
+              uint16_t v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int ly = l0 + u * LSTEP;
+                if (ly < span) {
+                  int ys = y0 - r + ly;
+                  if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+                  v[u] = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int ly = l0 + u * LSTEP;
+                if (ly < span) {
+                  hcol[ly] = static_cast<uint8_t>(v[u] >> 8);
+                  lcol[ly] = static_cast<uint8_t>(v[u] & 0xFF);
+                }
+              }
             }
           }
         }
