@@ -300,6 +300,40 @@ __device__ __forceinline__ void dp4a_run(const uint32_t* __restrict__ S, const u
   }
 }
 
+// Both passes of a fused (whole box in shared memory) Gaussian item with the taps in registers: KT >= ksize taps,
+// the ones beyond ksize are zero and read table entry 0.  out = (sum_j q[j] * (sum_i q[i] * src[refl]) + 32768) >> 16.
+template <int KT>
+__device__ __forceinline__ void fused_passes(const uint8_t* __restrict__ src, uint16_t* __restrict__ mid,
+                                             const uint16_t* __restrict__ xtab, const uint16_t* __restrict__ ytab,
+                                             const uint16_t* __restrict__ s_q, int bw, int bh, uint8_t* img, int pitch,
+                                             int x1, int y1) {
+  const int tid = threadIdx.x;
+  const int row3 = bw * 3, n = bh * row3;
+  uint32_t q[KT];
+#pragma unroll
+  for (int t = 0; t < KT; ++t) q[t] = s_q[t];
+  for (int i = tid; i < n; i += kThreads) {
+    const int y = i / row3, e = i - y * row3;
+    const int x = e / 3, c = e - x * 3;
+    const uint8_t* srow = src + y * row3 + c;
+    const uint16_t* tb = xtab + x;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) acc += q[t] * srow[tb[t]];
+    mid[i] = static_cast<uint16_t>(min(acc, 65535u));
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kThreads) {
+    const int y = i / row3, e = i - y * row3;
+    const uint16_t* tb = ytab + y;
+    const uint16_t* col = mid + e;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) acc += q[t] * col[tb[t] * row3];
+    img[static_cast<size_t>(y1 + y) * pitch + x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 3)
 composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int mode, int ksize, Taps taps,
                      uint32_t* __restrict__ status, Ws ws) {
@@ -438,16 +472,20 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         }
       }
     } else if (m.fused) {
-      // whole box in shared memory: u8 source [bh][bw*3], u16 horizontal result [bh][bw*3]
+      // whole box in shared memory: u8 source [bh][bw*3], u16 horizontal result [bh][bw*3], and the
+      // REFLECT_101 index tables of both axes (a small box is all border: bw, bh < ksize is the common case)
+      const int n = bh * row3;
       uint8_t* src = dsm;
-      uint16_t* mid = reinterpret_cast<uint16_t*>(dsm + ((bh * row3 + 15) & ~15));
+      uint16_t* mid = reinterpret_cast<uint16_t*>(dsm + ((n + 15) & ~15));
+      uint16_t* xtab = mid + ((n + 7) & ~7);                 // [bw + 2r + 32]: 3 * reflect(i - r), then zeros
+      uint16_t* ytab = xtab + ((bw + 2 * r + 32 + 7) & ~7);  // [bh + 2r + 32]:     reflect(i - r), then zeros
       // loads are issued in batches of 8 per thread before any of them is consumed: the item is latency-bound
-      for (int base = 0; base < bh * row3; base += 8 * kThreads) {
+      for (int base = 0; base < n; base += 8 * kThreads) {
         uint8_t v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = base + u * kThreads + tid;
-          if (i < bh * row3) {
+          if (i < n) {
             const int y = i / row3, e = i - y * row3;
             v[u] = __ldcg(img + static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e);
           }
@@ -455,34 +493,35 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = base + u * kThreads + tid;
-          if (i < bh * row3) src[i] = v[u];
+          if (i < n) src[i] = v[u];
         }
       }
+      for (int i = tid; i < bw + 2 * r + 32; i += kThreads)
+        xtab[i] = static_cast<uint16_t>(i < bw + 2 * r ? reflect101(i - r, bw) * 3 : 0);
+      for (int i = tid; i < bh + 2 * r + 32; i += kThreads)
+        ytab[i] = static_cast<uint16_t>(i < bh + 2 * r ? reflect101(i - r, bh) : 0);
       __syncthreads();
-      for (int i = tid; i < bh * row3; i += kThreads) {
-        const int y = i / row3, e = i - y * row3;
-        const int x = e / 3, c = e - x * 3;
-        const uint8_t* srow = src + y * row3 + c;
-        uint32_t acc = 0;
-        if (x >= r && x + r < bw) {
-          const uint8_t* s = srow + (x - r) * 3;
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * 3];
-        } else {
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * srow[reflect101(x - r + tt, bw) * 3];
+      if (ksize <= 8) fused_passes<8>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
+      else if (ksize <= 16) fused_passes<16>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
+      else if (ksize <= 32) fused_passes<32>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
+      else {
+        for (int i = tid; i < n; i += kThreads) {
+          const int y = i / row3, e = i - y * row3;
+          const int x = e / 3, c = e - x * 3;
+          const uint8_t* srow = src + y * row3 + c;
+          const uint16_t* tb = xtab + x;
+          uint32_t acc = 0;
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * srow[tb[tt]];
+          mid[i] = static_cast<uint16_t>(min(acc, 65535u));
         }
-        mid[i] = static_cast<uint16_t>(min(acc, 65535u));
-      }
-      __syncthreads();
-      for (int i = tid; i < bh * row3; i += kThreads) {
-        const int y = i / row3, e = i - y * row3;
-        uint32_t acc = 0;
-        if (y >= r && y + r < bh) {
-          const uint16_t* s = mid + (y - r) * row3 + e;
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * row3];
-        } else {
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * mid[reflect101(y - r + tt, bh) * row3 + e];
+        __syncthreads();
+        for (int i = tid; i < n; i += kThreads) {
+          const int y = i / row3, e = i - y * row3;
+          const uint16_t* tb = ytab + y;
+          uint32_t acc = 0;
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * mid[tb[tt] * row3 + e];
+          img[static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
         }
-        img[static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
       }
     } else if (phaseA) {
       // ---------------- horizontal pass: GA_H rows x GA_W pixels ----------------
@@ -738,7 +777,8 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
       a = static_cast<size_t>(3) * GA_H * ((GA_W + 2 * r + 3 + 4 * KW_MAX) / 4) * 4;
       b = static_cast<size_t>(2) * GB_E * ((((GB_H + 2 * r + 3 + 4 * KW_MAX) / 4) | 1)) * 4;
     }
-    const size_t fz = static_cast<size_t>(FUSE_MAX_PX) * 9 + 64;
+    // fused item: u8 source + u16 intermediate + the two reflect tables (bw + bh <= FUSE_MAX_PX + 1)
+    const size_t fz = static_cast<size_t>(FUSE_MAX_PX) * 9 + 64 + 2 * (static_cast<size_t>(FUSE_MAX_PX) + 1 + 4 * r + 64 + 16);
     smem = a > b ? a : b;
     if (fz > smem) smem = fz;
   }
