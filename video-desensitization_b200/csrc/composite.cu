@@ -438,7 +438,8 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       for (int i = tid; i < n; i += kThreads)
         spin_flag(done + m.item_base + (ay0 + i / nax) * atx + ax0 + i % nax, status);
     }
-    __threadfence();
+    // flag acquire (per thread) -> bar.sync -> ld.global.cg by every thread of the CTA: the barrier extends the
+    // acquiring thread's view to the whole CTA, no fence (and no L1 invalidation) needed
     __syncthreads();
 
     const vd_frame_t fr = frames[f];
@@ -672,7 +673,8 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         }
       }
     }
-    __threadfence();
+    // every thread's stores -> bar.sync -> st.release.gpu by one thread (release is cumulative over what the
+    // barrier ordered before it): no fence needed
     __syncthreads();
     if (tid == 0) st_release(done + local, 1);
   }
