@@ -33,10 +33,11 @@ H, W, BATCH = 1080, 1920, 16
 KSIZE = 31
 N_PLATES = 4
 CONV_GFLOP_PER_FRAME = 449.71          # 82 convs at 1080p, 2*MAC
-# average dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 16-frame step, from the ncu capture
-# summarised in profiles/r01_ncu_summary.md §2 (33.96 GB over the 73 captured launches); algorithmic activation traffic
-# is 2.085 GB/frame * 16 = 33.4 GB per step, i.e. no wasted re-reads
-CONV_DRAM_BYTES_PER_LAUNCH = 4.65e8
+# average dram__bytes_read.sum + dram__bytes_write.sum per convolution launch of one 16-frame step, from the ncu capture
+# summarised in profiles/r01_ncu_summary.md §2 (31.64 GB over the 72 launches of a step); algorithmic activation
+# traffic is 2.085 GB/frame unfused minus the 0.133 GB/frame of conv1's output that the fused
+# conv1+maxpool kernel keeps on chip = 1.95 GB/frame * 16 = 31.2 GB per step, i.e. no wasted re-reads
+CONV_DRAM_BYTES_PER_LAUNCH = 4.395e8
 METRIC = "1080p detect+blur frames/sec"
 
 
@@ -293,7 +294,7 @@ def run_ours(args):
                 "steps": e2e_steps, "host_ms_per_batch": e2e_host, "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step (double-buffered), max over ranks"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3; + maxpool)" % (len(eng.plans) - 1),
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + stem_pool_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3, maxpool fused into conv1)" % n_conv,
                      "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
                      "peak_source": peak_src + " bf16_tflops_sustained",
                      "traffic": CONV_DRAM_BYTES_PER_LAUNCH if precision == "bf16" else None,
