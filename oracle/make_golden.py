@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — generates the committed fixtures by EXECUTING THE UNMODIFIED REFERENCE
 (imported read-only from /root/reference through oracle/ref_shims.py) in the build container.
 
-    python oracle/make_golden.py            # writes  video-desensitization_b200/vdesens_b200/data/bn_calib_seed0.npz
-                                            #         tests/golden/{ref_detect,nms,cv}_golden.npz
+    python oracle/make_golden.py            # writes  video-desensitization_b200/vdesens_b200/data/bn_calib{,_mnet}_seed0.npz
+                                            #         tests/golden/{ref_detect,ref_detect_mnet,nms,cv}_golden.npz
+    python oracle/make_golden.py --mnet-only   # only the MobileNet0.25 files
 
 The GPU box has no /root/reference; tests there read only the committed .npz files.
 """
@@ -87,6 +88,63 @@ def make_ref_detect(ref_face):
     np.savez_compressed(os.path.join(GOLD, "ref_detect_golden.npz"), **out)
 
 
+def make_bn_calib_mnet():
+    """same recipe for the cfg_mnet network."""
+    from vdesens_b200 import arch_mnet as am
+    sd = ro.to_torch_sd(synth._raw_state_dict(0, "mobilenet"))
+    frames = synth.synthetic_clip(4, 480, 640, base_seed=7000)
+    x, _ = ro.preprocess(frames, (480, 640))
+    ro.forward_mnet(sd, x, calibrate=True)
+    out = {k: v.numpy() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    ds = [[], [], []]
+    offs = am.level_offsets(1080, 1920) + [am.num_anchors(1080, 1920)]
+    for i in range(8):
+        xf, _ = ro.preprocess([synth.synthetic_frame(1080, 1920, 7100 + i)], (1080, 1920))
+        _, cls, _ = ro.forward_mnet(sd, xf, softmax=False)
+        d = (cls[..., 1] - cls[..., 0])[0]
+        for l in range(3):
+            ds[l].append(d[offs[l]:offs[l + 1]])
+    for name, rate in RATES.items():
+        sh = [-float(np.quantile(torch.cat(ds[l]).numpy().astype(np.float64), 1 - rate)) for l in range(3)]
+        out["shift." + name] = np.array(sh, np.float32)
+    np.savez_compressed(synth.BN_CALIB_FILE_MNET, **out)
+    print("wrote", synth.BN_CALIB_FILE_MNET, os.path.getsize(synth.BN_CALIB_FILE_MNET), "bytes")
+
+
+def make_ref_detect_mnet(ref_face):
+    """the unmodified reference with backbone='mobilenet' (face.py:35) on the synthetic cfg_mnet weights"""
+    sd = synth.synthetic_state_dict(0, face_rate="r01", backbone="mobilenet")
+    tmp = tempfile.mkdtemp()
+    pth = os.path.join(tmp, "w_mnet.pth")
+    synth.save_state_dict_pth(sd, pth)
+    cases = {
+        "native": dict(frames=[(96, 128, 9000), (96, 128, 9001)], input_shape=[96, 128, 3]),
+        "letterbox": dict(frames=[(150, 200, 9100), (260, 180, 9101)], input_shape=[128, 128, 3]),
+        "odd": dict(frames=[(135, 241, 9200)], input_shape=[135, 241, 3]),
+        "vga": dict(frames=[(480, 640, 1000)], input_shape=[480, 640, 3]),
+    }
+    out = {}
+    for name, cs in cases.items():
+        frames = [synth.synthetic_frame(h, w, s) for h, w, s in cs["frames"]]
+        det = ref_face.Retinaface(model_path=pth, backbone="mobilenet", input_shape=cs["input_shape"],
+                                  confidence=0.5, nms_iou=0.4, letterbox_image=True, cuda=False)
+        x, shapes = det.preprocess(frames)
+        with torch.no_grad():
+            loc, conf, landms = det.net(x)
+            rows = det.postprocess(loc, conf, landms, shapes, len(frames))
+        res = det.detect_images(frames)
+        out[name + ".frames"] = np.array(cs["frames"], np.int64)
+        out[name + ".input_shape"] = np.array(cs["input_shape"], np.int64)
+        out[name + ".loc"] = loc.numpy()
+        out[name + ".conf"] = conf.numpy()
+        out[name + ".landms"] = landms.numpy()
+        for i, (r, (img, boxes)) in enumerate(zip(rows, res)):
+            out[f"{name}.rows{i}"] = r.numpy().astype(np.float32).reshape(-1, 15)
+            out[f"{name}.boxes{i}"] = np.array(boxes, np.float64).reshape(-1, 4)
+        print("mnet", name, "kept per frame:", [len(r) for r in rows])
+    np.savez_compressed(os.path.join(GOLD, "ref_detect_mnet_golden.npz"), **out)
+
+
 def make_nms():
     from torchvision.ops import nms
     rng = np.random.default_rng(4242)
@@ -145,8 +203,14 @@ if __name__ == "__main__":
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLD, exist_ok=True)
     ref_face, ref_combine = load_reference()
+    if "--mnet-only" in sys.argv:
+        make_bn_calib_mnet()
+        make_ref_detect_mnet(ref_face)
+        sys.exit(0)
     make_bn_calib()
     make_ref_detect(ref_face)
+    make_bn_calib_mnet()
+    make_ref_detect_mnet(ref_face)
     make_nms()
     make_cv(ref_face, ref_combine)
     for f in sorted(os.listdir(GOLD)):

@@ -115,6 +115,121 @@ def forward(sd, x, calibrate=False, capture=None, softmax=True):
 
 
 # ----------------------------------------------------------------------------------------------
+# MobileNet0.25 variant: detect_face/nets/mobilenet025.py:3-49 (conv_bn / conv_dw, LeakyReLU 0.1),
+# FPN / SSH with leaky = 0.1 because out_channel = 64 <= 64 (layers.py:41,71), heads on 64 channels
+# ----------------------------------------------------------------------------------------------
+_MNET_BLOCKS = (("stage1", 1, 1), ("stage1", 2, 2), ("stage1", 3, 1), ("stage1", 4, 2), ("stage1", 5, 1),
+                ("stage2", 0, 2), ("stage2", 1, 1), ("stage2", 2, 1), ("stage2", 3, 1), ("stage2", 4, 1), ("stage2", 5, 1),
+                ("stage3", 0, 2), ("stage3", 1, 1))
+
+
+def forward_mnet(sd, x, calibrate=False, capture=None, softmax=True):
+    """x: (B,3,H,W) fp32 mean-subtracted.  Returns (loc (B,A,4), conf (B,A,2), landms (B,A,10))."""
+    cap = capture if capture is not None else {}
+
+    def cba(x, wkey, bnkey, stride, pad, slope, groups=1):
+        y = F.conv2d(x, sd[wkey], None, stride, pad, 1, groups)
+        if calibrate:
+            yd = y.double()
+            sd[bnkey + ".running_mean"] = yd.mean(dim=(0, 2, 3)).float()
+            sd[bnkey + ".running_var"] = yd.var(dim=(0, 2, 3), unbiased=False).float().clamp_min(1e-6)
+        y = F.batch_norm(y, sd[bnkey + ".running_mean"], sd[bnkey + ".running_var"], sd[bnkey + ".weight"],
+                         sd[bnkey + ".bias"], False, 0.0, BN_EPS)
+        return y if slope is None else F.leaky_relu(y, slope)
+
+    with torch.no_grad():
+        y = cba(x, "body.stage1.0.0.weight", "body.stage1.0.1", 2, 1, 0.1)                 # mobilenet025.py:3-8
+        cap["m.stem"] = y
+        feats = {}
+        for st, i, stride in _MNET_BLOCKS:                                                 # conv_dw, :10-19
+            p = f"body.{st}.{i}"
+            y = cba(y, p + ".0.weight", p + ".1", stride, 1, 0.1, groups=y.shape[1])
+            cap[p + ".dw"] = y
+            y = cba(y, p + ".3.weight", p + ".4", 1, 0, 0.1)
+            cap[p + ".pw"] = y
+            feats[st] = y
+        o1 = cba(feats["stage1"], "fpn.output1.0.weight", "fpn.output1.1", 1, 0, 0.1)     # layers.py:94-96
+        o2 = cba(feats["stage2"], "fpn.output2.0.weight", "fpn.output2.1", 1, 0, 0.1)
+        o3 = cba(feats["stage3"], "fpn.output3.0.weight", "fpn.output3.1", 1, 0, 0.1)
+        o2 = o2 + F.interpolate(o3, size=[o2.size(2), o2.size(3)], mode="nearest")
+        o2 = cba(o2, "fpn.merge2.0.weight", "fpn.merge2.1", 1, 1, 0.1)
+        o1 = o1 + F.interpolate(o2, size=[o1.size(2), o1.size(3)], mode="nearest")
+        o1 = cba(o1, "fpn.merge1.0.weight", "fpn.merge1.1", 1, 1, 0.1)
+        cap["fpn.o1"], cap["fpn.o2"], cap["fpn.o3"] = o1, o2, o3
+        fs = []
+        for lvl, o in enumerate((o1, o2, o3)):                                             # layers.py:54-66
+            p = f"ssh{lvl + 1}"
+            a = cba(o, p + ".conv3X3.0.weight", p + ".conv3X3.1", 1, 1, None)
+            t = cba(o, p + ".conv5X5_1.0.weight", p + ".conv5X5_1.1", 1, 1, 0.1)
+            b = cba(t, p + ".conv5X5_2.0.weight", p + ".conv5X5_2.1", 1, 1, None)
+            u = cba(t, p + ".conv7X7_2.0.weight", p + ".conv7X7_2.1", 1, 1, 0.1)
+            d = cba(u, p + ".conv7x7_3.0.weight", p + ".conv7x7_3.1", 1, 1, None)
+            fs.append(F.relu(torch.cat([a, b, d], dim=1)))
+            cap[p + ".out"] = fs[-1]
+
+        def head(prefix, n):
+            outs = []
+            for i, f in enumerate(fs):
+                o = F.conv2d(f, sd[f"{prefix}.{i}.conv1x1.weight"], sd[f"{prefix}.{i}.conv1x1.bias"])
+                outs.append(o.permute(0, 2, 3, 1).contiguous().view(o.shape[0], -1, n))
+            return torch.cat(outs, dim=1)
+
+        loc, cls, ldm = head("BboxHead", 4), head("ClassHead", 2), head("LandmarkHead", 10)
+        if softmax:
+            cls = F.softmax(cls, dim=-1)
+    return loc, cls, ldm
+
+
+def forward_mnet_emulated(packed, x, capture=None, dtype=torch.bfloat16):
+    """The device op list of vdesens_b200.arch_mnet executed on the CPU with the SAME packed weights and the same
+    rounding points (activations rounded to `dtype` where the device stores them, fp32 math in between)."""
+    from vdesens_b200 import arch_mnet as am
+    ops, _ = am.build_graph()
+    bufs = {"x0": x}
+    heads = [None, None, None]
+
+    def bf(t):
+        return t.to(dtype).float()
+
+    def act(y, slope):
+        return torch.where(y > 0, y, y * slope.view(1, -1, 1, 1))
+
+    with torch.no_grad():
+        for op in ops:
+            w, b, slope = packed[op.name]
+            w = w.float()
+            xin = bufs[op.src]
+            if op.kind == "stem":
+                wt = w.view(3, 3, 4, 8)[:, :, :3, :].permute(3, 2, 0, 1).contiguous()
+                y = act(F.conv2d(xin, wt, b, 2, 1), slope)
+            elif op.kind == "dw":
+                wt = w.view(3, 3, op.cin).permute(2, 0, 1).unsqueeze(1).contiguous()
+                y = act(F.conv2d(xin, wt, b, op.stride, 1, 1, op.cin), slope)
+            elif op.kind == "pw":
+                y = act(F.conv2d(xin, w.t().contiguous().view(op.cout, op.cin, 1, 1), b), slope)
+            elif op.kind == "conv":
+                wt = w.view(op.cout, op.k, op.k, op.cin).permute(0, 3, 1, 2).contiguous()
+                y = act(F.conv2d(xin, wt, b, op.stride, op.pad), slope)
+                if op.upsample_add:
+                    y = y + F.interpolate(bufs[op.upsample_add], size=y.shape[2:], mode="nearest")
+            elif op.kind == "heads":
+                xx = torch.cat([xin, bufs[op.src2]], dim=1)
+                heads[op.level] = F.conv2d(xx, w.view(32, 128, 1, 1), b)
+                continue
+            bufs[op.dst] = bf(y)
+        if capture is not None:
+            capture.update(bufs)
+        locs, clss, ldms = [], [], []
+        for h in heads:
+            hh = h.permute(0, 2, 3, 1).contiguous()
+            B = hh.shape[0]
+            locs.append(hh[..., 0:8].reshape(B, -1, 4))
+            clss.append(hh[..., 8:12].reshape(B, -1, 2))
+            ldms.append(hh[..., 12:32].reshape(B, -1, 10))
+    return torch.cat(locs, 1), torch.cat(clss, 1), torch.cat(ldms, 1)
+
+
+# ----------------------------------------------------------------------------------------------
 # anchors: detect_face/utils/anchors.py:7-41  (python doubles, rounded once to fp32 by torch.Tensor)
 # ----------------------------------------------------------------------------------------------
 def anchors(h, w):

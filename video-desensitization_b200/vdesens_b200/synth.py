@@ -15,6 +15,7 @@ from . import arch
 
 _DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 BN_CALIB_FILE = os.path.join(_DATA_DIR, "bn_calib_seed0.npz")
+BN_CALIB_FILE_MNET = os.path.join(_DATA_DIR, "bn_calib_mnet_seed0.npz")
 
 
 def synthetic_frame(h: int, w: int, seed: int) -> np.ndarray:
@@ -53,20 +54,31 @@ def synthetic_boxes(n: int, h: int, w: int, seed: int, min_size: int = 32, max_s
     return [(int(a), int(b), int(a + c), int(b + d)) for a, b, c, d in zip(x1, y1, bw, bh)]
 
 
-def _raw_state_dict(seed: int):
+def _raw_state_dict(seed: int, backbone: str = "resnet50"):
     """numpy state dict with identity BN statistics."""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed + (0 if backbone == "resnet50" else 7919))
     sd = {}
-    for key, shape, kind in arch.state_dict_spec():
+    if backbone == "resnet50":
+        spec = arch.state_dict_spec()
+    else:
+        from . import arch_mnet
+        spec = arch_mnet.state_dict_spec()
+    for key, shape, kind in spec:
         if kind == "conv_backbone":      # kaiming-normal, fan_out (torchvision resnet init)
             fan_out = shape[0] * shape[2] * shape[3]
             sd[key] = rng.normal(0.0, np.sqrt(2.0 / fan_out), size=shape).astype(np.float32)
+        elif kind == "conv_dw":
+            # depthwise 3x3: positive taps (a local weighted mean).  Thirteen random-SIGN depthwise filters in a row
+            # on smooth images are thirteen near-cancelling sums, each re-normalised by its BN: an untrained net
+            # built that way amplifies fp16 rounding to 5 % and bf16 rounding to 27 % of the head outputs, which no
+            # reduced-precision execution can track (same reasoning as bn3 below)
+            sd[key] = rng.uniform(0.0, 0.25, size=shape).astype(np.float32)
         elif kind in ("conv_neck", "head_weight"):   # torch Conv2d default: U(+-1/sqrt(fan_in))
             fan_in = shape[1] * shape[2] * shape[3]
             b = 1.0 / np.sqrt(fan_in)
             sd[key] = rng.uniform(-b, b, size=shape).astype(np.float32)
         elif kind == "head_bias":
-            b = 1.0 / np.sqrt(256.0)
+            b = 1.0 / np.sqrt(256.0 if backbone == "resnet50" else 64.0)
             sd[key] = rng.uniform(-b, b, size=shape).astype(np.float32)
         elif kind == "bn_weight":        # non-trivial gamma/beta so BN folding is really exercised
             if key.endswith(".bn3.weight"):
@@ -89,17 +101,19 @@ def _raw_state_dict(seed: int):
     return sd
 
 
-def synthetic_state_dict(seed: int = 0, calibrated: bool = True, face_rate: str = "r01"):
+def synthetic_state_dict(seed: int = 0, calibrated: bool = True, face_rate: str = "r01", backbone: str = "resnet50"):
     """Returns {key: np.ndarray}.  `calibrated` loads the committed BN statistics for seed 0;
     `face_rate` picks the class-bias shift stored with them ("r01" ~ 1 % of anchors >= 0.5,
-    "r001" ~ 0.1 %, "dense" for the dense-ROI stress case, "" for no shift)."""
-    sd = _raw_state_dict(seed)
+    "r001" ~ 0.1 %, "dense" for the dense-ROI stress case, "" for no shift).
+    backbone "mobilenet" gives the cfg_mnet network (reference detect_face/utils/config.py:1-16)."""
+    sd = _raw_state_dict(seed, backbone)
     if calibrated:
         if seed != 0:
             raise ValueError("calibration statistics are committed for seed 0 only")
-        if not os.path.isfile(BN_CALIB_FILE):
-            raise FileNotFoundError(BN_CALIB_FILE + " (run oracle/make_golden.py in the build container)")
-        cal = np.load(BN_CALIB_FILE)
+        calib_file = BN_CALIB_FILE if backbone == "resnet50" else BN_CALIB_FILE_MNET
+        if not os.path.isfile(calib_file):
+            raise FileNotFoundError(calib_file + " (run oracle/make_golden.py in the build container)")
+        cal = np.load(calib_file)
         for key in cal.files:
             if key.startswith("shift."):
                 continue

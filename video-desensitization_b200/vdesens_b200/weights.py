@@ -93,3 +93,88 @@ def pack_all(sd, dtype=torch.bfloat16, split=False):
         else:
             packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(dtype), torch.from_numpy(np.concatenate(bs)))
     return packed
+
+
+# ------------------------------------------------------------------------------------------------
+# MobileNet0.25 variant (arch_mnet.py)
+# ------------------------------------------------------------------------------------------------
+def _fold_keys(sd, wkey, bnkey):
+    w = np.asarray(sd[wkey], np.float64)
+    g = np.asarray(sd[bnkey + ".weight"], np.float64)
+    beta = np.asarray(sd[bnkey + ".bias"], np.float64)
+    mean = np.asarray(sd[bnkey + ".running_mean"], np.float64)
+    var = np.asarray(sd[bnkey + ".running_var"], np.float64)
+    scale = g / np.sqrt(var + arch.BN_EPS)
+    return (w * scale[:, None, None, None]).astype(np.float32), (beta - mean * scale).astype(np.float32)
+
+
+def pack_mnet(sd, dtype=torch.bfloat16):
+    """{op name: (w, bias fp32, slope fp32)} for every op of arch_mnet.build_graph().  Layouts:
+    stem  w [(r,s,c4)=36][8]         dw  w [9][C]         pw  w [Cin][Cout]
+    conv  w [Cout][(r,s,cin)] (K-major GEMM operand of conv_tcgen05.cu)      heads  w [32][128] over [S1 | S3].
+    slope = negative-side factor per output channel: 0 ReLU, 0.1 LeakyReLU(0.1), 1 identity."""
+    from . import arch_mnet as am
+    sd = to_numpy_sd(sd)
+    L = am.LEAKY
+    packed = {}
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+    def put(name, w, b, slope):
+        packed[name] = (t(w).to(dtype), t(b), t(np.broadcast_to(np.asarray(slope, np.float32), b.shape)))
+
+    w, b = _fold_keys(sd, "body.stage1.0.0.weight", "body.stage1.0.1")          # (8,3,3,3)
+    ws = np.zeros((3, 3, 4, 8), np.float32)
+    ws[:, :, :3, :] = np.transpose(w, (2, 3, 1, 0))
+    put("body.stage1.0", ws.reshape(36, 8), b, L)
+    for st, i, cin, cout, _ in am.DW_BLOCKS:
+        p = f"body.{st}.{i}"
+        w, b = _fold_keys(sd, p + ".0.weight", p + ".1")                        # (cin,1,3,3)
+        put(p + ".dw", np.transpose(w[:, 0], (1, 2, 0)).reshape(9, cin), b, L)
+        w, b = _fold_keys(sd, p + ".3.weight", p + ".4")                        # (cout,cin,1,1)
+        if cin % 64 == 0:
+            put(p + ".pw", w.reshape(cout, cin), b, L)
+        else:
+            put(p + ".pw", w.reshape(cout, cin).T, b, L)
+    for name in ("output1", "output2", "output3", "merge1", "merge2"):
+        w, b = _fold_keys(sd, f"fpn.{name}.0.weight", f"fpn.{name}.1")
+        put(f"fpn.{name}", np.transpose(w, (0, 2, 3, 1)).reshape(w.shape[0], -1), b, L)
+    for lvl in range(3):
+        s = f"ssh{lvl + 1}"
+        f = {n: _fold_keys(sd, f"{s}.{n}.0.weight", f"{s}.{n}.1")
+             for n in ("conv3X3", "conv5X5_1", "conv5X5_2", "conv7X7_2", "conv7x7_3")}
+        # S1: [conv3X3 | conv5X5_1 | 0]
+        W = np.zeros((64, 3, 3, 64), np.float32)
+        B = np.zeros((64,), np.float32)
+        W[0:32] = np.transpose(f["conv3X3"][0], (0, 2, 3, 1))
+        W[32:48] = np.transpose(f["conv5X5_1"][0], (0, 2, 3, 1))
+        B[0:32], B[32:48] = f["conv3X3"][1], f["conv5X5_1"][1]
+        put(f"{s}.S1", W.reshape(64, -1), B, np.r_[np.zeros(32), np.full(16, L), np.zeros(16)])
+        # S2: reads channels 32:48 of S1 -> [conv5X5_2 | conv7X7_2 | 0]
+        W = np.zeros((64, 3, 3, 64), np.float32)
+        B = np.zeros((64,), np.float32)
+        W[0:16, :, :, 32:48] = np.transpose(f["conv5X5_2"][0], (0, 2, 3, 1))
+        W[16:32, :, :, 32:48] = np.transpose(f["conv7X7_2"][0], (0, 2, 3, 1))
+        B[0:16], B[16:32] = f["conv5X5_2"][1], f["conv7X7_2"][1]
+        put(f"{s}.S2", W.reshape(64, -1), B, np.r_[np.zeros(16), np.full(16, L), np.zeros(32)])
+        # S3: channels 0:16 pass through an identity centre tap, [16:32] = conv7x7_3 of channels 16:32
+        W = np.zeros((64, 3, 3, 64), np.float32)
+        B = np.zeros((64,), np.float32)
+        for c in range(16):
+            W[c, 1, 1, c] = 1.0
+        W[16:32, :, :, 16:32] = np.transpose(f["conv7x7_3"][0], (0, 2, 3, 1))
+        B[16:32] = f["conv7x7_3"][1]
+        put(f"{s}.S3", W.reshape(64, -1), B, np.zeros(64))
+        # heads over [S1 (64) | S3 (64)]: concat channel j of the reference = S1[j] (j < 32), S3[j - 32] (j >= 32)
+        ws, bs = [], []
+        for hk in ("BboxHead", "ClassHead", "LandmarkHead"):
+            ws.append(np.asarray(sd[f"{hk}.{lvl}.conv1x1.weight"], np.float32).reshape(-1, 64))
+            bs.append(np.asarray(sd[f"{hk}.{lvl}.conv1x1.bias"], np.float32))
+        hw = np.concatenate(ws, 0)
+        assert hw.shape == (am.HEAD_ROWS, 64)
+        mat = np.zeros((am.HEAD_ROWS, 128), np.float32)
+        mat[:, 0:32] = hw[:, 0:32]
+        mat[:, 64:96] = hw[:, 32:64]
+        put(f"heads.{lvl}", mat, np.concatenate(bs), 1.0)
+    return packed
