@@ -107,6 +107,9 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
                                   to the convolution's output inside the kernel; Hout/Wout stay conv1's extents and y is
                                   the POOLED tensor [B][(Hout+1)/2][(Wout+1)/2][64] (reference retinaface.py:71-73: the
                                   conv1 -> bn1 -> relu -> maxpool head of the ResNet body) */
+#define VD_CONV_SLOPE 256u     /* activation = per-channel negative-side slope (desc.slope) instead of VD_CONV_RELU: the
+                                  LeakyReLU(0.1) layers of the MobileNet0.25 variant (reference nets/layers.py:41,71,
+                                  nets/mobilenet025.py:3-19) and tiles that mix ReLU / leaky / pass-through channels */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 
@@ -128,6 +131,8 @@ typedef struct vd_conv_desc {
   /* VD_CONV_DUAL: y += conv1x1_stride2(x2); weights are [Cout][R*S*Cin + Cin2], bias is the sum */
   const void* x2;            /* [dev] bf16 NHWC [B][Hin2][Win2][Cin2] or NULL */
   int32_t Cin2, Hin2, Win2, stride2;
+  /* VD_CONV_SLOPE: fp32 [Cout], y = v > 0 ? v : v * slope[c] (0 = ReLU, 0.1 = LeakyReLU(0.1), 1 = identity) */
+  const float* slope;
 } vd_conv_desc_t;
 
 typedef struct vd_conv_plan vd_conv_plan_t;
@@ -144,6 +149,21 @@ int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, int* NB, int
 int vd_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
 /* same on split-precision tensors: [B][H][W][3*C] planes hi | lo | hi, maximum of hi + lo (VD_CONV_SPLIT) */
 int vd_maxpool3x3s2_split(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
+
+/* ---- MobileNet0.25 variant (Retinaface(backbone="mobilenet"), reference detect_face/nets/mobilenet025.py) ----------
+ * The layers whose channel count is below the tensor-core kernel's 64-channel granule are HBM-bound streaming
+ * kernels on the CUDA cores (bf16/fp16 NHWC in and out, fp32 accumulate, folded BN bias, per-channel slope):
+ *   vd_mnet_stem   conv_bn(3, 8, stride 2) on the ingest layout x0            (mobilenet025.py:3-8, :26)
+ *   vd_mnet_dw3x3  depthwise 3x3, stride 1 or 2, pad 1, C % 8 == 0            (conv_dw first half, :10-14)
+ *   vd_mnet_pw     pointwise 1x1, Cin % 8 == 0, Cout % 8 == 0, Cin*Cout <= 4096 (conv_dw second half, :16-18)
+ * Weights are in the activation type: stem [3][3][4][8] (r, s, channel incl. the zero 4th, cout), dw [9][C],
+ * pw [Cin][Cout]. */
+int vd_mnet_stem(const void* x0, const void* w, const float* bias, const float* slope, void* y, int B, int H, int W,
+                 vd_stream_t stream);                        /* y: [B][(H+1)/2][(W+1)/2][8] */
+int vd_mnet_dw3x3(const void* x, const void* w, const float* bias, const float* slope, void* y, int B, int H, int W,
+                  int C, int stride, vd_stream_t stream);    /* y: [B][ceil(H/stride)][ceil(W/stride)][C] */
+int vd_mnet_pw(const void* x, const void* w, const float* bias, const float* slope, void* y, long long npix, int Cin,
+               int Cout, vd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K3 decode + threshold + compaction                                                          */

@@ -55,6 +55,7 @@ struct ConvKParams {
   int w_bytes;            // wres: KB * BN * 128
   uint32_t flags;
   const float* bias;
+  const float* slope;     // VD_CONV_SLOPE: per-channel negative-side factor
   const __nv_bfloat16* residual;
   const __nv_bfloat16* upadd;
   void* y;
@@ -148,6 +149,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* afull = wfull + 1;                            // patch ring (<= 4 slots)
   uint64_t* aempty = afull + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
+  float* sSlope = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);   // VD_CONV_SLOPE only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -483,7 +485,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ncol0 = n_tile * BN + half * 32;       // first output channel of this thread in chunk 0
       if (n_tile != bias_tile) {                       // folded-BN bias of this N tile -> shared memory
         named_bar_sync(1, kEpiThreads);
-        if (etid < BN) sBias[etid] = __ldg(p.bias + n_tile * BN + etid);
+        if (etid < BN) {
+          sBias[etid] = __ldg(p.bias + n_tile * BN + etid);
+          if (p.flags & VD_CONV_SLOPE) sSlope[etid] = __ldg(p.slope + n_tile * BN + etid);
+        }
         named_bar_sync(1, kEpiThreads);
         bias_tile = n_tile;
       }
@@ -551,7 +556,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (p.flags & VD_CONV_RELU) {
+          if (p.flags & VD_CONV_SLOPE) {
+            const uint32_t sp = smem_u32(sSlope) + static_cast<uint32_t>((ch * 64 + half * 32) * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 sv = lds128(sp + j * 16);
+              f[4 * j + 0] = f[4 * j + 0] > 0.f ? f[4 * j + 0] : f[4 * j + 0] * __uint_as_float(sv.x);
+              f[4 * j + 1] = f[4 * j + 1] > 0.f ? f[4 * j + 1] : f[4 * j + 1] * __uint_as_float(sv.y);
+              f[4 * j + 2] = f[4 * j + 2] > 0.f ? f[4 * j + 2] : f[4 * j + 2] * __uint_as_float(sv.z);
+              f[4 * j + 3] = f[4 * j + 3] > 0.f ? f[4 * j + 3] : f[4 * j + 3] * __uint_as_float(sv.w);
+            }
+          } else if (p.flags & VD_CONV_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
@@ -705,7 +720,8 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   ConvKParams& k = pl->kp;
   const int KB = k.R * k.S * k.cin_blocks + k.kb2;
   const int budget = occ > 1 ? (kSmemBudget / occ - 1024) : kSmemBudget;
-  const int avail = budget - Cfg::FIXED_BYTES;
+  const int extra = (k.flags & VD_CONV_SLOPE) ? 1024 : 0;          // per-channel slope vector behind the barriers
+  const int avail = budget - Cfg::FIXED_BYTES - extra;
   const char* env = getenv("VD_CONV_KPS");
   const int force_kps = env ? atoi(env) : 0;
   if (k.patch) {
@@ -725,7 +741,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
           k.a_slots = slots;
           k.kps = 1;
           k.stages = 1;
-          pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + wb;
+          pl->smem_bytes = extra + Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + wb;
           return true;
         }
       }
@@ -745,7 +761,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
       st = (avail - k.a_slots * k.a_slot_bytes) / (k.kps * Cfg::B_BYTES);
     }
     k.stages = st > kMaxStages ? kMaxStages : st;
-    pl->smem_bytes = Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + k.stages * k.kps * Cfg::B_BYTES;
+    pl->smem_bytes = extra + Cfg::FIXED_BYTES + k.a_slots * k.a_slot_bytes + k.stages * k.kps * Cfg::B_BYTES;
     return k.stages >= min_stages;
   }
   if (ROWB == 64) {
@@ -755,7 +771,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
     k.kps = 1;
     const int st = (avail - k.w_bytes) / Cfg::A_BYTES;
     k.stages = st > kMaxStages ? kMaxStages : st;
-    pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * Cfg::A_BYTES;
+    pl->smem_bytes = extra + Cfg::FIXED_BYTES + k.w_bytes + k.stages * Cfg::A_BYTES;
     return k.stages >= min_stages;
   }
   const int w_bytes = KB * Cfg::B_BYTES;
@@ -777,7 +793,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   }
   k.kps = kps;
   k.stages = st > kMaxStages ? kMaxStages : st;
-  pl->smem_bytes = Cfg::FIXED_BYTES + k.w_bytes + k.stages * kps * per_block;
+  pl->smem_bytes = extra + Cfg::FIXED_BYTES + k.w_bytes + k.stages * kps * per_block;
   return k.stages >= min_stages;
 }
 
@@ -848,6 +864,8 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   VD_REQUIRE(x0 || (d->Cin % 64 == 0), "vd_conv_plan_create: Cin=%d must be a multiple of 64", d->Cin);
   VD_REQUIRE(d->x && d->w && d->bias && d->y, "vd_conv_plan_create: null tensor pointer");
   VD_REQUIRE(!(d->flags & VD_CONV_RESIDUAL) || d->residual, "vd_conv_plan_create: residual flag without tensor");
+  VD_REQUIRE(!(d->flags & VD_CONV_SLOPE) || (d->slope && !(d->flags & VD_CONV_SPLIT)),
+             "vd_conv_plan_create: VD_CONV_SLOPE needs desc.slope (and is not available in split mode)");
   VD_REQUIRE(!(d->flags & VD_CONV_UPADD) || (d->upadd && d->up_H > 0 && d->up_W > 0),
              "vd_conv_plan_create: upadd flag without tensor");
   VD_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
@@ -971,6 +989,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.up_H = d->up_H; k.up_W = d->up_W;
   k.flags = d->flags;
   k.bias = d->bias;
+  k.slope = d->slope;
   k.residual = static_cast<const __nv_bfloat16*>(d->residual);
   k.upadd = static_cast<const __nv_bfloat16*>(d->upadd);
   k.y = d->y;

@@ -4,7 +4,8 @@ backed by libvdesens (sm_100a CUDA kernels behind the C-ABI of include/vdesens.h
 Same constructor kwargs/defaults, attributes and methods; same return types; same error behaviour
 (Python exceptions).  Differences that are deliberate:
   * `cuda=False` raises: there is no CPU fallback in this build;
-  * `backbone="mobilenet"` raises NotImplementedError (outside BASELINE.json's hot path);
+  * `backbone="mobilenet"` (cfg_mnet) runs the MobileNet0.25 variant: sub-64-channel layers as streaming kernels,
+    the rest on the same tcgen05 convolution kernel with LeakyReLU(0.1) epilogues (bf16 / fp16 storage only);
   * multi-GPU is one process per GPU (vdesens_b200.shard), not nn.DataParallel (face.py:56);
   * extra optional kwargs: `state_dict` (weights given in memory instead of `model_path`),
     `batch_size` (engine batch, default = first batch seen), `cand_cap`, `max_det`, `device_index`,
@@ -19,7 +20,7 @@ import torch
 from vdesens_b200 import ops as _ops
 from vdesens_b200.engine import DetectorEngine
 from .utils.anchors import Anchors
-from .utils.config import cfg_re50
+from .utils.config import cfg_mnet, cfg_re50
 
 
 class _NetHandle(object):
@@ -80,9 +81,8 @@ class Retinaface(object):
         self.precision = "bf16"
         for name, value in kwargs.items():
             setattr(self, name, value)
-        if self.backbone == "mobilenet":
-            raise NotImplementedError("the B200 build implements the ResNet-50 detector only")
-        self.cfg = cfg_re50
+        # reference face.py:35: anything but "mobilenet" selects cfg_re50
+        self.cfg = cfg_mnet if self.backbone == "mobilenet" else cfg_re50
         if not (self.cuda and torch.cuda.is_available()):
             raise RuntimeError("vdesens Retinaface needs a CUDA (sm_100a) device; there is no CPU fallback")
         idx = torch.cuda.current_device() if self.device_index is None else int(self.device_index)
@@ -108,7 +108,8 @@ class Retinaface(object):
         if b not in self._engines:
             self._engines[b] = DetectorEngine(self._sd, b, self.input_shape[0], self.input_shape[1], device=self.device,
                                               confidence=self.confidence, nms_iou=self.nms_iou, cand_cap=self.cand_cap,
-                                              max_det=self.max_det, precision=self.precision)
+                                              max_det=self.max_det, precision=self.precision,
+                                              backbone="mobilenet" if self.backbone == "mobilenet" else "resnet50")
         eng = self._engines[b]
         eng.confidence, eng.nms_iou = float(self.confidence), float(self.nms_iou)
         return eng

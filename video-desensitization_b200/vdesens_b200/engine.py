@@ -1,4 +1,4 @@
-"""Device engine: one persistent RetinaFace-ResNet50 replica on one GPU.
+"""Device engine: one persistent RetinaFace replica (ResNet-50, or the MobileNet0.25 variant) on one GPU.
 
 Owns the packed weights, every activation buffer for a fixed (B, H, W), one conv plan (TMA tensor
 maps + tiling) per layer, the post-processing workspaces and a private CUDA stream.  `forward`
@@ -42,13 +42,19 @@ def _on_device(fn):
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16",
-                 fuse_stem_pool=None):
+                 fuse_stem_pool=None, backbone="resnet50"):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
         # planes for activations and weights, three tensor-core products per term (VD_CONV_SPLIT), ~1/3 of the speed
         self.precision = precision
         self.split = precision == "fp32x"
+        # "resnet50" (BASELINE's network) or "mobilenet" (reference face.py:35 / cfg_mnet)
+        if backbone not in ("resnet50", "mobilenet"):
+            raise ValueError(f"Unsupported backbone - `{backbone}`, Use mobilenet, resnet50.")
+        self.backbone = backbone
+        if backbone == "mobilenet" and self.split:
+            raise ValueError('precision="fp32x" is implemented for the resnet50 backbone only')
         # conv1+bn1+relu+maxpool as one kernel (VD_CONV_POOL); the split-precision mode keeps the two-kernel form
         if fuse_stem_pool is None:
             fuse_stem_pool = os.environ.get("VD_STEM_POOL", "1") != "0"
@@ -76,11 +82,16 @@ class DetectorEngine:
 
     # ------------------------------------------------------------------------------------------
     def _build(self, state_dict, scratch_frames):
+        self.plans = []      # ("conv", handle, name) / ("maxpool", (src, dst)) / ("stem"|"dw"|"pw", MOp, name), in order
+        self._plan_handles = []
+        if self.backbone == "mobilenet":
+            self._build_mnet(state_dict)
+        else:
+            self._build_resnet(state_dict)
+        self._build_post(scratch_frames)
+
+    def _alloc_buffers(self, bufs, P=1):
         dev, B, H, W = self.device, self.B, self.H, self.W
-        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool)
-        packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
-        P = 3 if self.split else 1            # channel planes per activation tensor
-        self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
         self.Wp = self.lib.vd_x0_pitch(W)
         self.buf, self.buf_hw = {}, {}
         for bs in bufs:
@@ -96,9 +107,56 @@ class DetectorEngine:
             self.heads.append(torch.empty((B, h * w, arch.HEAD_ROWS), dtype=torch.float32, device=dev))
         self.A = arch.num_anchors(H, W)
 
-        # ---- plans ----
-        self.plans = []      # list of ("conv", handle, name) / ("maxpool", (src, dst)) in execution order
-        self._plan_handles = []
+    def _build_mnet(self, state_dict):
+        """MobileNet0.25 variant: the op list of arch_mnet.build_graph() (reference nets/mobilenet025.py,
+        nets/layers.py with LeakyReLU(0.1), retinaface.py:60-73)."""
+        from . import arch_mnet
+        dev, B = self.device, self.B
+        ops, bufs = arch_mnet.build_graph()
+        packed = weights.pack_mnet(state_dict, self.act_dtype)
+        self.w = {k: tuple(t.to(dev) for t in v) for k, v in packed.items()}
+        self._alloc_buffers(bufs)
+        for op in ops:
+            if op.kind in ("stem", "dw", "pw"):
+                self.plans.append((op.kind, op, op.name))
+                continue
+            wt, bt, st = self.w[op.name]
+            hin, win, cin = self.buf_hw[op.src]
+            d = _lib.VdConvDesc()
+            d.B, d.Hin, d.Win, d.Cin = B, hin, win, cin
+            d.R = d.S = op.k
+            d.stride, d.pad = op.stride, op.pad
+            d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
+            if op.kind == "heads":             # 1x1 over [S1 | S3] as a two-segment K loop, fp32 out, no activation
+                x2 = self.buf[op.src2]
+                d.Hout, d.Wout, d.Cout = hin, win, arch.HEAD_ROWS
+                d.dst_C, d.dst_coff = arch.HEAD_ROWS, 0
+                d.flags = _lib.VD_CONV_OUT_F32 | _lib.VD_CONV_DUAL
+                d.x2 = x2.data_ptr()
+                d.Hin2, d.Win2, d.Cin2, d.stride2 = x2.shape[1], x2.shape[2], x2.shape[3], 1
+                d.y = self.heads[op.level].data_ptr()
+            else:
+                hout, wout, dst_c = self.buf_hw[op.dst]
+                d.Hout, d.Wout, d.Cout = hout, wout, op.cout
+                d.dst_C, d.dst_coff = dst_c, 0
+                d.flags = _lib.VD_CONV_SLOPE
+                d.slope = st.data_ptr()
+                if op.upsample_add:
+                    up = self.buf[op.upsample_add]
+                    d.flags |= _lib.VD_CONV_UPADD
+                    d.upadd = up.data_ptr()
+                    d.up_H, d.up_W = up.shape[1], up.shape[2]
+                d.y = self.buf[op.dst].data_ptr()
+            self.plans.append(("conv", self._make_plan(d, op.name), op.name))
+
+    def _build_resnet(self, state_dict):
+        dev, B, H, W = self.device, self.B, self.H, self.W
+        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool)
+        packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
+        P = 3 if self.split else 1            # channel planes per activation tensor
+        self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
+        self._alloc_buffers(bufs, P)
+
         for op in ops:
             if op.kind == "conv":
                 c = op.conv
@@ -159,7 +217,8 @@ class DetectorEngine:
                 d.y = self.heads[op.level].data_ptr()
                 self.plans.append(("conv", self._make_plan(d, f"heads.{op.level}"), f"heads.{op.level}"))
 
-        # ---- post-processing state ----
+    def _build_post(self, scratch_frames):
+        dev, B, H, W = self.device, self.B, self.H, self.W
         self.frame_desc_host = torch.zeros((B, 6), dtype=torch.int32).pin_memory()   # 24-byte vd_frame_t rows
         self.frame_desc = torch.zeros((B, 6), dtype=torch.int32, device=dev)
         self.cand = torch.empty((B, self.cap, 16), dtype=torch.float32, device=dev)
@@ -281,6 +340,18 @@ class DetectorEngine:
         for kind, h, name in self.plans:
             if kind == "conv":
                 _lib.check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
+            elif kind in ("stem", "dw", "pw"):
+                op = h
+                wt, bt, st = self.w[op.name]
+                hh, ww, cc = self.buf_hw[op.src]
+                x, y = _ptr(self.buf[op.src]), _ptr(self.buf[op.dst])
+                if kind == "stem":
+                    rc = self.lib.vd_mnet_stem(x, _ptr(wt), _ptr(bt), _ptr(st), y, self.B, self.H, self.W, s)
+                elif kind == "dw":
+                    rc = self.lib.vd_mnet_dw3x3(x, _ptr(wt), _ptr(bt), _ptr(st), y, self.B, hh, ww, cc, op.stride, s)
+                else:
+                    rc = self.lib.vd_mnet_pw(x, _ptr(wt), _ptr(bt), _ptr(st), y, self.B * hh * ww, op.cin, op.cout, s)
+                _lib.check(rc, f"vd_mnet_{kind}({name})")
             else:
                 src, dst = h
                 hh, ww, cc = self.buf_hw[src]

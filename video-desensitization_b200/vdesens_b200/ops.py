@@ -62,7 +62,7 @@ def ingest_nchw_f32(frames, H, W):
 
 
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False):
+           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
     The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
@@ -105,6 +105,9 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
         flags |= _lib.VD_CONV_DUAL
         d.x2 = x2.data_ptr()
         d.Hin2, d.Win2, d.Cin2, d.stride2 = x2.shape[1], x2.shape[2], x2.shape[3], stride2
+    if slope is not None:     # per-channel negative-side slope instead of relu (0 ReLU, 0.1 LeakyReLU, 1 identity)
+        flags |= _lib.VD_CONV_SLOPE
+        d.slope = slope.data_ptr()
     d.flags = flags
     d.x, d.w, d.bias = x.data_ptr(), w_packed.data_ptr(), bias.data_ptr()
     d.residual = residual.data_ptr() if residual is not None else None
@@ -117,6 +120,33 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     finally:
         lib.vd_conv_plan_destroy(h)
     return out
+
+
+def mnet_stem(x0, w, bias, slope, H, W):
+    """conv_bn(3, 8, stride 2) of the MobileNet0.25 variant on the ingest tensor (reference mobilenet025.py:3-8)."""
+    lib = _lib.lib(_lib.precision_of(x0.dtype))
+    y = torch.empty((x0.shape[0], (H + 1) // 2, (W + 1) // 2, 8), dtype=x0.dtype, device=x0.device)
+    _lib.check(lib.vd_mnet_stem(_p(x0), _p(w), _p(bias), _p(slope), _p(y), x0.shape[0], H, W, _stream()), "vd_mnet_stem")
+    return y
+
+
+def mnet_dw3x3(x, w, bias, slope, stride):
+    """depthwise 3x3 + folded BN + slope activation (reference mobilenet025.py:10-14); w is [9][C]."""
+    lib = _lib.lib(_lib.precision_of(x.dtype))
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, (H + stride - 1) // stride, (W + stride - 1) // stride, Cc), dtype=x.dtype, device=x.device)
+    _lib.check(lib.vd_mnet_dw3x3(_p(x), _p(w), _p(bias), _p(slope), _p(y), B, H, W, Cc, stride, _stream()), "vd_mnet_dw3x3")
+    return y
+
+
+def mnet_pw(x, w, bias, slope):
+    """pointwise 1x1 for Cin < 64 (reference mobilenet025.py:16-18); w is [Cin][Cout]."""
+    lib = _lib.lib(_lib.precision_of(x.dtype))
+    B, H, W, Cin = x.shape
+    Cout = w.shape[1]
+    y = torch.empty((B, H, W, Cout), dtype=x.dtype, device=x.device)
+    _lib.check(lib.vd_mnet_pw(_p(x), _p(w), _p(bias), _p(slope), _p(y), B * H * W, Cin, Cout, _stream()), "vd_mnet_pw")
+    return y
 
 
 def maxpool3x3s2(x):
