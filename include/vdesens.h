@@ -110,6 +110,11 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
 #define VD_CONV_SLOPE 256u     /* activation = per-channel negative-side slope (desc.slope) instead of VD_CONV_RELU: the
                                   LeakyReLU(0.1) layers of the MobileNet0.25 variant (reference nets/layers.py:41,71,
                                   nets/mobilenet025.py:3-19) and tiles that mix ReLU / leaky / pass-through channels */
+#define VD_CONV_CHAIN 512u     /* the kernel also runs the NEXT layer, a 1x1 convolution Cout -> chain_Cout (+bias, ReLU) of
+                                  its own output tile while that tile is still in shared memory (bottleneck conv3 followed
+                                  by the next bottleneck's conv1, reference torchvision resnet50 Bottleneck.forward): the
+                                  wide tensor is written once and not read back.  Needs R = S = 1, Cout = 256,
+                                  chain_Cout in {64, 128}; results are bit-identical to the two separate launches */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 
@@ -133,6 +138,12 @@ typedef struct vd_conv_desc {
   int32_t Cin2, Hin2, Win2, stride2;
   /* VD_CONV_SLOPE: fp32 [Cout], y = v > 0 ? v : v * slope[c] (0 = ReLU, 0.1 = LeakyReLU(0.1), 1 = identity) */
   const float* slope;
+  /* VD_CONV_CHAIN: y2 = relu(conv1x1(y) + chain_bias); chain_w is [chain_Cout][Cout] (K-major), chain_y is
+     [B][Hout][Wout][chain_Cout] in the activation type */
+  const void* chain_w;
+  const float* chain_bias;
+  void* chain_y;
+  int32_t chain_Cout;
 } vd_conv_desc_t;
 
 typedef struct vd_conv_plan vd_conv_plan_t;

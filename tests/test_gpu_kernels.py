@@ -873,3 +873,54 @@ def test_detector_called_from_pool_threads_like_the_reference(sd_np):
             got, plates = f1.result(), f2.result()
             assert [b for _, b in got] == [b for _, b in want]
             assert len(plates) == 2
+
+
+# ------------------------------------------------------------------------------------------------
+# VD_CONV_CHAIN: conv3 + the next bottleneck's conv1 in one kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("residual,dual,n2,shape", [
+    (True, False, 64, (2, 24, 32)), (True, False, 64, (1, 17, 31)), (True, False, 64, (4, 68, 120)),
+    (False, True, 64, (2, 45, 77)), (True, False, 128, (3, 33, 50)), (False, False, 128, (2, 24, 32)),
+    (True, False, 64, (8, 135, 240)),
+])
+def test_conv_chain_is_bit_identical_to_two_launches(ops, residual, dual, n2, shape):
+    """1x1 conv (Cout 256, +residual / +projection segment, ReLU) chained with the next 1x1 conv (256 -> 64/128, ReLU):
+    both outputs equal the two separate launches bit for bit (same MMA order, same rounding points)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * H + W + n2)
+    dt = torch.bfloat16
+    x = torch.randn(B, H, W, 64, generator=g).to(dt).to(DEV)
+    cin = 128 if dual else 64
+    w = (torch.randn(256, cin, generator=g) * 0.1).to(dt).to(DEV)
+    bias = (torch.randn(256, generator=g) * 0.1).to(DEV)
+    x2 = torch.randn(B, H, W, 64, generator=g).to(dt).to(DEV) if dual else None
+    res = torch.randn(B, H, W, 256, generator=g).to(dt).to(DEV) if residual else None
+    w2 = (torch.randn(n2, 256, generator=g) * 0.06).to(dt).to(DEV)
+    b2 = (torch.randn(n2, generator=g) * 0.1).to(DEV)
+    y_ref = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=res, x2=x2)
+    t_ref = ops.conv2d(y_ref, w2, b2, 1, 1, 0, relu=True)
+    y, t = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=res, x2=x2, chain=(w2, b2))
+    torch.cuda.synchronize()
+    assert tuple(t.shape) == (B, H, W, n2)
+    assert torch.equal(y, y_ref), float((y.float() - y_ref.float()).abs().max())
+    assert torch.equal(t, t_ref), float((t.float() - t_ref.float()).abs().max())
+    assert float(t.float().abs().max()) > 0
+
+
+def test_chain_engine_matches_unfused_engine(sd_np):
+    """whole network with and without VD_CONV_CHAIN (3 fusion points in layer1): identical head tensors and rows."""
+    from vdesens_b200.engine import DetectorEngine
+    frames = [synth.synthetic_frame(135, 241, 4242 + i) for i in range(3)]
+    outs = []
+    for fuse in (False, True):
+        eng = DetectorEngine(sd_np, len(frames), 135, 241, device=DEV, confidence=0.5, nms_iou=0.4, fuse_chain=fuse)
+        assert sum(1 for k, _, _ in eng.plans if k == "conv") == (69 if fuse else 72) - (0 if eng.fuse_stem_pool else 0)
+        eng.set_frames(_dev_frames(frames))
+        eng.forward()
+        rows, counts = eng.fetch_results()
+        outs.append(([t.clone() for t in eng.head_tensors()], rows.copy(), counts.copy(),
+                     eng.activation("layer1.2.out").clone(), eng.activation("layer2.0.t1").clone()))
+    assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][1], outs[1][1])

@@ -52,17 +52,22 @@ with torch.cuda.stream(eng.stream):
         rows.append((name, ms))
 # flops per layer from output extents
 out_hw = {}
-_, ops_, _ = arch.build_graph(fuse_stem_pool=eng.fuse_stem_pool)
+_, ops_, _ = arch.build_graph(fuse_stem_pool=eng.fuse_stem_pool, fuse_chain=eng.fuse_chain)
+chained = {}
 for op in ops_:
     if op.kind == "conv":
         hh, ww, _ = eng.buf_hw[op.dst]
         out_hw[op.conv.name] = hh * ww
+        if op.chain is not None:          # the kernel also runs the next 1x1 convolution
+            flops[op.conv.name] += flops[op.chain.name]
+            chained[op.conv.name] = op.chain.name
 print(f"B={B} {H}x{W}  sum of per-layer times {tot:.3f} ms  ({B / tot * 1e3:.1f} frames/s network-only)")
 for name, ms in rows:
     if name in flops and name in out_hw:
         gf = flops[name] * out_hw[name] * B / 1e9
         tw, th, nb, bn, nt, grid = info[name]
-        print(f"{name:28s} {ms:8.4f} ms  {gf / ms:9.1f} TFLOP/s-eq  tile {tw}x{th}x{nb} BN{bn} tiles {nt} grid {grid}")
+        extra = f"  (+ {chained[name]})" if name in chained else ""
+        print(f"{name:28s} {ms:8.4f} ms  {gf / ms:9.1f} TFLOP/s-eq  tile {tw}x{th}x{nb} BN{bn} tiles {nt} grid {grid}{extra}")
     else:
         print(f"{name:28s} {ms:8.4f} ms")
 # whole forward

@@ -56,6 +56,9 @@ struct ConvKParams {
   uint32_t flags;
   const float* bias;
   const float* slope;     // VD_CONV_SLOPE: per-channel negative-side factor
+  const float* bias2;     // VD_CONV_CHAIN: folded-BN bias of the chained 1x1 convolution
+  int N2;                 // VD_CONV_CHAIN: its output channels (64 or 128)
+  int w2_bytes;           // VD_CONV_CHAIN: N2 * Cout * 2 (its whole weight matrix, resident in shared memory)
   const __nv_bfloat16* residual;
   const __nv_bfloat16* upadd;
   void* y;
@@ -124,12 +127,28 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) 
   return c;
 }
 
-template <int BN, bool RES, int ROWB>
-__global__ void __launch_bounds__((ConvCfg<BN, RES, ROWB>::THREADS), (BN <= 128 && !RES) ? 2 : 1)
+// tile visited by this CTA in iteration `it`.  CHAIN: the N tiles of one M tile run back to back on the same CTA (the
+// chained convolution accumulates over all of them), M tiles are dealt round-robin.
+template <bool CHAIN>
+__device__ __forceinline__ int tile_at(const ConvKParams& p, int it) {
+  if (CHAIN) return (static_cast<int>(blockIdx.x) + (it >> 1) * static_cast<int>(gridDim.x)) * 2 + (it & 1);
+  return static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+}
+
+// CHAIN (VD_CONV_CHAIN, BN = 128, Cout = 256): the kernel also computes the NEXT layer, a 1x1 convolution
+// Cout -> N2 (+bias, ReLU) of its own output — bottleneck conv3 followed by the next bottleneck's conv1.  Every
+// 64-channel output chunk already sits in shared memory as a SWIZZLE_128B 128-row tile for the TMA store; that tile IS
+// the K-major A operand of one K block of the chained GEMM, so the MMA warp accumulates it (4 MMAs, B = resident
+// W2 block) into a second TMEM accumulator while the store drains, and the wide tensor is never read back from HBM.
+template <int BN, bool RES, int ROWB, bool CHAIN>
+__global__ void __launch_bounds__((ConvCfg<BN, RES, ROWB>::THREADS), (BN <= 128 && !RES && !CHAIN) ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmA2, const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmY2, const ConvKParams p) {
   using Cfg = ConvCfg<BN, RES, ROWB>;
+  static_assert(!CHAIN || (BN == 128 && ROWB == 128), "CHAIN: two 128-wide N tiles per M tile");
+  constexpr int kTmemCols = CHAIN ? 512 : Cfg::TMEM_COLS;      // CHAIN: 2 x 128 (main) + 2 x N2 (chained), N2 <= 128
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
@@ -138,7 +157,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sB = smem + (p.patch ? p.a_slots * p.a_slot_bytes : STAGES * KPS * Cfg::A_BYTES);   // B stages / resident W
   uint8_t* sOut = sB + (p.wres ? p.w_bytes : STAGES * KPS * Cfg::B_BYTES);
   uint8_t* sRes = sOut + Cfg::OUT_BYTES;
-  float* sBias = reinterpret_cast<float*>(sRes + Cfg::RES_BYTES);
+  uint8_t* sW2 = sRes + Cfg::RES_BYTES;                   // CHAIN: resident weights of the chained convolution
+  uint8_t* sOut2 = sW2 + (CHAIN ? p.w2_bytes : 0);        // CHAIN: staging tile of the chained output
+  float* sBias2 = reinterpret_cast<float*>(sOut2 + (CHAIN ? 128 * 128 : 0));      // CHAIN: bias of the chained conv (512 B)
+  float* sBias = sBias2 + (CHAIN ? 128 : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
   uint64_t* empty = full + kMaxStages;
   uint64_t* tfull = empty + kMaxStages;
@@ -149,6 +171,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* afull = wfull + 1;                            // patch ring (<= 4 slots)
   uint64_t* aempty = afull + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
+  uint64_t* ystaged = full + 38;                          // CHAIN: output chunk staged in sOut[k] (epilogue -> MMA warp)
+  uint64_t* yfree = ystaged + 2;                          //        chained MMAs have read sOut[k]
+  uint64_t* t1full = yfree + 2;                           //        chained accumulator complete
+  uint64_t* t1empty = t1full + 2;                         //        chained accumulator drained by the epilogue
+  uint64_t* w2full = t1empty + 2;                         //        W2 landed
   float* sSlope = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);   // VD_CONV_SLOPE only
 
   const int warp = threadIdx.x >> 5;
@@ -160,6 +187,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmY);
     if (RES) tma_prefetch_desc(&tmR);
     if (p.flags & VD_CONV_DUAL) tma_prefetch_desc(&tmA2);
+    if (CHAIN) {
+      tma_prefetch_desc(&tmB2);
+      tma_prefetch_desc(&tmY2);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -180,10 +211,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_init(&rfull[i], 1);
         mbar_init(&rempty[i], 8);
       }
+      if (CHAIN) {
+        for (int i = 0; i < 2; ++i) {
+          mbar_init(&ystaged[i], 1);
+          mbar_init(&yfree[i], 1);
+          mbar_init(&t1full[i], 1);
+          mbar_init(&t1empty[i], 8);
+        }
+        mbar_init(w2full, 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   // Programmatic dependent launch: the next kernel of the stream may start its own prologue on SMs this grid has
@@ -208,9 +248,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * (ROWB / 2), 0);
     }
+    if (CHAIN && elect_one()) {                       // chained convolution's weights: [N2][Cout], one box per K block
+      mbar_expect_tx(w2full, static_cast<uint32_t>(p.w2_bytes));
+      for (int kb = 0; kb < p.Cout / 64; ++kb) tma_load_2d(sW2 + kb * p.N2 * 128, &tmB2, w2full, kb * 64, 0);
+    }
     __syncwarp();
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_bytes + (p.wres ? 0 : Cfg::B_BYTES));
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int it = 0, tile; (tile = tile_at<CHAIN>(p, it)) < p.num_tiles; ++it) {
       const TileCoord tc = tile_coord(p, tile);
       const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
       const int xin0 = tx * p.TW * p.stride_w - p.pad_w;
@@ -317,7 +361,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int aslot = 0;
     uint32_t aphase = 0;
     if (p.wres) mbar_wait(wfull, 0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // CHAIN: K blocks of the chained GEMM, one per staged 64-channel output chunk, issued one iteration behind the
+    // main MMAs (the epilogue of iteration it-1 stages them while the MMAs of iteration `it` already run)
+    int acc1 = 0;
+    uint32_t acc1_phase = 0;
+    uint32_t ychunk = 0;
+    const uint32_t idesc2 = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(p.N2 >> 3) << 17) |
+                            (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t o_lo0 = ((smem_u32(sOut) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w2_lo0 = ((smem_u32(sW2) & 0x3FFFFu) >> 4) | (1u << 16);
+    auto chain_issue = [&](int it_prev) {
+      constexpr int CPT = BN / 64;                       // chunks per tile
+      const int n = it_prev & 1;
+      for (int c = 0; c < CPT; ++c, ++ychunk) {
+        const int g = n * CPT + c;                       // K block of the chained GEMM
+        if (g == 0) {
+          if (ychunk == 0) mbar_wait(w2full, 0);
+          mbar_wait(&t1empty[acc1], acc1_phase ^ 1u);
+        }
+        const uint32_t buf = ychunk & 1u;
+        mbar_wait(&ystaged[buf], (ychunk >> 1) & 1u);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t d2 = tmem_base + static_cast<uint32_t>(2 * BN + acc1 * p.N2);
+          const uint32_t al = o_lo0 + buf * static_cast<uint32_t>((128 * 128) >> 4);
+          const uint32_t bl = w2_lo0 + static_cast<uint32_t>(g * ((p.N2 * 128) >> 4));
+          umma_bf16_words(d2, al, hi_std, bl, hi_std, idesc2, static_cast<uint32_t>(g != 0));
+          umma_bf16_words(d2, al + 2, hi_std, bl + 2, hi_std, idesc2, 1u);
+          umma_bf16_words(d2, al + 4, hi_std, bl + 4, hi_std, idesc2, 1u);
+          umma_bf16_words(d2, al + 6, hi_std, bl + 6, hi_std, idesc2, 1u);
+          umma_commit(&yfree[buf]);
+          if (g == 2 * CPT - 1) umma_commit(&t1full[acc1]);
+        }
+        __syncwarp();
+        if (g == 2 * CPT - 1) {
+          acc1 ^= 1;
+          if (acc1 == 0) acc1_phase ^= 1u;
+        }
+      }
+    };
+    int it_done = 0;
+    for (int it = 0, tile; (tile = tile_at<CHAIN>(p, it)) < p.num_tiles; ++it) {
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -424,14 +508,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      if (CHAIN) {
+        if (it > 0) chain_issue(it - 1);
+        it_done = it + 1;
+      }
     }
+    if (CHAIN && it_done > 0) chain_issue(it_done - 1);
   } else if (RES && warp == 10) {
     // ===================== residual producer =====================
     if (lane == 0) {
       constexpr int NCHUNK_R = (BN >= 64) ? BN / 64 : 1;
       int slot = 0;
       uint32_t rphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int it = 0, tile; (tile = tile_at<CHAIN>(p, it)) < p.num_tiles; ++it) {
         const TileCoord tc = tile_coord(p, tile);
         const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
         const int nplanes = (p.flags & VD_CONV_SPLIT) ? 2 : 1;      // split residual = hi plane + lo plane
@@ -470,7 +559,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t rphase = 0;
     int bias_tile = -1;
     const int etid = threadIdx.x - 64;               // 0..255 inside the epilogue group
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int acc1e = 0;                                   // CHAIN: chained accumulator being drained
+    uint32_t acc1e_phase = 0;
+    int pend_tx = 0, pend_ty = 0, pend_tb = 0;       // CHAIN: M tile whose chained epilogue is still owed
+    bool pending = false;
+    if (CHAIN) {                                     // both N tiles' biases and the chained bias, once
+      sBias[etid] = __ldg(p.bias + etid);
+      if (etid < p.N2) sBias2[etid] = __ldg(p.bias2 + etid);
+      named_bar_sync(1, kEpiThreads);
+    }
+    // ---- chained convolution's epilogue for one M tile: all its K blocks are in -> +bias2, ReLU, store ----
+    auto chain_epilogue = [&](int ptx, int pty, int ptb) {
+      mbar_wait(&t1full[acc1e], acc1e_phase);
+      tcgen05_fence_after();
+      for (int c2 = 0; c2 < p.N2 / 64; ++c2) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                          static_cast<uint32_t>(2 * BN + acc1e * p.N2 + c2 * 64 + half * 32), v);
+        tmem_ld_wait();
+        float f[32];
+        const uint32_t bp = smem_u32(sBias2) + static_cast<uint32_t>((c2 * 64 + half * 32) * 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 bv = lds128(bp + j * 16);
+          f[4 * j + 0] = fmaxf(__uint_as_float(v[4 * j + 0]) + __uint_as_float(bv.x), 0.0f);
+          f[4 * j + 1] = fmaxf(__uint_as_float(v[4 * j + 1]) + __uint_as_float(bv.y), 0.0f);
+          f[4 * j + 2] = fmaxf(__uint_as_float(v[4 * j + 2]) + __uint_as_float(bv.z), 0.0f);
+          f[4 * j + 3] = fmaxf(__uint_as_float(v[4 * j + 3]) + __uint_as_float(bv.w), 0.0f);
+        }
+        if (issuer) {                                       // previous store out of sOut2 has read it (the newest
+          if (c2 == 0) tma_store_wait_read<1>();            // group is the main output chunk staged just before)
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(1, kEpiThreads);
+        const uint32_t srow = smem_u32(sOut2) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          sts128(srow + (((half * 4 + j) ^ (row & 7)) << 4), o);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (issuer) {
+          tma_store_4d(&tmY2, sOut2, c2 * 64, ptx * p.TW, pty * p.TH, ptb * p.NB);
+          tma_store_commit();
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t1empty[acc1e]);
+      acc1e ^= 1;
+      if (acc1e == 0) acc1e_phase ^= 1u;
+    };
+    for (int it = 0, tile; (tile = tile_at<CHAIN>(p, it)) < p.num_tiles; ++it) {
       const TileCoord tc = tile_coord(p, tile);
       const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tb = tc.tb;
       const int x = tx * p.TW + tx_;
@@ -483,7 +628,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         up_pix = (static_cast<size_t>(b) * p.up_H + uy) * p.up_W + ux;
       }
       const int ncol0 = n_tile * BN + half * 32;       // first output channel of this thread in chunk 0
-      if (n_tile != bias_tile) {                       // folded-BN bias of this N tile -> shared memory
+      if (!CHAIN && n_tile != bias_tile) {             // folded-BN bias of this N tile -> shared memory
         named_bar_sync(1, kEpiThreads);
         if (etid < BN) {
           sBias[etid] = __ldg(p.bias + n_tile * BN + etid);
@@ -527,7 +672,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float f[32];
         if (active) {
           tmem_ld_wait();
-          const uint32_t bp = smem_u32(sBias) + static_cast<uint32_t>((ch * 64 + half * 32) * 4);
+          const uint32_t bp = smem_u32(sBias) + static_cast<uint32_t>(((CHAIN ? n_tile * BN : 0) + ch * 64 + half * 32) * 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 bv = lds128(bp + j * 16);
@@ -623,6 +768,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // staging tile `sbuf` is free once the TMA store issued two chunks ago has read it
         uint8_t* sbuf = sOut + (chunk_ctr & 1u) * (128 * 128);
         if (issuer) tma_store_wait_read<1>();
+        if (CHAIN) mbar_wait(&yfree[chunk_ctr & 1u], ((chunk_ctr >> 1) & 1u) ^ 1u);   // chained MMAs have read it too
         named_bar_sync(1, kEpiThreads);
         if (active) {
           // SWIZZLE_128B staging: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
@@ -651,6 +797,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int cch = f32out ? 0 : (p.dst_coff + n_tile * BN + ch * 64);
           tma_store_4d(&tmY, sbuf, cch, tx * p.TW, ty * p.TH, tb * p.NB);
           tma_store_commit();
+          if (CHAIN) mbar_arrive(&ystaged[chunk_ctr & 1u]);    // the staged tile is also a K block of the chained GEMM
+        }
+        if (CHAIN && pending && ch == 0) {       // by now the previous M tile's last chained MMAs have long completed
+          chain_epilogue(pend_tx, pend_ty, pend_tb);
+          pending = false;
         }
       }
       tcgen05_fence_before();
@@ -658,7 +809,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      if (CHAIN && (it & 1)) {           // chained epilogue of this M tile: owed, paid after the next tile's first chunk
+        pend_tx = tx; pend_ty = ty; pend_tb = tb;
+        pending = true;
+      }
     }
+    if (CHAIN && pending) chain_epilogue(pend_tx, pend_ty, pend_tb);
     if (issuer) tma_store_wait_all<0>();       // all output bytes written before the CTA retires
   }
 
@@ -667,7 +823,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -703,6 +859,8 @@ struct vd_conv_plan {
   CUtensorMap tmY;
   CUtensorMap tmR;
   CUtensorMap tmA2;
+  CUtensorMap tmB2;        // VD_CONV_CHAIN: weights of the chained convolution
+  CUtensorMap tmY2;        // VD_CONV_CHAIN: its output
   ConvKParams kp;
   int BN;
   int grid;
@@ -720,7 +878,9 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   ConvKParams& k = pl->kp;
   const int KB = k.R * k.S * k.cin_blocks + k.kb2;
   const int budget = occ > 1 ? (kSmemBudget / occ - 1024) : kSmemBudget;
-  const int extra = (k.flags & VD_CONV_SLOPE) ? 1024 : 0;          // per-channel slope vector behind the barriers
+  // per-channel slope vector behind the barriers; CHAIN: resident W2 + the chained output's staging tile
+  const int extra =
+      ((k.flags & VD_CONV_SLOPE) ? 1024 : 0) + ((k.flags & VD_CONV_CHAIN) ? k.w2_bytes + 128 * 128 + 512 : 0);
   const int avail = budget - Cfg::FIXED_BYTES - extra;
   const char* env = getenv("VD_CONV_KPS");
   const int force_kps = env ? atoi(env) : 0;
@@ -800,7 +960,7 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
 // occupancy policy: variants compiled with two CTAs per SM (see __launch_bounds__) try occ = 2 first
 template <int BN, bool RES, int ROWB = 128>
 static bool plan_occ(vd_conv_plan* pl, int sms) {
-  constexpr bool kTwo = (BN <= 128 && !RES);
+  const bool kTwo = (BN <= 128 && !RES) && !(pl->kp.flags & VD_CONV_CHAIN);
   const char* env = getenv("VD_CONV_OCC");
   const int want = env ? atoi(env) : 2;
   if (pl->kp.patch) {                       // narrow 3x3: one CTA per SM with the filter bank resident, if it fits
@@ -906,6 +1066,18 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   ConvKParams& k = pl->kp;
   memset(&k, 0, sizeof(k));
   int BN = d->Cout >= 256 ? 256 : d->Cout;
+  const bool chain = (d->flags & VD_CONV_CHAIN) != 0;
+  if (chain) {
+    if (x0 || split_mode || d->R != 1 || d->S != 1 || d->Cout != 256 || (d->chain_Cout != 64 && d->chain_Cout != 128) ||
+        !d->chain_w || !d->chain_bias || !d->chain_y || (d->flags & (VD_CONV_OUT_F32 | VD_CONV_UPADD | VD_CONV_SLOPE)) ||
+        (reinterpret_cast<uintptr_t>(d->chain_w) & 15) != 0 || (reinterpret_cast<uintptr_t>(d->chain_y) & 15) != 0) {
+      delete pl;
+      vd_set_error("vd_conv_plan_create: VD_CONV_CHAIN needs a 1x1 convolution with Cout = 256, chain_Cout 64/128 and "
+                   "16-byte aligned chain tensors");
+      return VD_ERR_UNSUPPORTED;
+    }
+    BN = 128;                    // two N tiles per M tile: 2 x 128 + 2 x chain_Cout TMEM columns
+  }
   if (BN != 32 && BN != 64 && BN != 128 && BN != 256) {
     delete pl;
     vd_set_error("vd_conv_plan_create: unsupported Cout=%d", d->Cout);
@@ -990,6 +1162,9 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.flags = d->flags;
   k.bias = d->bias;
   k.slope = d->slope;
+  k.bias2 = d->chain_bias;
+  k.N2 = chain ? d->chain_Cout : 0;
+  k.w2_bytes = chain ? d->chain_Cout * d->Cout * 2 : 0;
   k.residual = static_cast<const __nv_bfloat16*>(d->residual);
   k.upadd = static_cast<const __nv_bfloat16*>(d->upadd);
   k.y = d->y;
@@ -1115,6 +1290,33 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
       return VD_ERR_CUDA;
     }
   }
+  pl->tmB2 = pl->tmB;
+  pl->tmY2 = pl->tmY;
+  if (chain) {
+    cuuint64_t wdim2[2] = {static_cast<cuuint64_t>(d->Cout), static_cast<cuuint64_t>(d->chain_Cout)};
+    cuuint64_t wstr2[1] = {static_cast<cuuint64_t>(d->Cout) * 2};
+    cuuint32_t wbox2[2] = {64, static_cast<cuuint32_t>(d->chain_Cout)};
+    cuuint32_t one2[2] = {1, 1};
+    r = enc(&pl->tmB2, kActTmapType, 2, const_cast<void*>(d->chain_w), wdim2, wstr2, wbox2, one2,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      const cuuint64_t c2 = static_cast<cuuint64_t>(d->chain_Cout);
+      cuuint64_t ydim2[4] = {c2, static_cast<cuuint64_t>(d->Wout), static_cast<cuuint64_t>(d->Hout),
+                             static_cast<cuuint64_t>(d->B)};
+      cuuint64_t ystr2[3] = {c2 * 2, c2 * 2 * d->Wout, c2 * 2 * d->Wout * d->Hout};
+      cuuint32_t ybox2[4] = {64, static_cast<cuuint32_t>(k.TW), static_cast<cuuint32_t>(k.TH),
+                             static_cast<cuuint32_t>(k.NB)};
+      cuuint32_t one4[4] = {1, 1, 1, 1};
+      r = enc(&pl->tmY2, kActTmapType, 4, d->chain_y, ydim2, ystr2, ybox2, one4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      vd_set_error("cuTensorMapEncodeTiled(chain) failed: CUresult %d", (int)r);
+      delete pl;
+      return VD_ERR_CUDA;
+    }
+  }
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
   pl->grid = k.num_tiles < sms ? k.num_tiles : sms;
@@ -1163,13 +1365,13 @@ static const bool g_conv_pdl = [] {
   return e && atoi(e) == 1;
 }();
 
-template <int BN, bool RES, int ROWB = 128>
+template <int BN, bool RES, int ROWB = 128, bool CHAIN = false>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, RES, ROWB>;
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmemBudget));
+    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES, ROWB, CHAIN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1183,8 +1385,8 @@ static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, RES, ROWB>, pl->tmA, pl->tmB, pl->tmY, pl->tmR, pl->tmA2,
-                                   pl->kp));
+  VD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, RES, ROWB, CHAIN>, pl->tmA, pl->tmB, pl->tmY, pl->tmR,
+                                   pl->tmA2, pl->tmB2, pl->tmY2, pl->kp));
   return VD_OK;
 }
 
@@ -1194,6 +1396,8 @@ extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
   if (plan->fused) return vd_stem_pool_run(plan->fused, st);
   const bool res = (plan->kp.flags & VD_CONV_RESIDUAL) != 0;
   if (plan->kp.flags & VD_CONV_IN_X0) return launch_conv<64, false, 64>(plan, st);
+  if (plan->kp.flags & VD_CONV_CHAIN)
+    return res ? launch_conv<128, true, 128, true>(plan, st) : launch_conv<128, false, 128, true>(plan, st);
   switch (plan->BN) {
     case 32: return launch_conv<32, false>(plan, st);
     case 64: return res ? launch_conv<64, true>(plan, st) : launch_conv<64, false>(plan, st);

@@ -59,6 +59,8 @@ class Op:
     upsample_add: str = ""    # buffer (half resolution) nearest-upsampled and added AFTER ReLU (FPN top-down)
     pool: bool = False        # conv1 only: the 3x3/2 max-pool runs inside the convolution kernel, dst is the pooled tensor
     level: int = -1           # heads: pyramid level 0..2
+    chain: Optional[ConvSpec] = None   # VD_CONV_CHAIN: the NEXT 1x1 convolution, computed by the same kernel from the
+    chain_dst: str = ""                # output tile while it is still in shared memory; chain_dst is its output buffer
 
 
 @dataclass
@@ -96,13 +98,15 @@ def level_offsets(h: int, w: int) -> List[int]:
     return offs
 
 
-def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False):
+def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False, fuse_chain: bool = False):
     """Returns (convs, ops, bufs).  Buffer 'x0' is the ingested frame (3 real channels).
     With fuse_stem_pool conv1+bn1+relu+maxpool (retinaface.py:71-73) is one op writing 'p1' directly; the
     half-resolution 64-channel tensor 'c1' (4x the size of either neighbour) is never materialised.
     With fuse_downsample the projection shortcut of each stage's first bottleneck (torchvision
     Bottleneck.downsample) is not a separate convolution: its 1x1 GEMM accumulates into conv3's
-    accumulator (same output pixels), which removes one write and one read of the widest tensors."""
+    accumulator (same output pixels), which removes one write and one read of the widest tensors.
+    With fuse_chain a 256-channel conv3 also computes the 1x1 convolution that follows it (the next bottleneck's conv1,
+    64 or 128 outputs): layer1's three block outputs are written once and read back only as residuals."""
     convs: List[ConvSpec] = []
     ops: List[Op] = []
     bufs: List[BufSpec] = []
@@ -192,6 +196,20 @@ def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False):
         conv(f"{s}.conv7x7_3", f"{s}.conv7x7_3.0.weight", f"{s}.conv7x7_3.1", oc // 4, oc // 4, 3, 1, 1,
              True, t7, f_out, dst_coff=3 * oc // 4)
         ops.append(Op("heads", None, f_out, "heads", level=lvl))
+    if fuse_chain:
+        fused, i = [], 0
+        while i < len(ops):
+            op = ops[i]
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            if (op.kind == "conv" and op.conv.k == 1 and op.conv.cout == 256 and not op.upsample_add and nxt is not None
+                    and nxt.kind == "conv" and nxt.src == op.dst and nxt.conv.k == 1 and nxt.conv.stride == 1
+                    and nxt.conv.cout in (64, 128) and nxt.conv.relu and not nxt.residual and not nxt.src2
+                    and not nxt.upsample_add and nxt.dst_coff == 0 and op.conv.name.startswith("body.")):
+                op.chain, op.chain_dst = nxt.conv, nxt.dst
+                i += 1
+            fused.append(op)
+            i += 1
+        ops = fused
     return convs, ops, bufs
 
 

@@ -42,7 +42,7 @@ def _on_device(fn):
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16",
-                 fuse_stem_pool=None, backbone="resnet50"):
+                 fuse_stem_pool=None, backbone="resnet50", fuse_chain=None):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
@@ -59,6 +59,10 @@ class DetectorEngine:
         if fuse_stem_pool is None:
             fuse_stem_pool = os.environ.get("VD_STEM_POOL", "1") != "0"
         self.fuse_stem_pool = bool(fuse_stem_pool) and not self.split
+        # conv3 + the next bottleneck's conv1 as one kernel where conv3 has 256 outputs (layer1): VD_CONV_CHAIN
+        if fuse_chain is None:
+            fuse_chain = os.environ.get("VD_CHAIN", "1") != "0"
+        self.fuse_chain = bool(fuse_chain) and not self.split
         storage = "fp16" if self.split else precision
         self.act_dtype = _lib.torch_dtype(storage)
         self.lib = _lib.lib(storage)
@@ -151,7 +155,8 @@ class DetectorEngine:
 
     def _build_resnet(self, state_dict):
         dev, B, H, W = self.device, self.B, self.H, self.W
-        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool)
+        convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool,
+                                            fuse_chain=self.fuse_chain)
         packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
         P = 3 if self.split else 1            # channel planes per activation tensor
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
@@ -194,6 +199,12 @@ class DetectorEngine:
                     flags |= _lib.VD_CONV_UPADD
                     up = self.buf[op.upsample_add]
                     d.up_H, d.up_W = up.shape[1], up.shape[2]
+                if op.chain is not None:
+                    flags |= _lib.VD_CONV_CHAIN
+                    w2, b2 = self.w[op.chain.name]
+                    assert tuple(self.buf[op.chain_dst].shape) == (B, hout, wout, op.chain.cout)
+                    d.chain_w, d.chain_bias, d.chain_y = w2.data_ptr(), b2.data_ptr(), self.buf[op.chain_dst].data_ptr()
+                    d.chain_Cout = op.chain.cout
                 d.flags = flags
                 wt, bt = self.w[c.name]
                 d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()

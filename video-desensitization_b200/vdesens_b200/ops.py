@@ -62,7 +62,7 @@ def ingest_nchw_f32(frames, H, W):
 
 
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None):
+           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
     The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
@@ -108,6 +108,12 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     if slope is not None:     # per-channel negative-side slope instead of relu (0 ReLU, 0.1 LeakyReLU, 1 identity)
         flags |= _lib.VD_CONV_SLOPE
         d.slope = slope.data_ptr()
+    out2 = None
+    if chain is not None:     # (w2 [N2][Cout], bias2 [N2]): also returns relu(conv1x1(out) + bias2) from the same kernel
+        w2, b2 = chain
+        out2 = torch.empty((B, hout, wout, w2.shape[0]), dtype=x.dtype, device=x.device)
+        flags |= _lib.VD_CONV_CHAIN
+        d.chain_w, d.chain_bias, d.chain_y, d.chain_Cout = w2.data_ptr(), b2.data_ptr(), out2.data_ptr(), w2.shape[0]
     d.flags = flags
     d.x, d.w, d.bias = x.data_ptr(), w_packed.data_ptr(), bias.data_ptr()
     d.residual = residual.data_ptr() if residual is not None else None
@@ -119,7 +125,7 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
         _lib.check(lib.vd_conv_run(h, _stream()), "vd_conv_run")
     finally:
         lib.vd_conv_plan_destroy(h)
-    return out
+    return out if out2 is None else (out, out2)
 
 
 def mnet_stem(x0, w, bias, slope, H, W):
