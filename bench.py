@@ -34,10 +34,13 @@ KSIZE = 31
 N_PLATES = 4
 CONV_GFLOP_PER_FRAME = 449.71          # 82 convs at 1080p, 2*MAC
 # average dram__bytes_read.sum + dram__bytes_write.sum per convolution launch of one 16-frame step, from the ncu capture
-# summarised in profiles/r01_ncu_summary.md §2 (31.64 GB over the 72 launches of a step); algorithmic activation
-# traffic is 2.085 GB/frame unfused minus the 0.133 GB/frame of conv1's output that the fused
-# conv1+maxpool kernel keeps on chip = 1.95 GB/frame * 16 = 31.2 GB per step, i.e. no wasted re-reads
-CONV_DRAM_BYTES_PER_LAUNCH = 4.395e8
+# summarised in profiles/r01_ncu_summary.md §2 (28.54 GB over the 69 launches of a step).  Algorithmic activation
+# traffic: 2.085 GB/frame unfused - 0.133 GB/frame (conv1's output stays on chip in the fused
+# conv1+maxpool kernel) - 0.199 GB/frame (the three 256-channel layer1 outputs are not read back by the next conv1,
+# VD_CONV_CHAIN) = 1.75 GB/frame * 16 = 28.0 GB per step, i.e. no wasted re-reads.  The figure belongs to the
+# configuration it was captured on: CONV_DRAM_LAUNCHES convolution launches per step.
+CONV_DRAM_BYTES_PER_LAUNCH = 4.136e8
+CONV_DRAM_LAUNCHES = 69
 METRIC = "1080p detect+blur frames/sec"
 
 
@@ -294,10 +297,10 @@ def run_ours(args):
                 "steps": e2e_steps, "host_ms_per_batch": e2e_host, "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step (double-buffered), max over ranks"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + stem_pool_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3, maxpool fused into conv1)" % n_conv,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + stem_pool_kernel (%d launches per step: 82 convolutions, 4 projections fused into conv3, 9 heads fused to 3, maxpool fused into conv1, %d next-block conv1 chained into the preceding conv3)" % (n_conv, getattr(eng, "n_chained", 0)),
                      "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
                      "peak_source": peak_src + " bf16_tflops_sustained",
-                     "traffic": CONV_DRAM_BYTES_PER_LAUNCH if precision == "bf16" else None,
+                     "traffic": CONV_DRAM_BYTES_PER_LAUNCH if (precision == "bf16" and n_conv == CONV_DRAM_LAUNCHES) else None,
                      "traffic_note": "avg DRAM bytes per conv launch (ncu, profiles/r01_ncu_summary.md)",
                      "launches_per_step": n_conv, "avg_launch_ms": net_ms / n_conv,
                      "algorithmic_flops_per_launch": CONV_GFLOP_PER_FRAME * 1e9 * BATCH / n_conv,

@@ -175,6 +175,10 @@ int vd_mnet_dw3x3(const void* x, const void* w, const float* bias, const float* 
                   int C, int stride, vd_stream_t stream);    /* y: [B][ceil(H/stride)][ceil(W/stride)][C] */
 int vd_mnet_pw(const void* x, const void* w, const float* bias, const float* slope, void* y, long long npix, int Cin,
                int Cout, vd_stream_t stream);
+/* one whole conv_dw block (mobilenet025.py:10-19) = vd_mnet_dw3x3 followed by vd_mnet_pw in one kernel, the depthwise
+ * result staying in shared memory; (Cin, Cout) in {(8,16), (16,32), (32,32), (32,64)}; bit-identical to the two calls */
+int vd_mnet_dwpw(const void* x, const void* wdw, const float* bdw, const float* sdw, const void* wpw, const float* bpw,
+                 const float* spw, void* y, int B, int H, int W, int Cin, int Cout, int stride, vd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K3 decode + threshold + compaction                                                          */

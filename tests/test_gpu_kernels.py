@@ -883,12 +883,12 @@ def test_detector_called_from_pool_threads_like_the_reference(sd_np):
     (False, True, 64, (2, 45, 77)), (True, False, 128, (3, 33, 50)), (False, False, 128, (2, 24, 32)),
     (True, False, 64, (8, 135, 240)),
 ])
-def test_conv_chain_is_bit_identical_to_two_launches(ops, residual, dual, n2, shape):
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_conv_chain_is_bit_identical_to_two_launches(ops, residual, dual, n2, shape, dt):
     """1x1 conv (Cout 256, +residual / +projection segment, ReLU) chained with the next 1x1 conv (256 -> 64/128, ReLU):
     both outputs equal the two separate launches bit for bit (same MMA order, same rounding points)."""
     B, H, W = shape
     g = torch.Generator().manual_seed(B * H + W + n2)
-    dt = torch.bfloat16
     x = torch.randn(B, H, W, 64, generator=g).to(dt).to(DEV)
     cin = 128 if dual else 64
     w = (torch.randn(256, cin, generator=g) * 0.1).to(dt).to(DEV)

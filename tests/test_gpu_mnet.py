@@ -97,6 +97,22 @@ def test_mnet_pointwise(ops, cin, cout, dtype):
     _close_to_rounded(y.cpu().permute(0, 3, 1, 2), want, dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,stride,shape", [(8, 16, 1, (2, 23, 31)), (16, 32, 2, (2, 23, 31)), (32, 32, 1, (1, 40, 64)),
+                                                   (32, 64, 2, (3, 33, 17)), (32, 64, 2, (2, 67, 121)), (8, 16, 1, (1, 8, 32))])
+def test_mnet_fused_dwpw_is_bit_identical_to_two_kernels(ops, cin, cout, stride, shape, dtype):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin * cout + stride + H)
+    x = torch.randn(B, H, W, cin, generator=g).to(dtype).to(DEV)
+    wdw = (torch.randn(9, cin, generator=g) * 0.3).to(dtype).to(DEV)
+    bdw, sdw = torch.randn(cin, generator=g).to(DEV), torch.rand(cin, generator=g).to(DEV)
+    wpw = (torch.randn(cin, cout, generator=g) * 0.2).to(dtype).to(DEV)
+    bpw, spw = torch.randn(cout, generator=g).to(DEV), torch.rand(cout, generator=g).to(DEV)
+    want = ops.mnet_pw(ops.mnet_dw3x3(x, wdw, bdw, sdw, stride), wpw, bpw, spw)
+    got = ops.mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride)
+    assert got.shape == want.shape and torch.equal(got, want), float((got.float() - want.float()).abs().max())
+
+
 def test_mnet_kernel_argument_errors(ops):
     x = torch.zeros((1, 4, 4, 12), dtype=torch.bfloat16, device=DEV)
     w = torch.zeros((9, 12), dtype=torch.bfloat16, device=DEV)
@@ -131,10 +147,10 @@ def test_conv_slope_epilogue(ops, k, cin, cout, hw):
     assert bool(neg.any()) and float((got - want).abs()[neg].max()) <= 0.02 * float(want.abs().max())
 
 
-def _engine(sd_np, frames, H, W, precision="bf16"):
+def _engine(sd_np, frames, H, W, precision="bf16", fuse_dwpw=True):
     from vdesens_b200.engine import DetectorEngine
     eng = DetectorEngine(sd_np, len(frames), H, W, device=DEV, confidence=0.5, nms_iou=0.4, precision=precision,
-                         backbone="mobilenet")
+                         backbone="mobilenet", fuse_dwpw=fuse_dwpw)
     eng.set_frames([torch.from_numpy(f).to(DEV) for f in frames])
     eng.forward()
     return eng
@@ -152,8 +168,14 @@ def test_mnet_network_vs_emulated_op_list(gold, sd_np, case, precision, dtype):
     re-normalising depthwise stages of this untrained network like any other storage noise (bounds stated below)."""
     frames = _frames(gold, case)
     H, W = (int(v) for v in gold[case + ".input_shape"][:2])
-    eng = _engine(sd_np, frames, H, W, precision)
+    eng = _engine(sd_np, frames, H, W, precision, fuse_dwpw=False)       # layer-by-layer form: every tensor exists
     loc, cls, ldm = (t.cpu() for t in eng.head_tensors())
+    # the engine's default form (conv_dw blocks with Cin <= 32 as one kernel) gives the same bits
+    engf = _engine(sd_np, frames, H, W, precision)
+    assert sum(1 for k, _, _ in engf.plans if k == "dwpw") == 4 and "body.stage1.1.dw" not in engf.buf
+    for a, b in zip(engf.head_tensors(), eng.head_tensors()):
+        assert torch.equal(a, b)
+    assert torch.equal(engf.buf["body.stage1.4.pw"], eng.buf["body.stage1.4.pw"])
     x, _ = ro.preprocess(frames, (H, W))
     cap = {}
     eloc, ecls, eldm = ro.forward_mnet_emulated(weights.pack_mnet(sd_np, dtype), x, capture=cap, dtype=dtype)

@@ -22,7 +22,7 @@ frames = torch.stack([torch.from_numpy(synth.synthetic_frame(H, W, 1000 + i)) fo
 eng.set_frames(frames)
 eng.forward()
 eng.stream.synchronize()
-ops, _ = arch_mnet.build_graph()
+ops, _ = arch_mnet.build_graph(fuse_dwpw=eng.fuse_dwpw)
 byname = {op.name: op for op in ops}
 
 

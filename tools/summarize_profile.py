@@ -98,7 +98,9 @@ if os.path.exists(rep):
         for n, b in enumerate(body):
             f.write(f'{n},"{short(b[kn])}",' + ",".join(f"{b[i]} {units[i]}" for i in idx) + "\n")
     out.append(f"## 3. `ncu --set full --import-source on` on {len(body)} consecutive convolution launches\n")
-    out.append(f"Key metrics per launch: `profiles/{tag}_conv_igemm_ncu_full_key_metrics.csv` (the .ncu-rep itself is not committed).\n")
+    out.append(f"Key metrics per launch: `profiles/{tag}_conv_igemm_ncu_full_key_metrics.csv` (the .ncu-rep itself is not committed).  "
+               "This capture was started with the launch offset of the 72-launch graph (`-s 216`), i.e. it begins at convolution "
+               "launch 9 of the first timed step (layer2.0.conv3), not at launch 0; section 2 above is aligned to the step.\n")
 
 md = os.path.join(P, f"{tag}_ncu_summary.md")
 keep = ""

@@ -12,6 +12,8 @@ How the ops map onto kernels (vdesens_b200/engine.py executes this list):
   "stem"  3x3/2 3->8 on the ingest layout              -> vd_mnet_stem         (CUDA cores, HBM-bound)
   "dw"    depthwise 3x3 (+BN+leaky)                    -> vd_mnet_dw3x3        (CUDA cores, HBM-bound)
   "pw"    pointwise 1x1 with Cin < 64                  -> vd_mnet_pw           (CUDA cores, HBM-bound)
+  "dwpw"  a whole conv_dw block with Cin <= 32         -> vd_mnet_dwpw         (dw result stays in shared memory;
+          build_graph(fuse_dwpw=True), what the engine runs; bit-identical to "dw" + "pw")
   "conv"  everything with Cin % 64 == 0                -> conv_igemm_kernel    (tcgen05), activation by a per-channel
           negative-side slope vector (VD_CONV_SLOPE: 0 = ReLU, 0.1 = LeakyReLU, 1 = identity)
   "heads" fused N = 32 1x1 GEMM over TWO inputs (VD_CONV_DUAL)
@@ -56,7 +58,7 @@ DW_BLOCKS = [
 
 @dataclass
 class MOp:
-    kind: str                 # "stem" | "dw" | "pw" | "conv" | "heads"
+    kind: str                 # "stem" | "dw" | "pw" | "dwpw" | "conv" | "heads"
     name: str                 # key into weights.pack_mnet()
     src: str
     dst: str
@@ -107,8 +109,12 @@ def state_dict_spec():
     return spec
 
 
-def build_graph():
-    """Returns (ops, bufs).  Buffer 'x0' is the ingested frame."""
+DWPW_PAIRS = ((8, 16), (16, 32), (32, 32), (32, 64))     # (cin, cout) instantiated by vd_mnet_dwpw
+
+
+def build_graph(fuse_dwpw: bool = False):
+    """Returns (ops, bufs).  Buffer 'x0' is the ingested frame.  fuse_dwpw: conv_dw blocks with (cin, cout) in
+    DWPW_PAIRS become one "dwpw" op (weights <block>.dw and <block>.pw) and their depthwise buffer disappears."""
     ops: List[MOp] = []
     bufs: List[BufSpec] = [BufSpec("x0", 3, 1)]
 
@@ -121,6 +127,13 @@ def build_graph():
     feats = {}
     for st, i, cin, cout, s in DW_BLOCKS:
         p = f"body.{st}.{i}"
+        if fuse_dwpw and (cin, cout) in DWPW_PAIRS:
+            cur_stride *= s
+            o = buf(p + ".pw", cout, cur_stride)
+            ops.append(MOp("dwpw", p, cur, o, cin, cout, 3, s, 1))
+            cur = o
+            feats[st] = cur
+            continue
         d = buf(p + ".dw", cin, cur_stride * s)
         ops.append(MOp("dw", p + ".dw", cur, d, cin, cin, 3, s, 1))
         cur_stride *= s

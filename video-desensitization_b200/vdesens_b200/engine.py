@@ -42,7 +42,7 @@ def _on_device(fn):
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16",
-                 fuse_stem_pool=None, backbone="resnet50", fuse_chain=None):
+                 fuse_stem_pool=None, backbone="resnet50", fuse_chain=None, fuse_dwpw=True):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
@@ -63,6 +63,7 @@ class DetectorEngine:
         if fuse_chain is None:
             fuse_chain = os.environ.get("VD_CHAIN", "1") != "0"
         self.fuse_chain = bool(fuse_chain) and not self.split
+        self.fuse_dwpw = bool(fuse_dwpw)      # mobilenet: conv_dw blocks with Cin <= 32 as one kernel (vd_mnet_dwpw)
         storage = "fp16" if self.split else precision
         self.act_dtype = _lib.torch_dtype(storage)
         self.lib = _lib.lib(storage)
@@ -116,12 +117,12 @@ class DetectorEngine:
         nets/layers.py with LeakyReLU(0.1), retinaface.py:60-73)."""
         from . import arch_mnet
         dev, B = self.device, self.B
-        ops, bufs = arch_mnet.build_graph()
+        ops, bufs = arch_mnet.build_graph(fuse_dwpw=self.fuse_dwpw)
         packed = weights.pack_mnet(state_dict, self.act_dtype)
         self.w = {k: tuple(t.to(dev) for t in v) for k, v in packed.items()}
         self._alloc_buffers(bufs)
         for op in ops:
-            if op.kind in ("stem", "dw", "pw"):
+            if op.kind in ("stem", "dw", "pw", "dwpw"):
                 self.plans.append((op.kind, op, op.name))
                 continue
             wt, bt, st = self.w[op.name]
@@ -161,6 +162,7 @@ class DetectorEngine:
         P = 3 if self.split else 1            # channel planes per activation tensor
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
         self._alloc_buffers(bufs, P)
+        self.n_chained = sum(1 for op in ops if op.kind == "conv" and op.chain is not None)
 
         for op in ops:
             if op.kind == "conv":
@@ -351,6 +353,14 @@ class DetectorEngine:
         for kind, h, name in self.plans:
             if kind == "conv":
                 _lib.check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
+            elif kind == "dwpw":
+                op = h
+                wd, bd, sd = self.w[op.name + ".dw"]
+                wp, bp, sp = self.w[op.name + ".pw"]
+                hh, ww, cc = self.buf_hw[op.src]
+                _lib.check(self.lib.vd_mnet_dwpw(_ptr(self.buf[op.src]), _ptr(wd), _ptr(bd), _ptr(sd), _ptr(wp), _ptr(bp),
+                                                 _ptr(sp), _ptr(self.buf[op.dst]), self.B, hh, ww, op.cin, op.cout,
+                                                 op.stride, s), f"vd_mnet_dwpw({name})")
             elif kind in ("stem", "dw", "pw"):
                 op = h
                 wt, bt, st = self.w[op.name]

@@ -145,6 +145,17 @@ def mnet_dw3x3(x, w, bias, slope, stride):
     return y
 
 
+def mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride):
+    """conv_dw block (depthwise 3x3 + pointwise 1x1, reference mobilenet025.py:10-19) as one kernel."""
+    lib = _lib.lib(_lib.precision_of(x.dtype))
+    B, H, W, Cin = x.shape
+    Cout = wpw.shape[1]
+    y = torch.empty((B, (H + stride - 1) // stride, (W + stride - 1) // stride, Cout), dtype=x.dtype, device=x.device)
+    _lib.check(lib.vd_mnet_dwpw(_p(x), _p(wdw), _p(bdw), _p(sdw), _p(wpw), _p(bpw), _p(spw), _p(y), B, H, W, Cin, Cout,
+                                stride, _stream()), "vd_mnet_dwpw")
+    return y
+
+
 def mnet_pw(x, w, bias, slope):
     """pointwise 1x1 for Cin < 64 (reference mobilenet025.py:16-18); w is [Cin][Cout]."""
     lib = _lib.lib(_lib.precision_of(x.dtype))
