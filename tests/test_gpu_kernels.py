@@ -915,6 +915,14 @@ def test_chain_engine_matches_unfused_engine(sd_np):
     for fuse in (False, True):
         eng = DetectorEngine(sd_np, len(frames), 135, 241, device=DEV, confidence=0.5, nms_iou=0.4, fuse_chain=fuse)
         assert sum(1 for k, _, _ in eng.plans if k == "conv") == (69 if fuse else 72) - (0 if eng.fuse_stem_pool else 0)
+        if fuse:
+            # a chained plan hands whole M tiles (= 2 N tiles) to a CTA: never more CTAs than M tiles, so no CTA retires
+            # with its W2 copy still in flight (135x241 frames: 34x61 pixels in layer1, fewer M tiles than SMs)
+            info = {p[0]: p for p in eng.plan_info()}
+            for name in ("body.layer1.0.conv3", "body.layer1.1.conv3", "body.layer1.2.conv3"):
+                _, tw, th, nb, bn, tiles, grid = info[name]
+                assert bn == 128 and tiles % 2 == 0 and grid <= tiles // 2, (name, tiles, grid)
+            assert eng.n_chained == 3
         eng.set_frames(_dev_frames(frames))
         eng.forward()
         rows, counts = eng.fetch_results()

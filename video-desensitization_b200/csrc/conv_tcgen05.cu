@@ -361,6 +361,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int aslot = 0;
     uint32_t aphase = 0;
     if (p.wres) mbar_wait(wfull, 0);
+    if (CHAIN) mbar_wait(w2full, 0);      // also keeps a CTA without tiles alive until its W2 copy has landed
     // CHAIN: K blocks of the chained GEMM, one per staged 64-channel output chunk, issued one iteration behind the
     // main MMAs (the epilogue of iteration it-1 stages them while the MMAs of iteration `it` already run)
     int acc1 = 0;
@@ -375,10 +376,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = it_prev & 1;
       for (int c = 0; c < CPT; ++c, ++ychunk) {
         const int g = n * CPT + c;                       // K block of the chained GEMM
-        if (g == 0) {
-          if (ychunk == 0) mbar_wait(w2full, 0);
-          mbar_wait(&t1empty[acc1], acc1_phase ^ 1u);
-        }
+        if (g == 0) mbar_wait(&t1empty[acc1], acc1_phase ^ 1u);
         const uint32_t buf = ychunk & 1u;
         mbar_wait(&ystaged[buf], (ychunk >> 1) & 1u);
         tcgen05_fence_after();
@@ -963,6 +961,11 @@ static bool plan_occ(vd_conv_plan* pl, int sms) {
   const bool kTwo = (BN <= 128 && !RES) && !(pl->kp.flags & VD_CONV_CHAIN);
   const char* env = getenv("VD_CONV_OCC");
   const int want = env ? atoi(env) : 2;
+  if (pl->kp.flags & VD_CONV_CHAIN) {        // a CTA walks whole M tiles (tile_at<true>): one CTA per M tile at most
+    const int m_tiles = pl->kp.num_tiles / pl->kp.n_tiles;
+    pl->grid = m_tiles < sms ? m_tiles : sms;
+    return plan_smem<BN, RES, ROWB>(pl, 1, 2);
+  }
   if (pl->kp.patch) {                       // narrow 3x3: one CTA per SM with the filter bank resident, if it fits
     pl->grid = pl->kp.num_tiles < sms ? pl->kp.num_tiles : sms;
     if (plan_smem<BN, RES, ROWB>(pl, 1, 2) && pl->kp.wres) return true;
