@@ -203,6 +203,8 @@ def run_ours(args):
     def step(i, ev=None):
         with torch.cuda.stream(st):
             work.copy_(pristine[i % NB], non_blocking=True)      # the reference's img.copy() (combine_detect.py:247)
+            if ev is not None:
+                ev[4].record(st)
             eng.enqueue_ingest()
             if ev is not None:
                 ev[0].record(st)
@@ -232,7 +234,7 @@ def run_ours(args):
     barrier()
     tw0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seg = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    seg = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     e0.record(st)
     for i in range(args.steps):
         step(i, seg[i])
@@ -245,6 +247,31 @@ def run_ours(args):
     net_ms = sum(s[0].elapsed_time(s[1]) for s in seg) / args.steps
     post_ms = sum(s[1].elapsed_time(s[2]) for s in seg) / args.steps
     comp_ms = sum(s[2].elapsed_time(s[3]) for s in seg) / args.steps
+    ingest_ms = sum(s[4].elapsed_time(s[0]) for s in seg) / args.steps
+    copy_ms = ms_total / args.steps - net_ms - post_ms - comp_ms - ingest_ms
+    # algorithmic bytes of the streaming stages: each ROI pixel read once and written once for the blur;
+    # u8 frame in + 4-channel bf16 x0 out for the ingest; the fp32 head rows (16 values per anchor) for the decode
+    roi_bytes = 0                            # boxes of the last timed step (its detections + the fixed plate boxes)
+    for f in range(BATCH):
+        bx = [[float(v) for v in r[:4] * np.array([W, H, W, H], np.float32)] for r in rows[f, :int(counts[f])]]
+        for (x1, y1, x2, y2) in [tuple(int(v) for v in b) for b in bx] + list(plates[0][f]):
+            x1, y1, x2, y2 = max(0, x1), max(0, y1), min(W, x2), min(H, y2)
+            if x2 > x1 and y2 > y1:
+                roi_bytes += 6 * (x2 - x1) * (y2 - y1)
+    n_anchor = 2 * sum(-(-H // s) * -(-W // s) for s in (8, 16, 32))
+    x0_pitch = int(eng.buf["x0"].shape[2])
+
+    def hbm_stage(nbytes, ms, note):
+        gbs = nbytes / ms / 1e6
+        return {"bytes": int(nbytes), "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "note": note}
+
+    stage_hbm = {
+        "frame_copy": hbm_stage(2 * BATCH * H * W * 3, copy_ms, "device copy of the batch (the reference's img.copy()), torch copy kernel"),
+        "ingest": hbm_stage(BATCH * (3 * H * W + 8 * H * x0_pitch), ingest_ms, "u8 HWC read + 4-channel bf16 x0 written"),
+        "decode_threshold_nms": hbm_stage(BATCH * n_anchor * 16 * 4, post_ms,
+                                          "fp32 head rows read once; the NMS part is compare-bound (no bandwidth roofline)"),
+        "composite": hbm_stage(roi_bytes, comp_ms, "2*3*w*h per clipped box; sequential box chains make this stage latency-bound"),
+    }
 
     # ---- e2e: public API, host buffers, copies inside the timed region ----
     # StreamingAnonymizer.run() is the call a user makes for a stream of batches: every step copies its
@@ -306,7 +333,8 @@ def run_ours(args):
                      "algorithmic_flops_per_launch": CONV_GFLOP_PER_FRAME * 1e9 * BATCH / n_conv,
                      "algorithmic_flops_per_step": CONV_GFLOP_PER_FRAME * 1e9 * BATCH, "segment_ms": net_ms},
         "segments_ms": {"network": net_ms, "decode_nms": post_ms, "composite": comp_ms,
-                        "copy_ingest": ms_total / args.steps - net_ms - post_ms - comp_ms},
+                        "ingest": ingest_ms, "frame_copy": copy_ms},
+        "stage_hbm": stage_hbm, "hbm_peak_gbs": hbm_peak,
         "faces_per_frame": float(np.mean(counts)),
     }
     if world == 1:

@@ -646,6 +646,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                             static_cast<uint32_t>(acc * BN + ch * 64 + half * 32), v);
         }
+        // FPN top-down term (nearest-upsampled coarser level): the four 16-byte loads are issued here, behind the
+        // TMEM load, so that their L2 latency overlaps the accumulator read instead of following it
+        uint4 upv[4];
+        // (only in the BN = 256 one-CTA-per-SM variant the FPN laterals use: the 96-register two-CTA variants would spill)
+        constexpr bool UP_EARLY = (BN == 256) && !RES && !CHAIN;
+        const bool up_early = UP_EARLY && (p.flags & VD_CONV_UPADD) && !split && active && valid;
+        if (up_early) {
+          const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * up_C + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) upv[j] = __ldg(up + j);
+        }
         uint4 rcur[4], rlo[4];
         if (RES) {
           // residual chunk staged by the residual-producer warp (SWIZZLE_128B tile, same geometry as the output);
@@ -713,7 +724,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if ((p.flags & VD_CONV_UPADD) && valid) {
+          if (up_early) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = upv[j];
+              f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
+              f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
+              f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
+              f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+            }
+          } else if ((p.flags & VD_CONV_UPADD) && valid) {
             for (int pl = 0; pl < (split ? 2 : 1); ++pl) {
               const uint4* up = reinterpret_cast<const uint4*>(p.upadd + up_pix * up_C + pl * p.Cout + n0);
 #pragma unroll

@@ -88,43 +88,48 @@ ingest_x0_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__ x0, 
 }
 
 // fast path: frame size == network input (BASELINE configs 2-5): no resize, no pad.
-// Each thread converts 4 pixels: 12 B in (3 x u32), 32 B out (4 x uint2).
-__global__ void __launch_bounds__(256)
-ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__ x0, int H, int W, int Wp,
+// One thread = one 16-byte store = two x0 columns (2j, 2j+1), i.e. pixels 2j-3 and 2j-2: every store instruction of a
+// warp writes 512 contiguous bytes (whole 32-byte sectors; the first version's 8-byte stores at a 32-byte lane stride
+// wrote a quarter of a sector per instruction and reached 41 % of the HBM peak).  The six source bytes of a pair are
+// fetched with byte loads — any frame pitch / alignment works, a warp's loads cover 192 contiguous bytes and hit L1
+// after the first touch — and all loads of the PAIRS pairs a thread owns are issued before the first conversion.
+// The pad columns (0..2 and W+3..Wp-1) are written as zero, so the kernel does not depend on a pre-zeroed tensor.
+constexpr int ID_THREADS = 256;
+constexpr int ID_PAIRS = 4;            // pairs per thread per row: 4 * 256 * 2 = 2048 columns per block pass
+
+__global__ void __launch_bounds__(ID_THREADS)
+ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp,
                           float m0, float m1, float m2) {
   const int b = blockIdx.z;
   const int y = blockIdx.y;
   const vd_frame_t fr = frames[b];
-  const uint8_t* src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
-  uint2* row = x0 + (static_cast<size_t>(b) * H + y) * Wp + 3;
-  const int groups = W >> 2;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
-  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
-    uint8_t px[12];
-    if (aligned) {
-      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src) + gi * 3;
-      const uint32_t a = __ldg(s32), bb = __ldg(s32 + 1), c = __ldg(s32 + 2);
-      *reinterpret_cast<uint32_t*>(px) = a;
-      *reinterpret_cast<uint32_t*>(px + 4) = bb;
-      *reinterpret_cast<uint32_t*>(px + 8) = c;
-    } else {
-      for (int i = 0; i < 12; ++i) px[i] = src[gi * 12 + i];
+  const uint8_t* __restrict__ src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
+  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * (Wp >> 1);
+  const int npairs = Wp >> 1;
+  for (int j0 = blockIdx.x * (ID_THREADS * ID_PAIRS); j0 < npairs; j0 += gridDim.x * (ID_THREADS * ID_PAIRS)) {
+    uint32_t px[ID_PAIRS][6];
+#pragma unroll
+    for (int p = 0; p < ID_PAIRS; ++p) {
+      const int j = j0 + p * ID_THREADS + threadIdx.x;
+      const int xa = 2 * j - 3;                      // pixel of column 2j; xa + 1 is the pixel of column 2j + 1
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int x = xa + (i >= 3);
+        px[p][i] = (j < npairs && x >= 0 && x < W) ? __ldg(src + 3 * x + (i % 3)) : 0xFFFFFFFFu;   // marker: pad column
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint2 o;
-      o.x = pack_bf16x2(static_cast<float>(px[3 * i]) - m0, static_cast<float>(px[3 * i + 1]) - m1);
-      o.y = pack_bf16x2(static_cast<float>(px[3 * i + 2]) - m2, 0.f);
-      row[gi * 4 + i] = o;
+    for (int p = 0; p < ID_PAIRS; ++p) {
+      const int j = j0 + p * ID_THREADS + threadIdx.x;
+      if (j >= npairs) continue;
+      uint4 o;
+      const bool va = px[p][0] != 0xFFFFFFFFu, vb = px[p][3] != 0xFFFFFFFFu;
+      o.x = va ? pack_bf16x2(static_cast<float>(px[p][0]) - m0, static_cast<float>(px[p][1]) - m1) : 0u;
+      o.y = va ? pack_bf16x2(static_cast<float>(px[p][2]) - m2, 0.f) : 0u;
+      o.z = vb ? pack_bf16x2(static_cast<float>(px[p][3]) - m0, static_cast<float>(px[p][4]) - m1) : 0u;
+      o.w = vb ? pack_bf16x2(static_cast<float>(px[p][5]) - m2, 0.f) : 0u;
+      row[j] = o;
     }
-  }
-  // tail pixels (W % 4)
-  if (blockIdx.x == 0 && threadIdx.x < (W & 3)) {
-    const int x = (groups << 2) + threadIdx.x;
-    uint2 o;
-    o.x = pack_bf16x2(static_cast<float>(src[x * 3]) - m0, static_cast<float>(src[x * 3 + 1]) - m1);
-    o.y = pack_bf16x2(static_cast<float>(src[x * 3 + 2]) - m2, 0.f);
-    row[x] = o;
   }
 }
 
@@ -167,9 +172,9 @@ extern "C" int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x
   VD_REQUIRE(frames && x0 && mean, "vd_ingest_u8hwc_identity: null argument");
   VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc_identity: bad extent");
   const int Wp = vd_x0_pitch(W);
-  dim3 grid(vd_cdiv(vd_cdiv(W, 4), 256), H, B);
-  ingest_x0_identity_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, static_cast<uint2*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
+  dim3 grid(vd_cdiv(Wp / 2, ID_THREADS * ID_PAIRS), H, B);     // 1080p: one block per row (968 pairs)
+  ingest_x0_identity_kernel<<<grid, ID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
