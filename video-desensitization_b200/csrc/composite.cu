@@ -29,6 +29,9 @@
 
 namespace {
 
+#ifndef VD_COMP_MINB
+#define VD_COMP_MINB 4            // resident CTAs per SM the run kernel is compiled for (64 registers; A/B on B200: 3 -> 0.676 ms, 4 -> 0.645, 5 -> 0.632 on the bench boxes, single-frame chains 0.046 / 0.055 / 0.058)
+#endif
 constexpr int kThreads = 256;
 constexpr int MA_PIX = 256;               // mosaic phase A: small pixels per tile
 constexpr int MB_W = 64, MB_H = 16;       // mosaic phase B tile
@@ -334,7 +337,7 @@ __device__ __forceinline__ void fused_passes(const uint8_t* __restrict__ src, ui
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, VD_COMP_MINB)
 composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int mode, int ksize, Taps taps,
                      uint32_t* __restrict__ status, Ws ws) {
   extern __shared__ __align__(16) uint8_t dsm[];
@@ -795,7 +798,8 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   int per_sm = 4;
   if (smem > 0) {
     const int fit = static_cast<int>((220 * 1024) / (smem + 2048));
-    per_sm = fit < 1 ? 1 : (fit > 4 ? 4 : fit);
+    const int cap = VD_COMP_MINB > 4 ? VD_COMP_MINB : 4;
+    per_sm = fit < 1 ? 1 : (fit > cap ? cap : fit);
   }
   composite_run_kernel<<<sms * per_sm, kThreads, smem, st>>>(frames, B, maxb, mode, ksize, taps, status, ws);
   VD_LAUNCH_CHECK();

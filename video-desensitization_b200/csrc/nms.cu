@@ -124,11 +124,16 @@ nms_mask_kernel(const int* __restrict__ cand_count, int cap, float thr, NmsWs ws
   }
 }
 
+// Greedy pass over the suppression bitmask, one warp per frame.  Everything with a global-memory round trip is issued
+// lane-parallel so the warp pays ONE latency per 64-candidate block instead of one per kept box: (1) the block's 64
+// diagonal words, (2) the propagation of the kept rows into the following column words (lanes own kept ROWS and OR
+// their words into shared memory — the first version walked the kept rows serially per lane), (3) the output rows,
+// which are only listed here and written after the loop, two rows per step with independent loads.
 __global__ void __launch_bounds__(32)
 nms_reduce_kernel(const float* __restrict__ cand, const int* __restrict__ cand_count, int cap,
                   const float* __restrict__ unlb, int max_det, float* __restrict__ out_rows,
                   int* __restrict__ out_count, uint32_t* __restrict__ status, NmsWs ws) {
-  extern __shared__ unsigned long long remv[];      // cap/64 words, then 64 diagonal words, then kept word
+  extern __shared__ unsigned long long remv[];      // cap/64 words, 64 diagonal words, kept word, kept list
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
   const int n = min(cand_count[b], cap);
@@ -136,6 +141,7 @@ nms_reduce_kernel(const float* __restrict__ cand, const int* __restrict__ cand_c
   const int words = cap >> 6;
   unsigned long long* diag = remv + words;
   unsigned long long* keptw = diag + 64;
+  int* klist = reinterpret_cast<int*>(keptw + 1);   // sorted positions of the kept boxes, first min(max_det, cap)
   const unsigned long long* mask = ws.mask + static_cast<size_t>(b) * cap * words;
   const int* sslot = ws.sslot + static_cast<size_t>(b) * cap;
   const float* cb = cand + static_cast<size_t>(b) * cap * 16;
@@ -162,38 +168,46 @@ nms_reduce_kernel(const float* __restrict__ cand, const int* __restrict__ cand_c
     }
     __syncwarp();
     const unsigned long long kept = *keptw;
-    // propagate kept rows to the following column blocks (lanes stride over words)
-    for (int w = blk + 1 + lane; w < nb; w += 32) {
-      unsigned long long acc = remv[w];
-      unsigned long long kk = kept;
-      while (kk) {
-        const int t = __ffsll(static_cast<long long>(kk)) - 1;
-        kk &= kk - 1;
-        acc |= mask[static_cast<size_t>(base + t) * words + w];
-      }
-      remv[w] = acc;
-    }
-    // emit kept rows in order: lanes 0..15 copy one row each step
-    unsigned long long kk = kept;
-    while (kk) {
-      const int t = __ffsll(static_cast<long long>(kk)) - 1;
-      kk &= kk - 1;
-      if (nkept < max_det) {
-        if (lane < 16) {
-          const int slot = sslot[base + t];
-          float v = cb[slot * 16 + lane];
-          if (lane != 4 && lane != 15) {
-            // utils_bbox.py:39-40: (coord - offset) * scale, x for even coordinate slots, y for odd
-            const int c = (lane < 4) ? lane : (lane - 5);
-            const bool is_x = (c & 1) == 0;
-            v = __fmul_rn(__fsub_rn(v, is_x ? offx : offy), is_x ? scx : scy);
+    // propagate: lane owns rows t = lane, lane + 32 of the block; its loads over w are independent
+    if (blk + 1 < nb) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        if ((kept >> t) & 1ull) {
+          const unsigned long long* mrow = mask + static_cast<size_t>(base + t) * words;
+          for (int w = blk + 1; w < nb; ++w) {
+            const unsigned long long m = mrow[w];
+            if (m) atomicOr(&remv[w], m);
           }
-          orow[static_cast<size_t>(nkept) * 16 + lane] = v;
         }
       }
-      ++nkept;
     }
+    // list the kept boxes in order (rank of bit t among the kept bits)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = lane + 32 * h;
+      if ((kept >> t) & 1ull) {
+        const int pos = nkept + __popcll(kept & ((1ull << t) - 1ull));
+        if (pos < max_det) klist[pos] = base + t;
+      }
+    }
+    nkept += __popcll(kept);
     __syncwarp();
+  }
+  // emit: half a warp per row, rows in kept order
+  const int nout = min(nkept, max_det);
+  const int col = lane & 15;
+#pragma unroll 4
+  for (int i = lane >> 4; i < nout; i += 2) {
+    const int slot = sslot[klist[i]];
+    float v = cb[slot * 16 + col];
+    if (col != 4 && col != 15) {
+      // utils_bbox.py:39-40: (coord - offset) * scale, x for even coordinate slots, y for odd
+      const int c = (col < 4) ? col : (col - 5);
+      const bool is_x = (c & 1) == 0;
+      v = __fmul_rn(__fsub_rn(v, is_x ? offx : offy), is_x ? scx : scy);
+    }
+    orow[static_cast<size_t>(i) * 16 + col] = v;
   }
   if (lane == 0) {
     if (nkept > max_det) {
@@ -237,7 +251,7 @@ extern "C" int vd_nms_batched(const float* cand, const int32_t* cand_count, int 
   dim3 mgrid(64, B);
   nms_mask_kernel<<<mgrid, 64, 0, st>>>(cand_count, cap, iou_thr, ws);
   VD_LAUNCH_CHECK();
-  const size_t red_smem = sizeof(unsigned long long) * (cap / 64 + 64 + 1);
+  const size_t red_smem = sizeof(unsigned long long) * (cap / 64 + 64 + 1) + sizeof(int) * static_cast<size_t>(max_det < cap ? max_det : cap);
   nms_reduce_kernel<<<B, 32, red_smem, st>>>(cand, cand_count, cap, unletterbox, max_det, out_rows, out_count, status,
                                              ws);
   VD_LAUNCH_CHECK();
