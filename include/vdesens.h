@@ -115,6 +115,10 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
                                   by the next bottleneck's conv1, reference torchvision resnet50 Bottleneck.forward): the
                                   wide tensor is written once and not read back.  Needs R = S = 1, Cout = 256,
                                   chain_Cout in {64, 128}; results are bit-identical to the two separate launches */
+#define VD_CONV_REVERSE 1024u   /* scheduling hint, no effect on results: the persistent CTAs walk the output tiles from the
+                                  last to the first.  A layer that reads what its predecessor has JUST written finds the
+                                  tail of that tensor still in the 126 MB L2 if it starts there; the executor alternates
+                                  the direction along the layer chain.  Ignored with VD_CONV_CHAIN / VD_CONV_POOL */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 

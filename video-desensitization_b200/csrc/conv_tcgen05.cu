@@ -53,6 +53,7 @@ struct ConvKParams {
   int stages;             // operand pipeline depth (<= kMaxStages), chosen on the host from the smem budget
   int wres;               // 1: the whole weight matrix of the (single) N tile stays resident in shared memory
   int w_bytes;            // wres: KB * BN * 128
+  int reverse;            // VD_CONV_REVERSE: tiles are visited from the last to the first
   uint32_t flags;
   const float* bias;
   const float* slope;     // VD_CONV_SLOPE: per-channel negative-side factor
@@ -132,7 +133,8 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) 
 template <bool CHAIN>
 __device__ __forceinline__ int tile_at(const ConvKParams& p, int it) {
   if (CHAIN) return (static_cast<int>(blockIdx.x) + (it >> 1) * static_cast<int>(gridDim.x)) * 2 + (it & 1);
-  return static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+  const int idx = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+  return (p.reverse && idx < p.num_tiles) ? p.num_tiles - 1 - idx : idx;
 }
 
 // CHAIN (VD_CONV_CHAIN, BN = 128, Cout = 256): the kernel also computes the NEXT layer, a 1x1 convolution
@@ -246,7 +248,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aphase = 0;
     if (p.wres && elect_one()) {                      // weights: loaded once, reused by every tile
       mbar_expect_tx(wfull, static_cast<uint32_t>(p.w_bytes));
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * (ROWB / 2), 0);
+      // several N tiles: the grid is a multiple of n_tiles (plan_smem), so this CTA only ever sees one of them
+      // (num_tiles = m_tiles * n_tiles, so this also holds for the reversed walk)
+      const int t0 = tile_at<CHAIN>(p, 0);
+      const int wrow = (p.n_tiles > 1 && t0 < p.num_tiles) ? tile_coord(p, t0).n_tile * BN : 0;
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, wfull, kb * (ROWB / 2), wrow);
     }
     if (CHAIN && elect_one()) {                       // chained convolution's weights: [N2][Cout], one box per K block
       mbar_expect_tx(w2full, static_cast<uint32_t>(p.w2_bytes));
@@ -955,6 +961,17 @@ static bool plan_smem(vd_conv_plan* pl, int occ, int min_stages) {
   const int w_bytes = KB * Cfg::B_BYTES;
   k.wres = (k.n_tiles == 1 && w_bytes <= kWresMaxBytes && w_bytes * 2 <= avail && k.num_tiles > pl->grid &&
             BN <= 64 && KB >= 4) ? 1 : 0;
+  // Short-K expansions with several 256-wide N tiles (bottleneck conv3 of layer2: K = 128, 64 KB per N tile): streamed,
+  // the weights are 64 KB of L2 -> SM traffic per tile next to 32 KB of activations.  With a grid that is a multiple of
+  // n_tiles, tile = blockIdx.x + it * gridDim.x keeps n_tile = blockIdx.x % n_tiles fixed per CTA, so its slice of the
+  // weights can stay resident.
+  {
+    const char* we = getenv("VD_CONV_WRES_NT");
+    const int want = we ? atoi(we) : 1;
+    if (want && !k.wres && BN == 256 && k.n_tiles > 1 && pl->grid % k.n_tiles == 0 && !(k.flags & VD_CONV_CHAIN) &&
+        w_bytes <= 64 * 1024 && (avail - w_bytes) / Cfg::A_BYTES >= 4 && k.num_tiles > pl->grid)
+      k.wres = 1;
+  }
   k.w_bytes = k.wres ? w_bytes : 0;
   // K blocks per stage: narrow N tiles finish a 64-deep block in 128 (BN=64) / 256 (BN=128) clk, far less
   // than one barrier round trip of the issuing warp
@@ -1183,6 +1200,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.dst_C = d->dst_C; k.dst_coff = d->dst_coff;
   k.up_H = d->up_H; k.up_W = d->up_W;
   k.flags = d->flags;
+  k.reverse = ((d->flags & VD_CONV_REVERSE) && !chain) ? 1 : 0;
   k.bias = d->bias;
   k.slope = d->slope;
   k.bias2 = d->chain_bias;

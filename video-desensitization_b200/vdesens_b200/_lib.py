@@ -10,6 +10,7 @@ LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libvdesens_fp16.so")
 
 VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32 = 1, 2, 4, 8
 VD_CONV_IN_X0, VD_CONV_DUAL, VD_CONV_SPLIT, VD_CONV_POOL, VD_CONV_SLOPE, VD_CONV_CHAIN = 16, 32, 64, 128, 256, 512
+VD_CONV_REVERSE = 1024
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
 VD_NMS_MAX_CAND = 8192

@@ -164,10 +164,20 @@ class DetectorEngine:
         self._alloc_buffers(bufs, P)
         self.n_chained = sum(1 for op in ops if op.kind == "conv" and op.chain is not None)
 
+        # tile-walk direction per layer (VD_CONV_REVERSE): a layer starts where its input was written LAST, so the
+        # part of that tensor still in L2 is read before it is evicted.  wdir[buffer] = 1 if its writer walked backwards.
+        alternate = os.environ.get("VD_CONV_ALT", "1") != "0"
+        wdir = {}
         for op in ops:
             if op.kind == "conv":
                 c = op.conv
                 flags = _lib.VD_CONV_RELU if c.relu else 0
+                rev = alternate and op.chain is None and not op.pool and wdir.get(op.src, 0) == 0 and op.src != "x0"
+                if rev:
+                    flags |= _lib.VD_CONV_REVERSE
+                wdir[op.dst] = 1 if rev else 0
+                if op.chain is not None:
+                    wdir[op.chain_dst] = 0
                 if self.split:
                     flags |= _lib.VD_CONV_SPLIT
                 hin, win, cin = self.buf_hw[op.src]
@@ -225,6 +235,8 @@ class DetectorEngine:
                 d.stride, d.pad = 1, 0
                 d.dst_C, d.dst_coff = arch.HEAD_ROWS, 0
                 d.flags = _lib.VD_CONV_OUT_F32 | (_lib.VD_CONV_SPLIT if self.split else 0)
+                if alternate and wdir.get(op.src, 0) == 0:
+                    d.flags |= _lib.VD_CONV_REVERSE
                 wt, bt = self.w[f"heads.{op.level}"]
                 d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
                 d.y = self.heads[op.level].data_ptr()
