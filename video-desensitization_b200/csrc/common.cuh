@@ -129,6 +129,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
       : "memory");
 }
 
+// two IEEE fp32 additions in one issue slot (Blackwell FADD2): (a0, a1) += (b0, b1), same results as two add.rn.f32
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+#ifdef VD_NO_FADD2
+  a0 = __fadd_rn(a0, b0);
+  a1 = __fadd_rn(a1, b1);
+  return;
+#endif
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
 // TMA store smem -> global (bulk async group), clipped at the tensor bounds
 __device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -235,6 +248,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);               // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// conversion with the ReLU folded in (cvt ... .relu: negative results become +0): same bits as fmaxf(x, 0) followed by the
+// plain conversion for every finite input, one instruction per pair instead of three
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu))); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
 __device__ __forceinline__ uint32_t act2_max(uint32_t a, uint32_t b) {
@@ -248,6 +268,11 @@ __device__ __forceinline__ uint32_t act2_max(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

@@ -54,6 +54,7 @@ struct ConvKParams {
   int wres;               // 1: the whole weight matrix of the (single) N tile stays resident in shared memory
   int w_bytes;            // wres: KB * BN * 128
   int reverse;            // VD_CONV_REVERSE: tiles are visited from the last to the first
+  int relu_pack;          // 1: ReLU folded into the bf16 conversion (cvt.rn.relu) where the layer allows it
   uint32_t flags;
   const float* bias;
   const float* slope;     // VD_CONV_SLOPE: per-channel negative-side factor
@@ -554,6 +555,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool f32out = (p.flags & VD_CONV_OUT_F32) != 0;
     const bool split = (p.flags & VD_CONV_SPLIT) != 0;
     const int up_C = split ? 3 * p.Cout : p.Cout;        // channels of the upadd tensor
+    // plain ReLU layers with a bf16/fp16 output: the ReLU rides on the conversion instruction (cvt.rn.relu)
+    const bool relu_in_pack = (p.flags & VD_CONV_RELU) && !(p.flags & (VD_CONV_SLOPE | VD_CONV_UPADD)) && !f32out && !split &&
+                              p.relu_pack;
     constexpr int NCHUNK = (BN >= 64) ? BN / 64 : 1;
     const bool active = (BN >= 64) || (half == 0);  // BN == 32 (head GEMM): one 32-column chunk
     int acc = 0;
@@ -586,10 +590,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 bv = lds128(bp + j * 16);
-          f[4 * j + 0] = fmaxf(__uint_as_float(v[4 * j + 0]) + __uint_as_float(bv.x), 0.0f);
-          f[4 * j + 1] = fmaxf(__uint_as_float(v[4 * j + 1]) + __uint_as_float(bv.y), 0.0f);
-          f[4 * j + 2] = fmaxf(__uint_as_float(v[4 * j + 2]) + __uint_as_float(bv.z), 0.0f);
-          f[4 * j + 3] = fmaxf(__uint_as_float(v[4 * j + 3]) + __uint_as_float(bv.w), 0.0f);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]);
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]);
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+          fadd2(f[4 * j + 0], f[4 * j + 1], __uint_as_float(bv.x), __uint_as_float(bv.y));   // ReLU: in the conversion below
+          fadd2(f[4 * j + 2], f[4 * j + 3], __uint_as_float(bv.z), __uint_as_float(bv.w));
         }
         if (issuer) {                                       // previous store out of sOut2 has read it (the newest
           if (c2 == 0) tma_store_wait_read<1>();            // group is the main output chunk staged just before)
@@ -600,10 +606,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 o;
-          o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          o.x = pack_bf16x2_relu(f[8 * j + 0], f[8 * j + 1]);
+          o.y = pack_bf16x2_relu(f[8 * j + 2], f[8 * j + 3]);
+          o.z = pack_bf16x2_relu(f[8 * j + 4], f[8 * j + 5]);
+          o.w = pack_bf16x2_relu(f[8 * j + 6], f[8 * j + 7]);
           sts128(srow + (((half * 4 + j) ^ (row & 7)) << 4), o);
         }
         fence_proxy_async_smem();
@@ -691,19 +697,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 bv = lds128(bp + j * 16);
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + __uint_as_float(bv.x);
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bv.y);
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bv.z);
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bv.w);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]);
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]);
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+            fadd2(f[4 * j + 0], f[4 * j + 1], __uint_as_float(bv.x), __uint_as_float(bv.y));
+            fadd2(f[4 * j + 2], f[4 * j + 3], __uint_as_float(bv.z), __uint_as_float(bv.w));
           }
           if (RES) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 rv = rcur[j];
-              f[8 * j + 0] += bf16lo_to_f32(rv.x); f[8 * j + 1] += bf16hi_to_f32(rv.x);
-              f[8 * j + 2] += bf16lo_to_f32(rv.y); f[8 * j + 3] += bf16hi_to_f32(rv.y);
-              f[8 * j + 4] += bf16lo_to_f32(rv.z); f[8 * j + 5] += bf16hi_to_f32(rv.z);
-              f[8 * j + 6] += bf16lo_to_f32(rv.w); f[8 * j + 7] += bf16hi_to_f32(rv.w);
+              fadd2(f[8 * j + 0], f[8 * j + 1], bf16lo_to_f32(rv.x), bf16hi_to_f32(rv.x));
+              fadd2(f[8 * j + 2], f[8 * j + 3], bf16lo_to_f32(rv.y), bf16hi_to_f32(rv.y));
+              fadd2(f[8 * j + 4], f[8 * j + 5], bf16lo_to_f32(rv.z), bf16hi_to_f32(rv.z));
+              fadd2(f[8 * j + 6], f[8 * j + 7], bf16lo_to_f32(rv.w), bf16hi_to_f32(rv.w));
             }
             if (split) {
 #pragma unroll
@@ -726,7 +734,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[4 * j + 2] = f[4 * j + 2] > 0.f ? f[4 * j + 2] : f[4 * j + 2] * __uint_as_float(sv.z);
               f[4 * j + 3] = f[4 * j + 3] > 0.f ? f[4 * j + 3] : f[4 * j + 3] * __uint_as_float(sv.w);
             }
-          } else if (p.flags & VD_CONV_RELU) {
+          } else if ((p.flags & VD_CONV_RELU) && !relu_in_pack) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
@@ -789,11 +797,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           continue;
         }
-        // staging tile `sbuf` is free once the TMA store issued two chunks ago has read it
+        // staging tile `sbuf` is free once the TMA store issued two chunks ago has read it.  ONE_BAR (every variant but
+        // CHAIN): the issuer checks that BEFORE the barrier that publishes the previous chunk's tile — it waits for the
+        // store issued one chunk ago, i.e. the one reading the tile the NEXT chunk overwrites — so a single CTA-wide
+        // barrier per chunk both publishes this tile and frees the next one.
+#ifdef VD_TWO_BAR
+        constexpr bool ONE_BAR = false;      // A/B build: the two-barrier protocol everywhere
+#else
+        constexpr bool ONE_BAR = !CHAIN;
+#endif
         uint8_t* sbuf = sOut + (chunk_ctr & 1u) * (128 * 128);
-        if (issuer) tma_store_wait_read<1>();
-        if (CHAIN) mbar_wait(&yfree[chunk_ctr & 1u], ((chunk_ctr >> 1) & 1u) ^ 1u);   // chained MMAs have read it too
-        named_bar_sync(1, kEpiThreads);
+        if (!ONE_BAR) {
+          if (issuer) tma_store_wait_read<1>();
+          if (CHAIN) mbar_wait(&yfree[chunk_ctr & 1u], ((chunk_ctr >> 1) & 1u) ^ 1u);   // chained MMAs have read it too
+          named_bar_sync(1, kEpiThreads);
+        }
         if (active) {
           // SWIZZLE_128B staging: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
           const uint32_t srow = smem_u32(sbuf) + row * 128;
@@ -803,6 +821,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               sts128(srow + ((j ^ (row & 7)) << 4),
                      make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
                                 __float_as_uint(f[4 * j + 3])));
+          } else if (relu_in_pack) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2_relu(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2_relu(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2_relu(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2_relu(f[8 * j + 6], f[8 * j + 7]);
+              sts128(srow + (((half * 4 + j) ^ (row & 7)) << 4), o);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -816,6 +844,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         fence_proxy_async_smem();              // generic-proxy smem writes -> visible to the TMA engine
+        if (ONE_BAR && issuer) tma_store_wait_read<0>();      // the other staging tile's store has read it
         named_bar_sync(1, kEpiThreads);
         if (issuer) {
           const int cch = f32out ? 0 : (p.dst_coff + n_tile * BN + ch * 64);
@@ -1201,6 +1230,10 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.up_H = d->up_H; k.up_W = d->up_W;
   k.flags = d->flags;
   k.reverse = ((d->flags & VD_CONV_REVERSE) && !chain) ? 1 : 0;
+  {
+    const char* re = getenv("VD_CONV_RELU_PACK");
+    k.relu_pack = re ? (atoi(re) != 0) : 1;
+  }
   k.bias = d->bias;
   k.slope = d->slope;
   k.bias2 = d->chain_bias;

@@ -216,12 +216,14 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 4; ++j) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * j + e]) + bias_r[8 * j + e], 0.f);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) fadd2(f[e], f[e + 1], bias_r[8 * j + e], bias_r[8 * j + e + 1]);   // ReLU: in the conversion
           uint4 o;
-          o.x = pack_bf16x2(f[0], f[1]);
-          o.y = pack_bf16x2(f[2], f[3]);
-          o.z = pack_bf16x2(f[4], f[5]);
-          o.w = pack_bf16x2(f[6], f[7]);
+          o.x = pack_bf16x2_relu(f[0], f[1]);
+          o.y = pack_bf16x2_relu(f[2], f[3]);
+          o.z = pack_bf16x2_relu(f[4], f[5]);
+          o.w = pack_bf16x2_relu(f[6], f[7]);
           if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
           sts128(crow + (((half * 4 + j) ^ c1_swz(row)) << 4), o);
         }
