@@ -89,6 +89,8 @@ if os.path.exists(rep):
     keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
             "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
             "smsp__warps_active.avg.per_cycle_active"]
     idx = [hdr.index(k) for k in keys if k in hdr]
@@ -99,8 +101,8 @@ if os.path.exists(rep):
             f.write(f'{n},"{short(b[kn])}",' + ",".join(f"{b[i]} {units[i]}" for i in idx) + "\n")
     out.append(f"## 3. `ncu --set full --import-source on` on {len(body)} consecutive convolution launches\n")
     out.append(f"Key metrics per launch: `profiles/{tag}_conv_igemm_ncu_full_key_metrics.csv` (the .ncu-rep itself is not committed).  "
-               "This capture was started with the launch offset of the 72-launch graph (`-s 216`), i.e. it begins at convolution "
-               "launch 9 of the first timed step (layer2.0.conv3), not at launch 0; section 2 above is aligned to the step.\n")
+               "The capture starts at convolution launch 0 of the first timed step (`-s 3*NCONV` skips the warm-up steps), so launch "
+               "n here is row n of section 2: stem, layer1 (three chained conv3 launches), layer2, the first bottlenecks of layer3.\n")
 
 md = os.path.join(P, f"{tag}_ncu_summary.md")
 keep = ""
