@@ -932,3 +932,50 @@ def test_chain_engine_matches_unfused_engine(sd_np):
     for a, b in zip(outs[0][0], outs[1][0]):
         assert torch.equal(a, b)
     assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("shape,cin,cout,res", [((8, 68, 120), 128, 512, True), ((4, 68, 120), 128, 1024, True),
+                                                ((8, 34, 60), 64, 512, False), ((2, 24, 32), 128, 512, True)])
+def test_conv_schedule_variants_are_bit_identical(ops, shape, cin, cout, res, monkeypatch):
+    """Scheduling options never change results: the reversed tile walk (VD_CONV_REVERSE) and the resident weight slice of
+    short-K layers with several 256-wide N tiles (grid a multiple of n_tiles; VD_CONV_WRES_NT=0 streams the weights
+    like every other layer) against the plain forward / streamed launch."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(B, H, W, cin, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(cout, cin, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    r = torch.randn(B, H, W, cout, generator=g).to(torch.bfloat16).to(DEV) if res else None
+    monkeypatch.setenv("VD_CONV_WRES_NT", "0")
+    base = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=r)
+    base_rev = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=r, reverse=True)
+    monkeypatch.setenv("VD_CONV_WRES_NT", "1")
+    wres = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=r)
+    wres_rev = ops.conv2d(x, w, bias, 1, 1, 0, relu=True, residual=r, reverse=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(x.float() @ w.float().t() + bias + (r.float() if res else 0))
+    assert float((base.float() - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max()) + 1e-2
+    for other in (base_rev, wres, wres_rev):
+        assert torch.equal(base, other)
+    # 3x3 halo-patch layer, reversed
+    w3 = (torch.randn(64, 3, 3, 64, generator=g) * 0.05).to(torch.bfloat16).reshape(64, -1).to(DEV)
+    x3 = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).to(DEV)
+    b3 = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    assert torch.equal(ops.conv2d(x3, w3, b3, 3, 1, 1, relu=True), ops.conv2d(x3, w3, b3, 3, 1, 1, relu=True, reverse=True))
+
+
+def test_engine_alternating_walk_matches_forward_walk(sd_np, monkeypatch):
+    """VD_CONV_ALT (the engine alternates the tile-walk direction along the layer chain) is a pure scheduling choice"""
+    from vdesens_b200.engine import DetectorEngine
+    frames = [synth.synthetic_frame(270, 480, 777 + i) for i in range(2)]
+    outs = []
+    for alt in ("0", "1"):
+        monkeypatch.setenv("VD_CONV_ALT", alt)
+        eng = DetectorEngine(sd_np, len(frames), 270, 480, device=DEV, confidence=0.5, nms_iou=0.4)
+        eng.set_frames(_dev_frames(frames))
+        eng.forward()
+        rows, counts = eng.fetch_results()
+        outs.append(([t.clone() for t in eng.head_tensors()], rows.copy(), counts.copy()))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])

@@ -29,6 +29,20 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.vd_build_info()
 
 
+def test_header_constants_match_the_binding():
+    """every numeric #define of include/vdesens.h that the ctypes binding mirrors has the same value there"""
+    from vdesens_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vdesens.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(VD_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)u?\b", hdr)}
+    mirrored = [n for n in dir(_lib) if n.startswith("VD_") and isinstance(getattr(_lib, n), int)]
+    assert len(mirrored) >= 15
+    for n in mirrored:
+        assert n in defs, f"{n} is not defined in vdesens.h"
+        assert defs[n] == getattr(_lib, n), (n, defs[n], getattr(_lib, n))
+    flags = [v for n, v in defs.items() if n.startswith("VD_CONV_")]
+    assert len(flags) == len(set(flags)) and all(v & (v - 1) == 0 for v in flags)      # distinct single bits
+
+
 def test_host_only_entry_points():
     from vdesens_b200 import _lib
     from oracle import cv_oracle as co

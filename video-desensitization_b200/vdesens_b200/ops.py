@@ -62,7 +62,7 @@ def ingest_nchw_f32(frames, H, W):
 
 
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None):
+           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None, reverse=False):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
     The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
@@ -94,6 +94,8 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     d.dst_C, d.dst_coff = out.shape[3], dst_coff
     if relu:
         flags |= _lib.VD_CONV_RELU
+    if reverse:               # scheduling hint only: tiles are walked from the last to the first (same results)
+        flags |= _lib.VD_CONV_REVERSE
     if residual is not None:
         flags |= _lib.VD_CONV_RESIDUAL
     if upadd is not None:
