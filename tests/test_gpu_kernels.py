@@ -979,3 +979,33 @@ def test_engine_alternating_walk_matches_forward_walk(sd_np, monkeypatch):
     for a, b in zip(outs[0][0], outs[1][0]):
         assert torch.equal(a, b)
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_two_gpus_driven_from_one_process(ops, sd_np):
+    """One process, one detector per GPU (the reference's single-process multi-GPU set-up, face.py:56): kernel attributes
+    are per device, launches follow the tensors' device, results are identical on both GPUs.  Needs 2 visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process (gpurun --gpus 2)")
+    from vdesens_b200.engine import DetectorEngine
+    frames = [synth.synthetic_frame(270, 480, 31 + i) for i in range(2)]
+    boxes = [synth.synthetic_boxes(10, 270, 480, seed=5 + i, min_size=8, max_size=200) for i in range(2)]
+    outs = []
+    for d in (1, 0, 1):                       # device 1 first: nothing may depend on device 0 having been set up
+        dev = torch.device("cuda", d)
+        eng = DetectorEngine(sd_np, 2, 270, 480, device=dev, confidence=0.5, nms_iou=0.4)
+        eng.set_frames([torch.from_numpy(f).to(dev) for f in frames])
+        eng.forward()
+        rows, counts = eng.fetch_results()
+        # stateless ops on tensors of device d while the CURRENT device is the other one
+        with torch.cuda.device(1 - d):
+            fr = [torch.from_numpy(f.copy()).to(dev) for f in frames]
+            ops.composite(fr, boxes, "gauss", ksize=31)
+            x0 = ops.ingest([torch.from_numpy(f).to(dev) for f in frames], 270, 480)
+        torch.cuda.synchronize(dev)
+        outs.append((rows.copy(), counts.copy(), [f.cpu().numpy() for f in fr], x0.float().cpu()))
+    want = [co.composite(f, b, "gauss", 8, 31) for f, b in zip(frames, boxes)]
+    for o in outs:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert all(np.array_equal(a, b) for a, b in zip(o[2], want))
+        assert torch.equal(o[3], outs[0][3])
+    assert int(outs[0][1].sum()) > 0

@@ -11,18 +11,20 @@ void vd_set_error(const char* fmt, ...) {
 }
 
 int vd_num_sms() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
-      sms = n;
-    else {
-      (void)cudaGetLastError();
-      return 0;
-    }
+  // per device ordinal (a process may drive several GPUs); plain ints: a racing first call stores the same value twice
+  static int sms[64];
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
   }
-  return sms;
+  if (dev >= 0 && dev < 64 && sms[dev] > 0) return sms[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (dev >= 0 && dev < 64) sms[dev] = n;
+  return n;
 }
 
 extern "C" int vd_abi_version(void) { return VD_ABI_VERSION; }

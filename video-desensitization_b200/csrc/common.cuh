@@ -36,6 +36,34 @@ void vd_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// Function attributes (opt-in dynamic shared memory) belong to a DEVICE: a process that drives several GPUs — one
+// Retinaface per GPU from one Python process, like the reference's single-process DataParallel set-up — must set them on
+// each.  One bit per device ordinal, relaxed atomics (setting an attribute twice is harmless).
+struct VdPerDeviceOnce {
+  unsigned long long mask = 0ull;
+  // returns the current device ordinal if the attribute still has to be set there, -1 if already done, -2 on error
+  int pending() const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    if (dev < 0 || dev >= 64) return dev < 0 ? -2 : dev;          // ordinals >= 64: set every time
+    return (__atomic_load_n(&mask, __ATOMIC_RELAXED) >> dev) & 1ull ? -1 : dev;
+  }
+  void done(int dev) {
+    if (dev >= 0 && dev < 64) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELAXED);
+  }
+};
+
+#define VD_SET_FUNC_ATTR_ONCE_PER_DEVICE(kernel, attr, value)                            \
+  do {                                                                                   \
+    static VdPerDeviceOnce _once;                                                        \
+    const int _dev = _once.pending();                                                    \
+    VD_REQUIRE(_dev != -2, "cudaGetDevice failed");                                      \
+    if (_dev >= 0) {                                                                     \
+      VD_CHECK_CUDA(cudaFuncSetAttribute(kernel, attr, value));                          \
+      _once.done(_dev);                                                                  \
+    }                                                                                    \
+  } while (0)
+
 #define VD_LAUNCH_CHECK()                                                                \
   do {                                                                                   \
     cudaError_t _e = cudaGetLastError();                                                 \

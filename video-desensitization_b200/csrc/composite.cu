@@ -788,11 +788,7 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
     if (fz > smem) smem = fz;
   }
   VD_REQUIRE(smem <= static_cast<size_t>(kMaxDynSmem), "vd_composite_rois: kernel size too large for shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(composite_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attr_set = true;
-  }
+  VD_SET_FUNC_ATTR_ONCE_PER_DEVICE(composite_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   int sms = vd_num_sms();
   if (sms <= 0) sms = 148;
   int per_sm = 4;

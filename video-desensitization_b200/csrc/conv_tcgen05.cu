@@ -1442,12 +1442,8 @@ static const bool g_conv_pdl = [] {
 template <int BN, bool RES, int ROWB = 128, bool CHAIN = false>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, RES, ROWB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, RES, ROWB, CHAIN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr_set = true;
-  }
+  VD_SET_FUNC_ATTR_ONCE_PER_DEVICE((conv_igemm_kernel<BN, RES, ROWB, CHAIN>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSmemBudget);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pl->grid);

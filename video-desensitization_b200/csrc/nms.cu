@@ -240,12 +240,7 @@ extern "C" int vd_nms_batched(const float* cand, const int32_t* cand_count, int 
   const NmsWs ws = carve(workspace, B, cap);
 
   const size_t sort_smem = static_cast<size_t>(cap) * (sizeof(unsigned long long) + sizeof(unsigned short));
-  static bool attr_set = false;
-  if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       VD_NMS_MAX_CAND * 10));
-    attr_set = true;
-  }
+  VD_SET_FUNC_ATTR_ONCE_PER_DEVICE(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VD_NMS_MAX_CAND * 10);
   nms_sort_kernel<<<B, kSortThreads, sort_smem, st>>>(cand, cand_count, cap, ws);
   VD_LAUNCH_CHECK();
   dim3 mgrid(64, B);

@@ -342,11 +342,7 @@ void vd_stem_pool_info(const vd_stem_pool_plan* pl, int* units, int* grid) {
 }
 
 int vd_stem_pool_run(const vd_stem_pool_plan* pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VD_CHECK_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    attr_set = true;
-  }
+  VD_SET_FUNC_ATTR_ONCE_PER_DEVICE(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM);
   stem_pool_kernel<<<pl->grid, SP_THREADS, SP_SMEM, st>>>(pl->tmA, pl->tmB, pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;

@@ -16,6 +16,20 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_arg_device(fn):
+    """run with the CUDA device of the first tensor argument current: the C-ABI launches on the current device and
+    on its current stream, and a process may hold tensors on several GPUs"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        first = args[0][0] if isinstance(args[0], (list, tuple)) else args[0]
+        assert first.is_cuda, "libvdesens ops need CUDA tensors (no CPU fallback)"
+        with torch.cuda.device(first.device):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _p(t):
     if t is None:
         return None
@@ -37,6 +51,7 @@ def x0_pitch(W):
     return int(_lib.lib().vd_x0_pitch(int(W)))
 
 
+@_on_arg_device
 def ingest(frames, H, W, identity=None, precision="bf16"):
     """-> x0 (B,H,Wp,4) in the library's activation type.  reference: Retinaface.preprocess (face.py:65-88)."""
     lib = _lib.lib(precision)
@@ -50,6 +65,7 @@ def ingest(frames, H, W, identity=None, precision="bf16"):
     return x0
 
 
+@_on_arg_device
 def ingest_nchw_f32(frames, H, W):
     """-> fp32 (B,3,H,W), the tensor Retinaface.preprocess returns (face.py:87)."""
     lib = _lib.lib()
@@ -61,6 +77,7 @@ def ingest_nchw_f32(frames, H, W):
     return out
 
 
+@_on_arg_device
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
            out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None, reverse=False):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
@@ -130,6 +147,7 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     return out if out2 is None else (out, out2)
 
 
+@_on_arg_device
 def mnet_stem(x0, w, bias, slope, H, W):
     """conv_bn(3, 8, stride 2) of the MobileNet0.25 variant on the ingest tensor (reference mobilenet025.py:3-8)."""
     lib = _lib.lib(_lib.precision_of(x0.dtype))
@@ -138,6 +156,7 @@ def mnet_stem(x0, w, bias, slope, H, W):
     return y
 
 
+@_on_arg_device
 def mnet_dw3x3(x, w, bias, slope, stride):
     """depthwise 3x3 + folded BN + slope activation (reference mobilenet025.py:10-14); w is [9][C]."""
     lib = _lib.lib(_lib.precision_of(x.dtype))
@@ -147,6 +166,7 @@ def mnet_dw3x3(x, w, bias, slope, stride):
     return y
 
 
+@_on_arg_device
 def mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride):
     """conv_dw block (depthwise 3x3 + pointwise 1x1, reference mobilenet025.py:10-19) as one kernel."""
     lib = _lib.lib(_lib.precision_of(x.dtype))
@@ -158,6 +178,7 @@ def mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride):
     return y
 
 
+@_on_arg_device
 def mnet_pw(x, w, bias, slope):
     """pointwise 1x1 for Cin < 64 (reference mobilenet025.py:16-18); w is [Cin][Cout]."""
     lib = _lib.lib(_lib.precision_of(x.dtype))
@@ -168,6 +189,7 @@ def mnet_pw(x, w, bias, slope):
     return y
 
 
+@_on_arg_device
 def maxpool3x3s2(x):
     lib = _lib.lib(_lib.precision_of(x.dtype))
     B, H, W, Cc = x.shape
@@ -176,6 +198,7 @@ def maxpool3x3s2(x):
     return y
 
 
+@_on_arg_device
 def decode_threshold_lcl(loc, conf, landms, H, W, conf_thr, cap=4096):
     """reference-layout head tensors -> (cand (B,cap,16), count (B,), status (1,))"""
     lib = _lib.lib()
@@ -189,6 +212,7 @@ def decode_threshold_lcl(loc, conf, landms, H, W, conf_thr, cap=4096):
     return cand, count, status
 
 
+@_on_arg_device
 def decode_threshold_heads(heads, H, W, conf_thr, cap=4096):
     lib = _lib.lib()
     B = heads[0].shape[0]
@@ -214,6 +238,7 @@ def unletterbox_params(input_hw, image_shapes):
     return out
 
 
+@_on_arg_device
 def nms(cand, count, iou_thr, unlb, max_det=1024):
     """-> (rows (B,max_det,16), out_count (B,), status (1,))"""
     lib = _lib.lib()
@@ -230,6 +255,7 @@ def nms(cand, count, iou_thr, unlb, max_det=1024):
     return rows, out_count, status
 
 
+@_on_arg_device
 def composite(frames, ext_boxes, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, det_rows=None,
               det_count=None, scratch_frames=8.0):
     """In-place sequential compositing on device frames.  frames: list of device uint8 (h,w,3);
