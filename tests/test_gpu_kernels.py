@@ -1009,3 +1009,39 @@ def test_two_gpus_driven_from_one_process(ops, sd_np):
         assert all(np.array_equal(a, b) for a, b in zip(o[2], want))
         assert torch.equal(o[3], outs[0][3])
     assert int(outs[0][1].sum()) > 0
+
+
+def test_config2_full_batch_invariances(sd_np):
+    """C2 at BASELINE's full size (16 x 1080p, the bench workload) through size-independent properties: a frame's
+    result does not depend on its slot in the batch nor on the batch size (tile shapes differ between B = 16 and B = 2, the
+    K order of every output does not), and blur + detection of the full batch equals the per-frame CPU compositing of
+    the boxes the device returned."""
+    from vdesens_b200.engine import DetectorEngine
+    from vdesens_b200.pipeline import Anonymizer
+    H, W, B = 1080, 1920, 16
+    uniq = [synth.synthetic_frame(H, W, 5000 + i) for i in range(8)]
+    frames = uniq + uniq[::-1]                                  # frame j also sits in slot 15 - j
+    eng = DetectorEngine(sd_np, B, H, W, device=DEV, confidence=0.5, nms_iou=0.4)
+    eng.set_frames(torch.from_numpy(np.stack(frames)).to(DEV))
+    eng.forward()
+    rows, counts = (a.copy() for a in eng.fetch_results())
+    heads = [t.clone() for t in eng.head_tensors()]
+    assert int(counts.min()) > 0
+    for j in range(8):
+        assert counts[j] == counts[15 - j] and np.array_equal(rows[j, :counts[j]], rows[15 - j, :counts[j]]), j
+        for t in heads:
+            assert torch.equal(t[j], t[15 - j])
+    eng2 = DetectorEngine(sd_np, 2, H, W, device=DEV, confidence=0.5, nms_iou=0.4)
+    eng2.set_frames(torch.from_numpy(np.stack(uniq[:2])).to(DEV))
+    eng2.forward()
+    rows2, counts2 = eng2.fetch_results()
+    for j in range(2):
+        assert counts2[j] == counts[j] and np.array_equal(rows2[j, :counts2[j]], rows[j, :counts[j]])
+    for t16, t2 in zip(heads, eng2.head_tensors()):
+        assert torch.equal(t16[:2], t2)
+    # detect + Gaussian blur (k = 31) of the whole batch == CPU compositing of the returned boxes, frame by frame
+    plates = [synth.synthetic_boxes(4, H, W, seed=90 + i) for i in range(B)]
+    out, boxes = Anonymizer(eng, "gauss", ksize=31).process_batch(frames, plates)
+    for i in (0, 7, 8, 15):
+        allb = [tuple(int(v) for v in b) for b in boxes[i]] + plates[i]
+        assert np.array_equal(out[i], co.composite(frames[i], allb, "gauss", ksize=31)), i
