@@ -265,7 +265,6 @@ class DetectorEngine:
         self.out_count_host = torch.zeros((B,), dtype=torch.int32).pin_memory()
         self.status_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
         self.launches_per_forward = 1 + sum(1 for p in self.plans) + 1 + 3
-        self._graph = None
 
     def _make_plan(self, d, name):
         h = C.c_void_p()

@@ -10,7 +10,7 @@ the ops can be traced / shape-checked without a GPU.
     x0 = torch.ops.vdesens.ingest(frames, 1080, 1920)
     y  = torch.ops.vdesens.conv2d(x, w_packed, bias, 3, 1, 1, True, None)
 
-The engine (`engine.py`) drives the same entry points through pre-built plans inside a CUDA graph; these ops are
+The engine (`engine.py`) drives the same entry points through pre-built plans on its private stream; these ops are
 the composable surface for callers that hold torch tensors.
 """
 from typing import List, Optional, Tuple
