@@ -181,7 +181,9 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    from vdesens_b200 import synth
+    from vdesens_b200 import shard, synth
+    # one rank per GPU: keep the rank and its pinned staging buffers on the GPU's NUMA node (host plumbing, N > 1 only)
+    numa_cpus = shard.bind_to_gpu_numa_node(local) if (world > 1 and os.environ.get("VD_NUMA_BIND", "1") != "0") else None
     from vdesens_b200.engine import DetectorEngine
     from vdesens_b200.pipeline import Anonymizer
 
@@ -319,6 +321,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32x": "f16x3 (split hi/lo, fp32-class)"}[precision],
         "data": "synthetic", "config": workload_config(world),
+        "host_affinity": (f"each rank bound to the CPUs local to its GPU (NVML; rank 0: {len(numa_cpus)} CPUs)" if numa_cpus else "unbound"),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BATCH * H * W * 3,
                 "d2h_bytes_per_step": BATCH * H * W * 3 + int(rows.nbytes) + int(counts.nbytes) + 4,
                 "steps": e2e_steps, "host_ms_per_batch": e2e_host, "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step (double-buffered), max over ranks"},

@@ -23,7 +23,11 @@ def _on_arg_device(fn):
 
     @functools.wraps(fn)
     def wrapped(*args, **kwargs):
-        first = args[0][0] if isinstance(args[0], (list, tuple)) else args[0]
+        first = args[0] if args else next(iter(kwargs.values()), None)
+        if isinstance(first, (list, tuple)):
+            first = first[0] if first else None
+        if not isinstance(first, torch.Tensor):
+            return fn(*args, **kwargs)              # nothing to take a device from: the function's own checks apply
         assert first.is_cuda, "libvdesens ops need CUDA tensors (no CPU fallback)"
         with torch.cuda.device(first.device):
             return fn(*args, **kwargs)

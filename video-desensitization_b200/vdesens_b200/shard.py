@@ -38,3 +38,32 @@ def gather_ordered(local_results: Sequence, start: int, group=None, dst: int = 0
     if seq != list(range(len(seq))):
         raise RuntimeError("frame sequence has gaps or duplicates after the gather")
     return [t[1] for t in flat]
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin the calling process to the CPUs NVML reports as local to CUDA device `device_index` (its NUMA node), BEFORE
+    any pinned staging buffer is allocated: with one rank per GPU every rank moves its frames host<->device each step
+    (2 x 100 MB per 16-frame 1080p batch), and buffers that were first touched on the other socket make that traffic
+    cross the inter-socket link (host PCIe / NUMA is the expected limiter at 8 GPUs).  Host-side plumbing
+    only; returns the sorted CPU list now in effect, or None when NVML / the affinity call is unavailable (nothing is
+    changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            before = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            after = os.sched_getaffinity(0)
+            if not after or not (after <= before):          # never widen or empty the mask we were started with
+                os.sched_setaffinity(0, before)
+                return None
+            return sorted(after)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return None
