@@ -241,6 +241,24 @@ int vd_composite_rois(const vd_frame_t* frames, int B, const float* det_rows,
                       const uint16_t* taps_q8, int ksize, uint32_t* status, void* workspace,
                       size_t workspace_bytes, vd_stream_t stream);
 
+/* ---- host half of a device-resident JPEG ingest (replaces the entropy-decoding part of cv2.imread,
+ * reference combine_detect.py:167-180).  HOST functions: no CUDA call, no allocation.  Baseline / sequential Huffman,
+ * 8-bit, 1 or 3 components with sampling factors <= 2, one interleaved scan, restart intervals — what cv2.imwrite
+ * produces.  Anything else returns VD_ERR_UNSUPPORTED and the caller keeps using its CPU decoder. ---- */
+typedef struct vd_jpeg_info {
+  int32_t width, height, ncomp;       /* ncomp = 1 (grey) or 3 (YCbCr) */
+  int32_t h[3], v[3];                 /* sampling factors per component */
+  int32_t blocks_x[3], blocks_y[3];   /* 8x8-block grid per component (whole MCUs) */
+  int32_t restart_interval;           /* MCUs between RSTn markers, 0 = none */
+  uint16_t quant[3][64];              /* quantisation table per component, natural (row-major) order */
+} vd_jpeg_info_t;
+
+int vd_jpeg_read_header(const uint8_t* data, size_t size, vd_jpeg_info_t* info);
+
+/* coefK [host]: blocks_y[K] * blocks_x[K] * 64 int16, blocks in raster order, coefficients in natural order, still
+ * quantised (multiply by info.quant[K] to de-quantise).  coef1 / coef2 may be NULL for a grey image. */
+int vd_jpeg_decode_coefficients(const uint8_t* data, size_t size, int16_t* coef0, int16_t* coef1, int16_t* coef2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,12 @@ class VdConvDesc(C.Structure):
                 ("chain_w", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_y", C.c_void_p), ("chain_Cout", C.c_int32)]
 
 
+class VdJpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32),
+                ("h", C.c_int32 * 3), ("v", C.c_int32 * 3), ("blocks_x", C.c_int32 * 3), ("blocks_y", C.c_int32 * 3),
+                ("restart_interval", C.c_int32), ("quant", (C.c_uint16 * 64) * 3)]
+
+
 _SIGS = {
     "vd_abi_version": (C.c_int, []),
     "vd_act_is_fp16": (C.c_int, []),
@@ -69,6 +75,8 @@ _SIGS = {
     "vd_composite_rois": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vd_jpeg_read_header": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegInfo)]),
+    "vd_jpeg_decode_coefficients": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED = tuple(_SIGS)
