@@ -6,7 +6,7 @@ opencv-python (pin 4.9.0.80, reference requirements.txt:109; 4.13.0 in this imag
 the reference: cv2.resize INTER_LINEAR at detect_face/utils/utils.py:15, cv2.resize INTER_NEAREST at
 combine_detect.py:157-158.  cv2.GaussianBlur has NO call site in the reference; BASELINE.json's
 north_star defines it as the oracle for the Gaussian mode.  Parity is "unpinned by the reference"
-(it has no tests); it is pinned here by tests/test_oracle_cv.py, which checks every function below
+(it has no tests); it is pinned here by tests/test_oracle_golden.py (test_cv_live_against_this_image), which checks every function below
 bit-for-bit against the cv2 build in this image, and by tests/golden/cv_golden.npz.
 """
 import math
