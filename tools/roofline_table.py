@@ -40,6 +40,7 @@ print("ncu durations are serialised and cold-cache (`profiles/%s_ncu_summary.md`
 print("| # | layer(s) | us | DRAM MB | GFLOP | DRAM-bound us | tensor-bound us | bound | eff |")
 print("|---|---|---:|---:|---:|---:|---:|---|---:|")
 tot_t = tot_b = tot_hbm = tot_tc = 0.0
+gaps = []
 cls = {"hbm": [0.0, 0.0], "tensor": [0.0, 0.0]}
 for i, (r, (label, f)) in enumerate(zip(rows, launches)):
     t = float(r["us"])
@@ -50,8 +51,16 @@ for i, (r, (label, f)) in enumerate(zip(rows, launches)):
     cls[kind][0] += t
     cls[kind][1] += bound
     tot_t += t; tot_b += bound; tot_hbm += th; tot_tc += tt
+    gaps.append((t - bound, label.replace("body.", ""), t, kind, bound / t))
     print(f"| {i} | {label.replace('body.', '')} | {t:.1f} | {by / 1e6:.0f} | {f / 1e9:.1f} | {th:.1f} | {tt:.1f} | {kind} | {bound / t:.2f} |")
 print(f"\nSum over the {len(rows)} launches: measured {tot_t / 1e3:.2f} ms; sum of per-launch bounds {tot_b / 1e3:.2f} ms "
       f"(= {tot_b / tot_t:.0%} of measured); all-DRAM {tot_hbm / 1e3:.2f} ms, all-tensor {tot_tc / 1e3:.2f} ms.")
 for k, (t, b) in cls.items():
     print(f"* launches bounded by {k}: {t / 1e3:.2f} ms measured, {b / 1e3:.2f} ms at the bound ({b / t:.0%}).")
+print("\n## Where the gap is (measured - bound, largest first)\n")
+print("| gap us | layer(s) | us | bound | eff |")
+print("|---:|---|---:|---|---:|")
+for g, label, t, kind, eff in sorted(gaps, reverse=True)[:16]:
+    print(f"| {g:.0f} | {label} | {t:.1f} | {kind} | {eff:.2f} |")
+print(f"\nTotal gap {sum(g[0] for g in gaps) / 1e3:.2f} ms.  conv1's bound counts its 147 real taps x channels; the kernel issues K = 224 (8 taps x 4 "
+      "channels per filter row) at N = 64, so its structural floor is about three times that bound.")
