@@ -158,3 +158,23 @@ def test_ordered_gather_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GATHER_OK 37" in r.stdout
+
+
+def test_load_image_rgb_equals_the_references_two_steps(tmp_path):
+    """combine_detect.load_image_rgb == cv2.cvtColor(cv2.imread(p), COLOR_BGR2RGB) (reference combine_detect.py:170-172)
+    for JPEG, PNG, greyscale and alpha files"""
+    import cv2
+    import combine_detect as cd
+    from vdesens_b200 import synth
+    rgb = synth.synthetic_frame(135, 241, 9)
+    bgr = cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)
+    files = {"a.jpg": bgr, "b.png": bgr, "c.png": bgr[..., 0].copy(), "d.png": np.dstack([bgr, bgr[..., :1]]),
+             "e.jpg": bgr[..., 1].copy()}
+    for name, img in files.items():
+        p = str(tmp_path / name)
+        assert cv2.imwrite(p, img)
+        want = cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB)
+        got = cd.load_image_rgb(p)
+        assert got.dtype == np.uint8 and got.shape == want.shape and np.array_equal(got, want), name
+    with pytest.raises(ValueError):
+        cd.load_image_rgb(str(tmp_path / "missing.jpg"))

@@ -88,11 +88,14 @@ def batch_process_frames(frames, face_detector, plate_detector=None, batch_size=
 
 
 def load_image_rgb(image_path):
+    """reference :167-180 (cv2.imread + BGR -> RGB).  OpenCV >= 4.10 can hand the decoder's output over in RGB order
+    directly (same bytes, one pass over the frame less); older builds take the reference's two steps."""
     import cv2
-    img = cv2.imread(image_path)
+    flag = getattr(cv2, "IMREAD_COLOR_RGB", None)
+    img = cv2.imread(image_path, flag) if flag is not None else cv2.imread(image_path)
     if img is None:
         raise ValueError(f"cannot read image: {image_path}")
-    return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    return img if flag is not None else cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
 
 
 def save_output_image(image_array, output_path):
