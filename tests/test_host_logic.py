@@ -178,3 +178,25 @@ def test_load_image_rgb_equals_the_references_two_steps(tmp_path):
         assert got.dtype == np.uint8 and got.shape == want.shape and np.array_equal(got, want), name
     with pytest.raises(ValueError):
         cd.load_image_rgb(str(tmp_path / "missing.jpg"))
+
+
+def test_decode_ahead_yields_groups_in_order(tmp_path):
+    """the frame loop's decode-ahead stage: every group comes back complete and in order, whatever the pool size"""
+    import cv2
+    import combine_detect as cd
+    from vdesens_b200 import synth
+    paths = []
+    for i in range(7):
+        p = str(tmp_path / f"f{i:02d}.png")
+        cv2.imwrite(p, cv2.cvtColor(synth.synthetic_frame(24, 32, 100 + i), cv2.COLOR_RGB2BGR))
+        paths.append(p)
+    groups = [paths[0:3], paths[3:6], paths[6:7]]
+    assert 6 <= cd._io_workers() <= 32
+    for workers in (None, 1, 4):
+        got = list(cd._decoded_batches(groups, workers=workers))
+        assert [g[0] for g in got] == groups
+        for files, frames in got:
+            assert len(frames) == len(files)
+            for f, fr in zip(files, frames):
+                assert np.array_equal(fr, synth.synthetic_frame(24, 32, 100 + int(os.path.basename(f)[1:3])))
+    assert list(cd._decoded_batches([])) == []
