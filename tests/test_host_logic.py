@@ -200,3 +200,70 @@ def test_decode_ahead_yields_groups_in_order(tmp_path):
             for f, fr in zip(files, frames):
                 assert np.array_equal(fr, synth.synthetic_frame(24, 32, 100 + int(os.path.basename(f)[1:3])))
     assert list(cd._decoded_batches([])) == []
+
+
+def test_plate_boxes_accepts_tuples_and_ultralytics_results():
+    """reference combine_detect.py:239 honours only tuples — which drops every plate of the Ultralytics model the
+    reference itself builds (:868-874).  Here a Results-like object (`.boxes.xyxy`) is read, and any other type warns."""
+    import combine_detect as cd
+
+    class _Boxes:
+        def __init__(self, a):
+            self.xyxy = torch.tensor(a, dtype=torch.float32)
+
+    class _Results:
+        def __init__(self, a):
+            self.boxes = _Boxes(a)
+
+    res = [(None, [[1, 2, 3, 4]]), _Results([[5.5, 6.5, 70.25, 80.0], [0, 0, 9, 9]]), _Results(np.zeros((0, 4))), None]
+    assert cd._plate_boxes(res, 0) == [[1, 2, 3, 4]]
+    assert cd._plate_boxes(res, 1) == [[5.5, 6.5, 70.25, 80.0], [0.0, 0.0, 9.0, 9.0]]
+    assert cd._plate_boxes(res, 2) == [] and cd._plate_boxes(res, 3) == [] and cd._plate_boxes(None, 0) == []
+    cd._warned_plate_type = False
+    with pytest.warns(RuntimeWarning, match="NOT applied"):
+        assert cd._plate_boxes([["not", "a", "tuple"]], 0) == []
+    # the integer boxes the compositing pass receives: int() truncation toward zero (reference :243)
+    assert cd._plates_of(lambda frames, verbose, conf: [_Results([[-5.5, 6.9, 70.25, 80.0]])], [None]) == [[(-5, 6, 70, 80)]]
+    assert cd._plates_of(None, [None, None]) == [[], []]
+
+
+def test_mode_and_switch_validation():
+    from vdesens_b200 import _lib
+    import combine_detect as cd
+    assert _lib.mode_id("mosaic") == _lib.VD_MODE_MOSAIC and _lib.mode_id("gauss") == _lib.VD_MODE_GAUSS
+    for bad in ("gaus", "Mosaic", "", None):
+        with pytest.raises(ValueError):
+            _lib.mode_id(bad)
+    with pytest.raises(ValueError):
+        cd.composite_frames([np.zeros((8, 8, 3), np.uint8)], [[(0, 0, 4, 4)]], mode="blur")
+    with pytest.raises(ValueError):
+        cd.batch_process_images("/nonexistent", "/nonexistent", None, None, on_error="ignore")
+
+
+def test_engine_cache_reuses_the_larger_replica(monkeypatch):
+    """every new list length used to build a full DetectorEngine replica.  A shorter batch now reuses the
+    engine already built, a longer one replaces it, and at most _MAX_ENGINES are alive."""
+    from detect_face import face as ff
+    built = []
+
+    class FakeEngine:
+        def __init__(self, sd, b, *a, **k):
+            self.B = b
+            built.append(b)
+
+    monkeypatch.setattr(ff, "DetectorEngine", FakeEngine)
+    r = ff.Retinaface.__new__(ff.Retinaface)
+    r.__dict__.update(ff.Retinaface._defaults)
+    r.batch_size, r.cand_cap, r.max_det, r.precision, r._sd, r.device, r._engines = None, 4096, 2048, "bf16", {}, "cuda:0", {}
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    assert r._engine_for(16).B == 16
+    assert r._engine_for(5).B == 16 and r._engine_for(16).B == 16 and r._engine_for(1).B == 16
+    assert built == [16]
+    assert r._engine_for(1, exact=True).B == 1 and built == [16, 1]
+    assert r._engine_for(32).B == 32 and built == [16, 1, 32] and len(r._engines) == ff.Retinaface._MAX_ENGINES
+    assert sorted(r._engines) == [1, 32]                 # the least recently used (16) was freed
+    assert r._engine_for(7).B == 32 and built == [16, 1, 32]
+    r.batch_size = 8                                     # a configured batch wins over the list length
+    assert r._engine_for(3).B == 32                      # still served by the larger replica
+    r._engines.clear()
+    assert r._engine_for(3).B == 8

@@ -100,3 +100,37 @@ def test_corrupt_huffman_table_is_rejected():
             jpeg.decode_coefficients(bytes(b))
         except RuntimeError:
             pass
+
+
+def test_tables_of_the_previous_file_are_never_reused():
+    """parse() runs on a thread_local scratch object.  A file WITHOUT a DHT segment (abbreviated MJPEG
+    frame) decoded right after a normal file on the same thread must fail with "missing table", not be entropy-decoded
+    with the previous file's Huffman tables; same for a scan that names one component twice."""
+    img = synth.synthetic_frame(48, 64, 3)
+    good = _encode(img, []).tobytes()
+    jpeg.decode_coefficients(good)
+
+    def strip(data, marker):
+        out, pos = bytearray(data[:2]), 2
+        while data[pos + 1] != 0xDA:
+            ln = (data[pos + 2] << 8) | data[pos + 3]
+            if data[pos + 1] != marker:
+                out += data[pos:pos + 2 + ln]
+            pos += 2 + ln
+        return bytes(out + data[pos:])
+
+    no_dht = strip(good, 0xC4)
+    assert len(no_dht) < len(good) - 400
+    with pytest.raises(RuntimeError, match="missing table"):
+        jpeg.decode_coefficients(no_dht)
+    jpeg.decode_coefficients(good)
+    with pytest.raises(RuntimeError, match="missing table"):
+        jpeg.decode_coefficients(strip(good, 0xDB))
+    # duplicate component id in the scan header
+    b = bytearray(good)
+    sos = b.index(b"\xff\xda")
+    assert b[sos + 4] == 3
+    b[sos + 7] = b[sos + 5]                 # second scan component := first component's id
+    jpeg.decode_coefficients(good)
+    with pytest.raises(RuntimeError, match="twice"):
+        jpeg.decode_coefficients(bytes(b))

@@ -32,6 +32,8 @@ def composite_frames(frames, boxes_per_frame, mode="mosaic", mosaic_level=8, ksi
     """frames: list of uint8 HxWx3 arrays (sizes may differ); boxes_per_frame: list of lists of
     (x1,y1,x2,y2) — applied one after another, int()-truncated, clipped, empty ones skipped
     (reference :242-249, :145-150).  Returns NEW arrays; inputs are not modified."""
+    from vdesens_b200 import _lib
+    _lib.mode_id(mode)
     dev = _device()
     dfr = [torch.from_numpy(np.ascontiguousarray(f)).to(dev) for f in frames]
     ib = [[tuple(int(v) for v in b) for b in bl] for bl in boxes_per_frame]
@@ -50,24 +52,51 @@ def gaussian_rectangle_region_single(img, x1, y1, x2, y2, ksize=31, sigma=0.0):
     return composite_frames([img], [[(x1, y1, x2, y2)]], "gauss", ksize=ksize, sigma=sigma)[0]
 
 
+_warned_plate_type = False
+
+
 def _plate_boxes(plate_results, j):
-    # reference :239 — only tuple results are honoured: (anything, [[x1,y1,x2,y2], ...])
+    """Boxes of frame j from whatever the plate provider returned.
+    reference :239 honours only tuples `(anything, [[x1,y1,x2,y2], ...])` — and therefore silently drops every
+    plate when the provider is the Ultralytics YOLO model its own __main__ builds (:868-874), whose per-frame result
+    is a `Results` object.  For an anonymiser that is a privacy hole, not a behaviour to reproduce: `Results`
+    (anything with `.boxes.xyxy`) is read explicitly, and any OTHER non-tuple result warns once instead of vanishing."""
+    global _warned_plate_type
     if plate_results is None:
         return []
     r = plate_results[j]
-    return list(r[1]) if isinstance(r, tuple) else []
+    if isinstance(r, tuple):
+        return list(r[1])
+    xyxy = getattr(getattr(r, "boxes", None), "xyxy", None)
+    if xyxy is not None:
+        if hasattr(xyxy, "detach"):
+            xyxy = xyxy.detach().cpu().numpy()
+        return [list(map(float, b[:4])) for b in np.asarray(xyxy).reshape(-1, 4)]
+    if r is not None and not _warned_plate_type:
+        import warnings
+        warnings.warn(f"plate_detector returned {type(r).__name__} per frame; expected a tuple (img, boxes) or an "
+                      f"Ultralytics Results object — its boxes are NOT applied", RuntimeWarning, stacklevel=2)
+        _warned_plate_type = True
+    return []
+
+
+def _plates_of(plate_detector, frames):
+    """per-frame integer plate boxes of one batch (reference :217, :239, :243)"""
+    res = plate_detector(list(frames), verbose=False, conf=0.5) if plate_detector is not None else None
+    return [[tuple(int(v) for v in b) for b in _plate_boxes(res, j)] for j in range(len(frames))]
 
 
 def batch_process_frames(frames, face_detector, plate_detector=None, batch_size=16, mode="mosaic", mosaic_level=8,
                          ksize=31, sigma=0.0):
     """The reference frame loop (:204-256) on in-memory RGB frames.  Returns (processed frames list,
     total_faces, total_plates).  Frames of one batch must share a size (as video frames do)."""
+    from vdesens_b200 import _lib
+    _lib.mode_id(mode)
     processed, total_faces, total_plates = [], 0, 0
     anon = None
     for i in range(0, len(frames), batch_size):
         batch = frames[i:i + batch_size]
-        plate_results = plate_detector(list(batch), verbose=False, conf=0.5) if plate_detector is not None else None
-        plates = [[tuple(int(v) for v in b) for b in _plate_boxes(plate_results, j)] for j in range(len(batch))]
+        plates = _plates_of(plate_detector, batch)
         if len({f.shape[:2] for f in batch}) > 1:
             # mixed frame sizes in one batch (the reference letterboxes each frame, face.py:73-80)
             res = face_detector.detect_images(list(batch))
@@ -153,27 +182,43 @@ def _one_shape(frames):
 
 
 def batch_process_images(input_dir, output_dir, face_detector, plate_detector, batch_size=16, mode="mosaic",
-                         mosaic_level=8, ksize=31, sigma=0.0):
+                         mosaic_level=8, ksize=31, sigma=0.0, sort=True, on_error="raise"):
     """Same signature and return value as the reference (:183-277): (n_frames, n_faces, n_plates).
 
     What changes is the schedule: the reference loads a batch, waits for both detectors,
     mosaics on the CPU and only then loads the next batch.  Here batch i+1 is decoded by a thread pool while the
     GPU processes batch i through the pipelined StreamingAnonymizer (H2D / compute / D2H overlapped) and the
-    saver pool encodes batch i-1.  Files are taken in sorted order, a failing batch raises instead of being
-    dropped silently (reference :226-228), and only tuple results of the plate provider are honoured (:239)."""
+    saver pool encodes batch i-1.  The plate provider runs on its own worker thread, concurrently with the face
+    detector of the same batch, as in the reference (:214-217); its boxes are only waited for when the compositing
+    pass is enqueued.
+
+    Two documented departures, each with a switch back to the reference's behaviour:
+      sort=True         files are processed in sorted name order (the reference takes os.listdir order, :186-189,
+                        which is arbitrary); sort=False restores that.
+      on_error="raise"  a failing batch raises (the reference logs and silently DROPS the batch, :226-228, so frames
+                        go missing from the output video); on_error="skip" restores that: the batches in flight when
+                        the error surfaced are dropped with a warning and the loop continues with the next one."""
     from collections import deque
+    from vdesens_b200 import _lib
     from vdesens_b200.pipeline import StreamingAnonymizer
-    paths = sorted(os.path.join(input_dir, f) for f in os.listdir(input_dir)
-                   if f.lower().endswith((".png", ".jpg", ".jpeg")))
+    _lib.mode_id(mode)
+    if on_error not in ("raise", "skip"):
+        raise ValueError(f"on_error must be 'raise' or 'skip', got {on_error!r}")
+    names = [f for f in os.listdir(input_dir) if f.lower().endswith((".png", ".jpg", ".jpeg"))]
+    if sort:
+        names.sort()
+    paths = [os.path.join(input_dir, f) for f in names]
     os.makedirs(output_dir, exist_ok=True)
     groups = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
     n_frames = n_faces = n_plates = 0
 
-    def plates_of(frames):
-        res = plate_detector(list(frames), verbose=False, conf=0.5) if plate_detector is not None else None
-        return [[tuple(int(v) for v in b) for b in _plate_boxes(res, j)] for j in range(len(frames))]
+    def failed(what, exc):
+        if on_error == "raise":
+            raise exc
+        import warnings
+        warnings.warn(f"batch_process_images: {what} dropped after {type(exc).__name__}: {exc}", RuntimeWarning)
 
-    with ThreadPoolExecutor(max_workers=_io_workers()) as savers:
+    with ThreadPoolExecutor(max_workers=_io_workers()) as savers, ThreadPoolExecutor(max_workers=1) as plate_pool:
         saves = []
 
         def emit(files, out):
@@ -187,10 +232,15 @@ def batch_process_images(input_dir, output_dir, face_detector, plate_detector, b
             if shape is None:
                 # mixed frame sizes inside one batch: every frame is letterboxed on its own (face.py:73-80)
                 files, frames = src.pop()
-                plates = plates_of(frames)
-                res = face_detector.detect_images(frames)
-                allb = [[tuple(int(v) for v in b) for b in r[1]] + plates[j] for j, r in enumerate(res)]
-                emit(files, composite_frames(frames, allb, mode, mosaic_level, ksize, sigma))
+                try:
+                    pf = plate_pool.submit(_plates_of, plate_detector, frames)      # sibling thread, as the reference
+                    res = face_detector.detect_images(frames)
+                    plates = pf.result()
+                    allb = [[tuple(int(v) for v in b) for b in r[1]] + plates[j] for j, r in enumerate(res)]
+                    emit(files, composite_frames(frames, allb, mode, mosaic_level, ksize, sigma))
+                except Exception as e:                                               # noqa: BLE001 (reference :226)
+                    failed(f"batch of {len(files)} frames", e)
+                    continue
                 n_frames += len(files)
                 n_faces += sum(len(r[1]) for r in res)
                 n_plates += sum(len(p) for p in plates)
@@ -198,26 +248,31 @@ def batch_process_images(input_dir, output_dir, face_detector, plate_detector, b
             # a run of consecutive batches of one frame size goes through the pipelined path
             eng = face_detector._engine_for(min(batch_size, len(paths)))
             sa = StreamingAnonymizer(eng, mode, mosaic_level, ksize, sigma)
-            inflight = deque()                       # (files, plate boxes) per submitted device batch
+            inflight = deque()                       # (files, Future of the plate boxes) per submitted device batch
 
             def device_batches():
                 while src.more() and _one_shape(src.peek()[1]) == shape:
                     files, frames = src.pop()
-                    plates = plates_of(frames)
                     for s in range(0, len(frames), eng.B):
-                        inflight.append((files[s:s + eng.B], plates[s:s + eng.B]))
-                        yield frames[s:s + eng.B]
+                        part = frames[s:s + eng.B]
+                        inflight.append((files[s:s + eng.B], plate_pool.submit(_plates_of, plate_detector, part)))
+                        yield part
 
             def plate_boxes():                       # run() asks for these right after it took the batch
                 while True:
                     yield inflight[-1][1]
 
-            for out, boxes in sa.run(device_batches(), plate_boxes(), copy_out=True):
-                files, plates = inflight.popleft()
-                emit(files, list(out))
-                n_frames += len(files)
-                n_faces += sum(len(b) for b in boxes)
-                n_plates += sum(len(p) for p in plates)
+            try:
+                for out, boxes in sa.run(device_batches(), plate_boxes(), copy_out=True):
+                    files, pf = inflight.popleft()
+                    plates = pf.result()
+                    emit(files, list(out))
+                    n_frames += len(files)
+                    n_faces += sum(len(b) for b in boxes)
+                    n_plates += sum(len(p) for p in plates)
+            except Exception as e:                                                   # noqa: BLE001 (reference :226)
+                failed(f"{len(inflight)} batch(es) in flight", e)
+                inflight.clear()
         for f in saves:
             f.result()
     return n_frames, n_faces, n_plates

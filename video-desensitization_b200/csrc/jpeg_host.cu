@@ -78,8 +78,14 @@ inline int rd16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 
 // returns VD_OK or an error code with the message set
 int parse(const uint8_t* d, size_t n, Parsed& P) {
+  // P is a thread_local scratch object reused across calls: EVERY piece of per-file state is reset here, so a file
+  // without a DHT segment (abbreviated MJPEG frames) can never be decoded with the previous file's Huffman tables
   memset(&P.info, 0, sizeof(P.info));
   memset(P.have_qt, 0, sizeof(P.have_qt));
+  for (int i = 0; i < 4; ++i) P.dc[i].present = P.ac[i].present = false;
+  for (int i = 0; i < 3; ++i) P.tq[i] = P.td[i] = P.ta[i] = 0;
+  P.scan = nullptr;
+  P.scan_size = 0;
   VD_REQUIRE(d && n >= 4 && d[0] == 0xFF && d[1] == 0xD8, "vd_jpeg: not a JPEG stream");
   size_t pos = 2;
   bool have_sof = false;
@@ -152,11 +158,14 @@ int parse(const uint8_t* d, size_t n, Parsed& P) {
         vd_set_error("vd_jpeg: non-interleaved scans are not supported");
         return VD_ERR_UNSUPPORTED;
       }
+      bool named[3] = {false, false, false};
       for (int s = 0; s < P.info.ncomp; ++s) {
         int c = -1;
         for (int q = 0; q < P.info.ncomp; ++q)
           if (cid[q] == seg[1 + 2 * s]) c = q;
         VD_REQUIRE(c >= 0, "vd_jpeg: scan names an unknown component");
+        VD_REQUIRE(!named[c], "vd_jpeg: scan names a component twice");
+        named[c] = true;
         P.td[c] = seg[2 + 2 * s] >> 4;
         P.ta[c] = seg[2 + 2 * s] & 15;
         VD_REQUIRE(P.td[c] < 4 && P.ta[c] < 4 && P.dc[P.td[c]].present && P.ac[P.ta[c]].present && P.have_qt[P.tq[c]],

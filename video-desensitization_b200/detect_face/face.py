@@ -47,13 +47,15 @@ class _NetHandle(object):
         if (H, W) != (o.input_shape[0], o.input_shape[1]):
             raise ValueError(f"network input {H}x{W} differs from input_shape {o.input_shape[:2]}")
         eng = o._engine_for(B)
+        if B > eng.B:
+            raise ValueError(f"batch {B} exceeds the engine batch {eng.B} (batch_size=...)")
         x0 = eng.buf["x0"]
         with torch.cuda.stream(eng.stream):
             eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
-            x0[:, :, 3:3 + W, :3] = x.to(eng.device).permute(0, 2, 3, 1).to(eng.act_dtype)
-            eng.enqueue_network()
+            x0[:B, :, 3:3 + W, :3] = x.to(eng.device).permute(0, 2, 3, 1).to(eng.act_dtype)
+            eng.enqueue_network()              # slots >= B keep whatever they held; their outputs are dropped below
         loc, cls, ldm = eng.head_tensors()
-        return loc, torch.softmax(cls, dim=-1), ldm
+        return loc[:B], torch.softmax(cls[:B], dim=-1), ldm[:B]
 
 
 class Retinaface(object):
@@ -103,14 +105,29 @@ class Retinaface(object):
         self.net = _NetHandle(self)
         print(f'Model {self.model_path if self.state_dict is None else "<state_dict>"} loaded.')
 
-    def _engine_for(self, batch):
-        b = int(self.batch_size or batch)
-        if b not in self._engines:
+    _MAX_ENGINES = 2          # a replica holds the packed weights and every activation buffer (GBs at 16 x 1280^2)
+
+    def _engine_for(self, batch, exact=False):
+        """The engine that runs `batch` frames.  An engine is built for a fixed batch (`batch_size` if given, else the
+        first batch seen) and REUSED for every shorter batch — the callers pad (detect_rows) or slice (net) — so the
+        tail batch of a directory does not build a second replica.  Only a LARGER batch (or exact=True: get_FPS times
+        a one-image forward) builds a new engine; at most _MAX_ENGINES are kept, the least recently used is freed."""
+        want = int(self.batch_size or batch)
+        fit = [b for b in self._engines if (b == want if exact else b >= want)]
+        if fit:
+            b = min(fit)
+        else:
+            while len(self._engines) >= self._MAX_ENGINES:
+                old = self._engines.pop(next(iter(self._engines)))       # dicts keep insertion (= LRU, see below) order
+                del old
+                torch.cuda.empty_cache()
+            b = want
             self._engines[b] = DetectorEngine(self._sd, b, self.input_shape[0], self.input_shape[1], device=self.device,
                                               confidence=self.confidence, nms_iou=self.nms_iou, cand_cap=self.cand_cap,
                                               max_det=self.max_det, precision=self.precision,
                                               backbone="mobilenet" if self.backbone == "mobilenet" else "resnet50")
-        eng = self._engines[b]
+        eng = self._engines.pop(b)
+        self._engines[b] = eng               # most recently used last
         eng.confidence, eng.nms_iou = float(self.confidence), float(self.nms_iou)
         return eng
 
@@ -185,7 +202,7 @@ class Retinaface(object):
         """seconds per network forward on one image (reference face.py:155-180), device-synchronised."""
         image = np.asarray(image)
         x, _ = self.preprocess([image.astype(np.uint8)])
-        eng = self._engine_for(1)
+        eng = self._engine_for(1, exact=self.batch_size is None)      # a one-image forward, as the reference times it
         for _ in range(10):
             self.net(x)
         eng.stream.synchronize()
@@ -197,7 +214,11 @@ class Retinaface(object):
         return (time.time() - t1) / test_interval
 
     def get_map_txt(self, image):
-        """(M,15) numpy in pixels of the original image (reference face.py:185-230)."""
+        """(M,15) numpy in pixels of the original image (reference face.py:185-230).
+        Deviation: the reference letterboxes the float32 image here (face.py:196-203, cv2.resize on float data);
+        this path casts to uint8 first and uses the same fixed-point uint8 resize as detect_images.  For uint8
+        input at the network's own size the two agree exactly; with a real down-scale they differ by < 1 grey level
+        per pixel (float bilinear vs cv2's 11-bit fixed point), which moves scores in the 4th decimal."""
         image = np.asarray(image)
         ih, iw = image.shape[:2]
         rows, counts = self.detect_rows([image.astype(np.uint8)])

@@ -115,17 +115,29 @@ def precision_of(dtype) -> str:
     return "fp16" if dtype == torch.float16 else "bf16"
 
 
-def last_error() -> str:
+def last_error(l=None) -> str:
+    """message of the last failure on this thread IN LIBRARY `l` (each .so keeps its own thread-local string,
+    so the caller passes the library whose entry point returned the status; default = the bf16 library)"""
     buf = C.create_string_buffer(512)
-    lib().vd_last_error(buf, 512)
+    (l if l is not None else lib()).vd_last_error(buf, 512)
     return buf.value.decode("utf-8", "replace")
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", l=None):
     """reference behaviour at the boundary: Python exceptions, never an abort (combine_detect.py:226-228
-    catches Exception and skips the batch)."""
+    catches Exception and skips the batch).  `l` = the library that produced `rc`."""
     if rc != 0:
-        raise RuntimeError(f"libvdesens {what} failed (status {rc}): {last_error()}")
+        raise RuntimeError(f"libvdesens {what} failed (status {rc}): {last_error(l)}")
+
+
+def mode_id(mode: str) -> int:
+    """"mosaic" (reference combine_detect.py:138-161) or "gauss" (north_star's cv2.GaussianBlur idiom); anything
+    else is an error — a typo must not silently change the anonymisation method"""
+    if mode == "mosaic":
+        return VD_MODE_MOSAIC
+    if mode == "gauss":
+        return VD_MODE_GAUSS
+    raise ValueError(f"mode must be 'mosaic' or 'gauss', got {mode!r}")
 
 
 def gaussian_taps_q8(ksize: int, sigma: float = 0.0):

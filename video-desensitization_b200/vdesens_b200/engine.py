@@ -77,7 +77,7 @@ class DetectorEngine:
         self.launches_per_forward = 0
         with torch.cuda.device(self.device):
             sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
-            _lib.check(self.lib.vd_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), "vd_device_info")
+            self._check(self.lib.vd_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), "vd_device_info")
             if mj.value != 10:
                 raise RuntimeError(f"libvdesens is built for sm_100a only; device is sm_{mj.value}{mn.value}")
             self.sm_count = sm.value
@@ -266,9 +266,12 @@ class DetectorEngine:
         self.status_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
         self.launches_per_forward = 1 + sum(1 for p in self.plans) + 1 + 3
 
+    def _check(self, rc, what):
+        _lib.check(rc, what, self.lib)
+
     def _make_plan(self, d, name):
         h = C.c_void_p()
-        _lib.check(self.lib.vd_conv_plan_create(C.byref(d), C.byref(h)), f"vd_conv_plan_create({name})")
+        self._check(self.lib.vd_conv_plan_create(C.byref(d), C.byref(h)), f"vd_conv_plan_create({name})")
         self._plan_handles.append(h)
         return h
 
@@ -279,7 +282,7 @@ class DetectorEngine:
             if kind != "conv":
                 continue
             v = [C.c_int() for _ in range(6)]
-            _lib.check(self.lib.vd_conv_plan_info(h, *[C.byref(x) for x in v]), "vd_conv_plan_info")
+            self._check(self.lib.vd_conv_plan_info(h, *[C.byref(x) for x in v]), "vd_conv_plan_info")
             out.append((name,) + tuple(x.value for x in v))
         return out
 
@@ -356,20 +359,20 @@ class DetectorEngine:
     def enqueue_ingest(self):
         s = C.c_void_p(self.stream.cuda_stream)
         fn = self.lib.vd_ingest_u8hwc_identity if self.identity else self.lib.vd_ingest_u8hwc
-        _lib.check(fn(_ptr(self.frame_desc), self.B, _ptr(self.buf["x0"]), self.H, self.W, self._mean, s), "vd_ingest")
+        self._check(fn(_ptr(self.frame_desc), self.B, _ptr(self.buf["x0"]), self.H, self.W, self._mean, s), "vd_ingest")
 
     @_on_device
     def enqueue_network(self, upto=None):
         s = C.c_void_p(self.stream.cuda_stream)
         for kind, h, name in self.plans:
             if kind == "conv":
-                _lib.check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
+                self._check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
             elif kind == "dwpw":
                 op = h
                 wd, bd, sd = self.w[op.name + ".dw"]
                 wp, bp, sp = self.w[op.name + ".pw"]
                 hh, ww, cc = self.buf_hw[op.src]
-                _lib.check(self.lib.vd_mnet_dwpw(_ptr(self.buf[op.src]), _ptr(wd), _ptr(bd), _ptr(sd), _ptr(wp), _ptr(bp),
+                self._check(self.lib.vd_mnet_dwpw(_ptr(self.buf[op.src]), _ptr(wd), _ptr(bd), _ptr(sd), _ptr(wp), _ptr(bp),
                                                  _ptr(sp), _ptr(self.buf[op.dst]), self.B, hh, ww, op.cin, op.cout,
                                                  op.stride, s), f"vd_mnet_dwpw({name})")
             elif kind in ("stem", "dw", "pw"):
@@ -383,19 +386,19 @@ class DetectorEngine:
                     rc = self.lib.vd_mnet_dw3x3(x, _ptr(wt), _ptr(bt), _ptr(st), y, self.B, hh, ww, cc, op.stride, s)
                 else:
                     rc = self.lib.vd_mnet_pw(x, _ptr(wt), _ptr(bt), _ptr(st), y, self.B * hh * ww, op.cin, op.cout, s)
-                _lib.check(rc, f"vd_mnet_{kind}({name})")
+                self._check(rc, f"vd_mnet_{kind}({name})")
             else:
                 src, dst = h
                 hh, ww, cc = self.buf_hw[src]
                 pool = self.lib.vd_maxpool3x3s2_split if self.split else self.lib.vd_maxpool3x3s2
-                _lib.check(pool(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s), "vd_maxpool3x3s2")
+                self._check(pool(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s), "vd_maxpool3x3s2")
             if upto is not None and name == upto:
                 break
 
     @_on_device
     def enqueue_postprocess(self):
         s = C.c_void_p(self.stream.cuda_stream)
-        _lib.check(self.lib.vd_decode_threshold(_ptr(self.heads[0]), _ptr(self.heads[1]), _ptr(self.heads[2]),
+        self._check(self.lib.vd_decode_threshold(_ptr(self.heads[0]), _ptr(self.heads[1]), _ptr(self.heads[2]),
                                                 self.B, self.H, self.W, self.confidence, self.cap, _ptr(self.cand),
                                                 _ptr(self.cand_count), _ptr(self.status), s), "vd_decode_threshold")
         self.enqueue_nms()
@@ -403,23 +406,23 @@ class DetectorEngine:
     @_on_device
     def enqueue_nms(self):
         s = C.c_void_p(self.stream.cuda_stream)
-        _lib.check(self.lib.vd_nms_batched(_ptr(self.cand), _ptr(self.cand_count), self.B, self.cap, self.nms_iou,
+        self._check(self.lib.vd_nms_batched(_ptr(self.cand), _ptr(self.cand_count), self.B, self.cap, self.nms_iou,
                                            _ptr(self.unlb), self.max_det, _ptr(self.out_rows), _ptr(self.out_count),
                                            _ptr(self.status), _ptr(self.nms_ws), self.nms_ws_bytes, s), "vd_nms_batched")
 
     @_on_device
     def enqueue_composite(self, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, use_faces=True, use_ext=True):
         s = C.c_void_p(self.stream.cuda_stream)
-        m = _lib.VD_MODE_MOSAIC if mode == "mosaic" else _lib.VD_MODE_GAUSS
+        m = _lib.mode_id(mode)
         taps = None
         if m == _lib.VD_MODE_GAUSS:
             key = (int(ksize), float(sigma))
             if getattr(self, "_taps_key", None) != key:
                 arr = (C.c_uint16 * 256)()
-                _lib.check(self.lib.vd_gaussian_taps_q8(int(ksize), float(sigma), arr), "vd_gaussian_taps_q8")
+                self._check(self.lib.vd_gaussian_taps_q8(int(ksize), float(sigma), arr), "vd_gaussian_taps_q8")
                 self._taps, self._taps_key = arr, key
             taps = self._taps
-        _lib.check(self.lib.vd_composite_rois(
+        self._check(self.lib.vd_composite_rois(
             _ptr(self.frame_desc), self.B,
             _ptr(self.out_rows) if use_faces else None, _ptr(self.out_count) if use_faces else None, self.max_det,
             _ptr(self.ext_boxes) if use_ext else None, _ptr(self.ext_count) if use_ext else None, self.max_ext,
@@ -462,7 +465,8 @@ class DetectorEngine:
 
     def check_status(self, st):
         if st:
-            self.status.zero_()
+            with torch.cuda.stream(self.stream):       # ordered with the batches already queued on the engine stream
+                self.status.zero_()
             msgs = []
             if st & _lib.VD_STAT_CAND_OVERFLOW:
                 msgs.append(f"more than cand_cap={self.cap} candidates above the confidence threshold in a frame")

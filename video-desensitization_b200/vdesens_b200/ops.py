@@ -65,7 +65,7 @@ def ingest(frames, H, W, identity=None, precision="bf16"):
     if identity is None:
         identity = all(f.shape[0] == H and f.shape[1] == W for f in frames)
     fn = lib.vd_ingest_u8hwc_identity if identity else lib.vd_ingest_u8hwc
-    _lib.check(fn(_p(desc), B, _p(x0), H, W, (C.c_float * 3)(*MEAN), _stream()), "vd_ingest_u8hwc")
+    _lib.check(fn(_p(desc), B, _p(x0), H, W, (C.c_float * 3)(*MEAN), _stream()), "vd_ingest_u8hwc", lib)
     return x0
 
 
@@ -76,8 +76,7 @@ def ingest_nchw_f32(frames, H, W):
     B = len(frames)
     desc = frame_descriptors(frames)
     out = torch.empty((B, 3, H, W), dtype=torch.float32, device=frames[0].device)
-    _lib.check(lib.vd_ingest_u8hwc_nchw_f32(_p(desc), B, _p(out), H, W, (C.c_float * 3)(*MEAN), _stream()),
-               "vd_ingest_u8hwc_nchw_f32")
+    _lib.check(lib.vd_ingest_u8hwc_nchw_f32(_p(desc), B, _p(out), H, W, (C.c_float * 3)(*MEAN), _stream()), "vd_ingest_u8hwc_nchw_f32", lib)
     return out
 
 
@@ -143,9 +142,9 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
     d.upadd = upadd.data_ptr() if upadd is not None else None
     d.y = out.data_ptr()
     h = C.c_void_p()
-    _lib.check(lib.vd_conv_plan_create(C.byref(d), C.byref(h)), "vd_conv_plan_create")
+    _lib.check(lib.vd_conv_plan_create(C.byref(d), C.byref(h)), "vd_conv_plan_create", lib)
     try:
-        _lib.check(lib.vd_conv_run(h, _stream()), "vd_conv_run")
+        _lib.check(lib.vd_conv_run(h, _stream()), "vd_conv_run", lib)
     finally:
         lib.vd_conv_plan_destroy(h)
     return out if out2 is None else (out, out2)
@@ -156,7 +155,7 @@ def mnet_stem(x0, w, bias, slope, H, W):
     """conv_bn(3, 8, stride 2) of the MobileNet0.25 variant on the ingest tensor (reference mobilenet025.py:3-8)."""
     lib = _lib.lib(_lib.precision_of(x0.dtype))
     y = torch.empty((x0.shape[0], (H + 1) // 2, (W + 1) // 2, 8), dtype=x0.dtype, device=x0.device)
-    _lib.check(lib.vd_mnet_stem(_p(x0), _p(w), _p(bias), _p(slope), _p(y), x0.shape[0], H, W, _stream()), "vd_mnet_stem")
+    _lib.check(lib.vd_mnet_stem(_p(x0), _p(w), _p(bias), _p(slope), _p(y), x0.shape[0], H, W, _stream()), "vd_mnet_stem", lib)
     return y
 
 
@@ -166,7 +165,7 @@ def mnet_dw3x3(x, w, bias, slope, stride):
     lib = _lib.lib(_lib.precision_of(x.dtype))
     B, H, W, Cc = x.shape
     y = torch.empty((B, (H + stride - 1) // stride, (W + stride - 1) // stride, Cc), dtype=x.dtype, device=x.device)
-    _lib.check(lib.vd_mnet_dw3x3(_p(x), _p(w), _p(bias), _p(slope), _p(y), B, H, W, Cc, stride, _stream()), "vd_mnet_dw3x3")
+    _lib.check(lib.vd_mnet_dw3x3(_p(x), _p(w), _p(bias), _p(slope), _p(y), B, H, W, Cc, stride, _stream()), "vd_mnet_dw3x3", lib)
     return y
 
 
@@ -178,7 +177,7 @@ def mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride):
     Cout = wpw.shape[1]
     y = torch.empty((B, (H + stride - 1) // stride, (W + stride - 1) // stride, Cout), dtype=x.dtype, device=x.device)
     _lib.check(lib.vd_mnet_dwpw(_p(x), _p(wdw), _p(bdw), _p(sdw), _p(wpw), _p(bpw), _p(spw), _p(y), B, H, W, Cin, Cout,
-                                stride, _stream()), "vd_mnet_dwpw")
+                                stride, _stream()), "vd_mnet_dwpw", lib)
     return y
 
 
@@ -189,7 +188,7 @@ def mnet_pw(x, w, bias, slope):
     B, H, W, Cin = x.shape
     Cout = w.shape[1]
     y = torch.empty((B, H, W, Cout), dtype=x.dtype, device=x.device)
-    _lib.check(lib.vd_mnet_pw(_p(x), _p(w), _p(bias), _p(slope), _p(y), B * H * W, Cin, Cout, _stream()), "vd_mnet_pw")
+    _lib.check(lib.vd_mnet_pw(_p(x), _p(w), _p(bias), _p(slope), _p(y), B * H * W, Cin, Cout, _stream()), "vd_mnet_pw", lib)
     return y
 
 
@@ -198,7 +197,7 @@ def maxpool3x3s2(x):
     lib = _lib.lib(_lib.precision_of(x.dtype))
     B, H, W, Cc = x.shape
     y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, Cc), dtype=x.dtype, device=x.device)
-    _lib.check(lib.vd_maxpool3x3s2(_p(x), _p(y), B, H, W, Cc, _stream()), "vd_maxpool3x3s2")
+    _lib.check(lib.vd_maxpool3x3s2(_p(x), _p(y), B, H, W, Cc, _stream()), "vd_maxpool3x3s2", lib)
     return y
 
 
@@ -211,8 +210,7 @@ def decode_threshold_lcl(loc, conf, landms, H, W, conf_thr, cap=4096):
     count = torch.zeros((B,), dtype=torch.int32, device=loc.device)
     status = torch.zeros((1,), dtype=torch.int32, device=loc.device)
     _lib.check(lib.vd_decode_threshold_lcl(_p(loc.contiguous()), _p(conf.contiguous()), _p(landms.contiguous()), B,
-                                           H, W, float(conf_thr), cap, _p(cand), _p(count), _p(status), _stream()),
-               "vd_decode_threshold_lcl")
+                                           H, W, float(conf_thr), cap, _p(cand), _p(count), _p(status), _stream()), "vd_decode_threshold_lcl", lib)
     return cand, count, status
 
 
@@ -225,7 +223,7 @@ def decode_threshold_heads(heads, H, W, conf_thr, cap=4096):
     count = torch.zeros((B,), dtype=torch.int32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
     _lib.check(lib.vd_decode_threshold(_p(heads[0]), _p(heads[1]), _p(heads[2]), B, H, W, float(conf_thr), cap,
-                                       _p(cand), _p(count), _p(status), _stream()), "vd_decode_threshold")
+                                       _p(cand), _p(count), _p(status), _stream()), "vd_decode_threshold", lib)
     return cand, count, status
 
 
@@ -255,7 +253,7 @@ def nms(cand, count, iou_thr, unlb, max_det=1024):
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     unlb_t = torch.as_tensor(np.asarray(unlb, np.float32)).to(dev)
     _lib.check(lib.vd_nms_batched(_p(cand), _p(count), B, cap, float(iou_thr), _p(unlb_t), max_det, _p(rows),
-                                  _p(out_count), _p(status), _p(ws), nbytes, _stream()), "vd_nms_batched")
+                                  _p(out_count), _p(status), _p(ws), nbytes, _stream()), "vd_nms_batched", lib)
     return rows, out_count, status
 
 
@@ -282,14 +280,13 @@ def composite(frames, ext_boxes, mode="mosaic", mosaic_level=8, ksize=31, sigma=
     px = int(scratch_frames * max(f.shape[0] * f.shape[1] for f in frames))
     nbytes = int(lib.vd_composite_workspace_bytes(B, max_det + max_ext, px))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    m = _lib.VD_MODE_MOSAIC if mode == "mosaic" else _lib.VD_MODE_GAUSS
+    m = _lib.mode_id(mode)
     taps = None
     if m == _lib.VD_MODE_GAUSS:
         taps = (C.c_uint16 * 256)()
-        _lib.check(lib.vd_gaussian_taps_q8(int(ksize), float(sigma), taps), "vd_gaussian_taps_q8")
+        _lib.check(lib.vd_gaussian_taps_q8(int(ksize), float(sigma), taps), "vd_gaussian_taps_q8", lib)
     _lib.check(lib.vd_composite_rois(_p(desc), B, _p(det_rows), _p(det_count), max_det, _p(eb_t), _p(ec_t), max_ext, m,
-                                     int(mosaic_level), taps, int(ksize), _p(status), _p(ws), nbytes, _stream()),
-               "vd_composite_rois")
+                                     int(mosaic_level), taps, int(ksize), _p(status), _p(ws), nbytes, _stream()), "vd_composite_rois", lib)
     torch.cuda.current_stream().synchronize()       # ws / desc are freed on return
     st = int(status.item())
     if st:

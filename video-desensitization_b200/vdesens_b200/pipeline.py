@@ -6,12 +6,14 @@ combine_detect.py:204-256 (detect_images, box merge with int() truncation, seque
 import numpy as np
 import torch
 
+from . import _lib
 from .engine import DetectorEngine
 
 
 class Anonymizer:
     def __init__(self, engine: DetectorEngine, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0):
         self.eng = engine
+        _lib.mode_id(mode)                     # ValueError on anything but "mosaic" / "gauss"
         self.mode, self.mosaic_level, self.ksize, self.sigma = mode, int(mosaic_level), int(ksize), float(sigma)
         self._pin_in = self._pin_out = self._dev = None
 
@@ -77,6 +79,7 @@ class _Slot:
         self.ev_done = torch.cuda.Event()
         self.ev_out = torch.cuda.Event()
         self.n = 0
+        self.ext = None
         self.busy = False
 
 
@@ -88,6 +91,7 @@ class StreamingAnonymizer:
 
     def __init__(self, engine: DetectorEngine, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0, depth=2):
         self.eng = engine
+        _lib.mode_id(mode)                     # ValueError on anything but "mosaic" / "gauss"
         self.mode, self.mosaic_level, self.ksize, self.sigma = mode, int(mosaic_level), int(ksize), float(sigma)
         self.depth = max(2, int(depth))
         self.slots = None
@@ -122,6 +126,17 @@ class StreamingAnonymizer:
                 pi[i] = batch[min(i, n - 1)]
             src = slot.pin_in
         slot.n = n
+        with torch.cuda.stream(self.s_in):
+            slot.dev.copy_(src, non_blocking=True)                # H2D
+            slot.ev_in.record(self.s_in)
+        eng.stream.wait_event(slot.ev_in)
+        eng.bind_frames_async(slot.desc, slot.unlb, slot.identity)
+        eng.forward()
+        # The external (plate) boxes are only needed by the compositing pass, so a provider that is still running —
+        # a Future, as combine_detect hands over: the reference runs the plate model on a sibling thread of the face
+        # detector (combine_detect.py:214-217) — is waited for AFTER the detector has been enqueued.
+        if hasattr(ext, "result"):
+            ext = ext.result()
         eb, ec = slot.eb.numpy(), slot.ec.numpy()
         ec[:] = 0
         for i, bl in enumerate(ext or []):
@@ -130,13 +145,8 @@ class StreamingAnonymizer:
             ec[i] = len(bl)
             for j, b in enumerate(bl):
                 eb[i, j] = [int(v) for v in b]
-        with torch.cuda.stream(self.s_in):
-            slot.dev.copy_(src, non_blocking=True)                # H2D
-            slot.ev_in.record(self.s_in)
-        eng.stream.wait_event(slot.ev_in)
-        eng.bind_frames_async(slot.desc, slot.unlb, slot.identity)
+        slot.ext = ext
         eng.upload_ext_async(slot.eb, slot.ec)
-        eng.forward()
         eng.enqueue_composite(self.mode, self.mosaic_level, self.ksize, self.sigma)
         eng.download_results_async(slot.rows, slot.counts, slot.status)
         slot.ev_done.record(eng.stream)
