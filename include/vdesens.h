@@ -86,6 +86,12 @@ int vd_ingest_u8hwc(const vd_frame_t* frames, int B, void* x0, int H, int W,
 int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x0, int H, int W,
                              const float mean[3], vd_stream_t stream);
 
+/* vd_ingest_u8hwc_identity that also copies frame i into frames_out[i] (same h and w; pitches may differ) while it
+ * has the bytes on chip: the reference's `img_with_mosaic = img.copy()` (combine_detect.py:247) fused into the
+ * ingest pass, so that compositing can run in place on the copy and the caller's frames stay untouched. */
+int vd_ingest_u8hwc_identity_copy(const vd_frame_t* frames, const vd_frame_t* frames_out, int B, void* x0,
+                                  int H, int W, const float mean[3], vd_stream_t stream);
+
 /* Optional fp32 NCHW output identical to Retinaface.preprocess()'s tensor (face.py:87). */
 int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H, int W,
                              const float mean[3], vd_stream_t stream);
@@ -119,6 +125,11 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
                                   last to the first.  A layer that reads what its predecessor has JUST written finds the
                                   tail of that tensor still in the 126 MB L2 if it starts there; the executor alternates
                                   the direction along the layer chain.  Ignored with VD_CONV_CHAIN / VD_CONV_POOL */
+#define VD_CONV_TWO_DST 2048u  /* two sibling layers that read the same tensor run as ONE convolution over the concatenated
+                                  filters (Cout = Cout1 + Cout2 in {128, 192}): output channels [0, Cout1) go to y
+                                  (dst_C, dst_coff), channels [Cout1, Cout) to y_b (dst_b_C, dst_b_coff).  The SSH module's
+                                  conv3X3 + conv5X5_1 and conv5X5_2 + conv7X7_2 (reference nets/layers.py:54-66);
+                                  bit-identical to the two launches */
 #define VD_CONV_DUAL 32u       /* second K segment: + 1x1 conv (stride2) of tensor x2 accumulated into
                                   the same output (bottleneck conv3 + downsample projection fused) */
 
@@ -148,6 +159,13 @@ typedef struct vd_conv_desc {
   const float* chain_bias;
   void* chain_y;
   int32_t chain_Cout;
+  /* VD_CONV_SPLIT: the packed weights are w * 2^k (k per layer, so that the lo plane stays a normal fp16 number);
+     the accumulators are multiplied by acc_scale = 2^-k before the bias is added.  0 means 1.0 */
+  float acc_scale;
+  /* VD_CONV_TWO_DST */
+  void* y_b;                 /* [dev] second destination, [B][Hout][Wout][dst_b_C] in the activation type */
+  int32_t Cout1;             /* channels of the first layer */
+  int32_t dst_b_C, dst_b_coff;
 } vd_conv_desc_t;
 
 typedef struct vd_conv_plan vd_conv_plan_t;

@@ -4,6 +4,8 @@
     python oracle/make_golden.py            # writes  video-desensitization_b200/vdesens_b200/data/bn_calib{,_mnet}_seed0.npz
                                             #         tests/golden/{ref_detect,ref_detect_mnet,nms,cv}_golden.npz
     python oracle/make_golden.py --mnet-only   # only the MobileNet0.25 files
+    python oracle/make_golden.py --default-only  # only the un-conditioned default-init files (bn_calib_default_seed0.npz,
+                                               #         tests/golden/ref_detect_default_golden.npz)
 
 The GPU box has no /root/reference; tests there read only the committed .npz files.
 """
@@ -27,9 +29,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 RATES = {"r01": 0.01, "dense": 0.0025, "r001": 0.001}
 
 
-def make_bn_calib():
-    """BN statistics of the seed-0 random init on a 4-frame synthetic batch + class-bias shifts."""
-    sd = ro.to_torch_sd(synth._raw_state_dict(0))
+def make_bn_calib(init="conditioned"):
+    """BN statistics of the seed-0 random init on a 4-frame synthetic batch + class-bias shifts.
+    init="default": the un-conditioned default initialisation (gamma = 1, beta = 0 everywhere)."""
+    sd = ro.to_torch_sd(synth._raw_state_dict(0, init=init))
     frames = synth.synthetic_clip(4, 480, 640, base_seed=7000)
     x, _ = ro.preprocess(frames, (480, 640))
     ro.forward(sd, x, calibrate=True)
@@ -47,9 +50,32 @@ def make_bn_calib():
     for name, rate in RATES.items():
         sh = [-float(np.quantile(torch.cat(ds[l]).numpy().astype(np.float64), 1 - rate)) for l in range(3)]
         out["shift." + name] = np.array(sh, np.float32)
-    os.makedirs(os.path.dirname(synth.BN_CALIB_FILE), exist_ok=True)
-    np.savez_compressed(synth.BN_CALIB_FILE, **out)
-    print("wrote", synth.BN_CALIB_FILE, os.path.getsize(synth.BN_CALIB_FILE), "bytes")
+    path = synth.BN_CALIB_FILE if init == "conditioned" else synth.BN_CALIB_FILE_DEFAULT
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def make_ref_detect_default(ref_face):
+    """the UNMODIFIED reference on the un-conditioned default-init weights (one small case: pins the oracle on them)"""
+    sd = synth.synthetic_state_dict(0, face_rate="r01", init="default")
+    tmp = tempfile.mkdtemp()
+    pth = os.path.join(tmp, "w_default.pth")
+    synth.save_state_dict_pth(sd, pth)
+    frames = [synth.synthetic_frame(96, 128, 9000), synth.synthetic_frame(96, 128, 9001)]
+    det = ref_face.Retinaface(model_path=pth, backbone="resnet50", input_shape=[96, 128, 3], confidence=0.5, nms_iou=0.4,
+                              letterbox_image=True, cuda=False)
+    x, shapes = det.preprocess(frames)
+    with torch.no_grad():
+        loc, conf, landms = det.net(x)
+        rows = det.postprocess(loc, conf, landms, shapes, len(frames))
+    out = {"native.frames": np.array([(96, 128, 9000), (96, 128, 9001)], np.int64),
+           "native.input_shape": np.array([96, 128, 3], np.int64),
+           "native.loc": loc.numpy(), "native.conf": conf.numpy(), "native.landms": landms.numpy()}
+    for i, r in enumerate(rows):
+        out[f"native.rows{i}"] = r.numpy().astype(np.float32).reshape(-1, 15)
+    print("default-init native kept per frame:", [len(r) for r in rows])
+    np.savez_compressed(os.path.join(GOLD, "ref_detect_default_golden.npz"), **out)
 
 
 def make_ref_detect(ref_face):
@@ -203,12 +229,18 @@ if __name__ == "__main__":
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLD, exist_ok=True)
     ref_face, ref_combine = load_reference()
+    if "--default-only" in sys.argv:
+        make_bn_calib("default")
+        make_ref_detect_default(ref_face)
+        sys.exit(0)
     if "--mnet-only" in sys.argv:
         make_bn_calib_mnet()
         make_ref_detect_mnet(ref_face)
         sys.exit(0)
     make_bn_calib()
     make_ref_detect(ref_face)
+    make_bn_calib("default")
+    make_ref_detect_default(ref_face)
     make_bn_calib_mnet()
     make_ref_detect_mnet(ref_face)
     make_nms()

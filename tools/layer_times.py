@@ -17,7 +17,7 @@ W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 
 sd = synth.synthetic_state_dict(0, face_rate="r01")
-eng = DetectorEngine(sd, B, H, W)
+eng = DetectorEngine(sd, B, H, W, precision=os.environ.get("VD_PRECISION", "bf16"))
 frames = torch.stack([torch.from_numpy(synth.synthetic_frame(H, W, 1000 + i)) for i in range(B)]).cuda()
 eng.set_frames(frames)
 eng.forward()
@@ -34,7 +34,7 @@ with torch.cuda.stream(eng.stream):
         e0.record(eng.stream)
         for _ in range(reps):
             if kind == "conv":
-                _lib.check(eng.lib.vd_conv_run(h, s))
+                _lib.check(eng.lib.vd_conv_run(h, s), "vd_conv_run", eng.lib)
             else:
                 src, dst = h
                 hh, ww, cc = eng.buf_hw[src]
@@ -52,7 +52,7 @@ with torch.cuda.stream(eng.stream):
         rows.append((name, ms))
 # flops per layer from output extents
 out_hw = {}
-_, ops_, _ = arch.build_graph(fuse_stem_pool=eng.fuse_stem_pool, fuse_chain=eng.fuse_chain)
+_, ops_, _ = arch.build_graph(fuse_stem_pool=eng.fuse_stem_pool, fuse_chain=eng.fuse_chain, fuse_siblings=eng.fuse_siblings)
 chained = {}
 for op in ops_:
     if op.kind == "conv":
@@ -61,6 +61,9 @@ for op in ops_:
         if op.chain is not None:          # the kernel also runs the next 1x1 convolution
             flops[op.conv.name] += flops[op.chain.name]
             chained[op.conv.name] = op.chain.name
+        if op.sibling is not None:        # one GEMM over the concatenated filters of two sibling layers
+            flops[op.conv.name] += flops[op.sibling.name]
+            chained[op.conv.name] = op.sibling.name
 print(f"B={B} {H}x{W}  sum of per-layer times {tot:.3f} ms  ({B / tot * 1e3:.1f} frames/s network-only)")
 for name, ms in rows:
     if name in flops and name in out_hw:

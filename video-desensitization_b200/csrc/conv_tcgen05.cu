@@ -64,6 +64,9 @@ struct ConvKParams {
   const __nv_bfloat16* residual;
   const __nv_bfloat16* upadd;
   void* y;
+  float acc_scale;        // VD_CONV_SPLIT: accumulators are multiplied by this (a power of two) before the bias is added
+  int cout1;              // VD_CONV_TWO_DST: output channels >= cout1 go to the second destination (tmY2) ...
+  int dst_b_coff;         //                  ... starting at this channel of it
 };
 
 // RES = the layer adds a residual tensor: it is prefetched by a dedicated TMA warp into a ring of
@@ -82,7 +85,7 @@ struct ConvCfg {
   // 128 B, see hi_raw), fetched by ONE tensor-map box
   static constexpr int A_BYTES = (ROWB == 64) ? 7 * 17 * 128 + 128 : 128 * ROWB;
   static constexpr int B_BYTES = BN * ROWB;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 384;
   static constexpr int OUT_BYTES = 2 * 128 * 128;                             // two staging tiles for the TMA store
   static constexpr int RES_SLOTS = 3;
@@ -194,6 +197,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tma_prefetch_desc(&tmB2);
       tma_prefetch_desc(&tmY2);
     }
+    if (!CHAIN && p.cout1 > 0) tma_prefetch_desc(&tmY2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -693,6 +697,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float f[32];
         if (active) {
           tmem_ld_wait();
+          if (split) {             // weights were packed as w * 2^k so that their lo plane stays a NORMAL fp16 number
+            const float sc = p.acc_scale;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * sc);
+          }
           const uint32_t bp = smem_u32(sBias) + static_cast<uint32_t>(((CHAIN ? n_tile * BN : 0) + ch * 64 + half * 32) * 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -789,7 +798,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           named_bar_sync(1, kEpiThreads);
           if (issuer) {
             const int plane = p.dst_C / 3;
-            const int cch = p.dst_coff + n_tile * BN + ch * 64;
+            const int cch = p.dst_coff + n_tile * BN + ch * 64;      // (TWO_DST is not available in split mode)
             tma_store_4d(&tmY, sOut, cch, tx * p.TW, ty * p.TH, tb * p.NB);
             tma_store_4d(&tmY, sOut + 128 * 128, plane + cch, tx * p.TW, ty * p.TH, tb * p.NB);
             tma_store_4d(&tmY, sOut, 2 * plane + cch, tx * p.TW, ty * p.TH, tb * p.NB);
@@ -847,8 +856,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (ONE_BAR && issuer) tma_store_wait_read<0>();      // the other staging tile's store has read it
         named_bar_sync(1, kEpiThreads);
         if (issuer) {
-          const int cch = f32out ? 0 : (p.dst_coff + n_tile * BN + ch * 64);
-          tma_store_4d(&tmY, sbuf, cch, tx * p.TW, ty * p.TH, tb * p.NB);
+          const int oc = n_tile * BN + ch * 64;                  // first output channel of this chunk
+          if (!CHAIN && p.cout1 > 0 && oc >= p.cout1) {          // VD_CONV_TWO_DST: the sibling layer's tensor
+            tma_store_4d(&tmY2, sbuf, p.dst_b_coff + oc - p.cout1, tx * p.TW, ty * p.TH, tb * p.NB);
+          } else {
+            const int cch = f32out ? 0 : (p.dst_coff + oc);
+            tma_store_4d(&tmY, sbuf, cch, tx * p.TW, ty * p.TH, tb * p.NB);
+          }
           tma_store_commit();
           if (CHAIN) mbar_arrive(&ystaged[chunk_ctr & 1u]);    // the staged tile is also a K block of the chained GEMM
         }
@@ -1102,7 +1116,8 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
              "vd_conv_plan_create: tensors must be 16-byte aligned");
   const bool split_mode = (d->flags & VD_CONV_SPLIT) != 0;
   VD_REQUIRE(d->dst_coff % 32 == 0 && d->dst_C % 8 == 0 &&
-                 d->dst_coff + d->Cout <= ((split_mode && !(d->flags & VD_CONV_OUT_F32)) ? d->dst_C / 3 : d->dst_C),
+                 d->dst_coff + ((d->flags & VD_CONV_TWO_DST) ? d->Cout1 : d->Cout) <=
+                     ((split_mode && !(d->flags & VD_CONV_OUT_F32)) ? d->dst_C / 3 : d->dst_C),
              "vd_conv_plan_create: bad destination slice");
   VD_REQUIRE(!split_mode || !(d->flags & VD_CONV_DUAL), "vd_conv_plan_create: SPLIT and DUAL cannot be combined");
   VD_REQUIRE(!split_mode || (d->flags & VD_CONV_OUT_F32) || d->dst_C % 3 == 0,
@@ -1147,7 +1162,21 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     }
     BN = 128;                    // two N tiles per M tile: 2 x 128 + 2 x chain_Cout TMEM columns
   }
-  if (BN != 32 && BN != 64 && BN != 128 && BN != 256) {
+  const bool two_dst = (d->flags & VD_CONV_TWO_DST) != 0;
+  if (two_dst) {
+    // two sibling layers that read the same tensor, as ONE GEMM over the concatenated filters: Cout = Cout1 + Cout2
+    // in one N tile (128 or 192), so the A operand is fetched and streamed through the MMA once for both
+    if (chain || x0 || split_mode || (d->flags & (VD_CONV_OUT_F32 | VD_CONV_RESIDUAL | VD_CONV_UPADD | VD_CONV_DUAL | VD_CONV_POOL)) ||
+        (d->Cout != 128 && d->Cout != 192) || d->Cout1 <= 0 || d->Cout1 >= d->Cout || d->Cout1 % 64 != 0 || !d->y_b ||
+        (reinterpret_cast<uintptr_t>(d->y_b) & 15) != 0 || d->dst_b_coff % 64 != 0 || d->dst_b_C % 8 != 0 ||
+        d->dst_b_coff + (d->Cout - d->Cout1) > d->dst_b_C) {
+      delete pl;
+      vd_set_error("vd_conv_plan_create: VD_CONV_TWO_DST needs Cout in {128, 192}, Cout1 a multiple of 64 inside it, "
+                   "a 16-byte aligned y_b and a 64-aligned slice of it; no residual / upadd / dual / chain / fp32 out");
+      return VD_ERR_UNSUPPORTED;
+    }
+  }
+  if (BN != 32 && BN != 64 && BN != 128 && BN != 256 && !(BN == 192 && two_dst)) {
     delete pl;
     vd_set_error("vd_conv_plan_create: unsupported Cout=%d", d->Cout);
     return VD_ERR_UNSUPPORTED;
@@ -1180,7 +1209,9 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
     const bool legal = !x0 && d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1;
     const long generic_tiles = static_cast<long>(vd_cdiv(d->Wout, k.TW)) * vd_cdiv(d->Hout, k.TH) * vd_cdiv(d->B, k.NB);
     const long patch_tiles = static_cast<long>(vd_cdiv(d->Wout, 8)) * vd_cdiv(d->Hout, 16) * d->B;
-    const bool worth = BN <= 128 && patch_tiles * 4 <= generic_tiles * 5;      // <= 25 % more tiles
+    // (BN = 192 exists only for two sibling layers (TWO_DST), each of which runs in patch mode on its own: the fused
+    //  GEMM keeps their K order — cin block outer, taps inner — and so stays bit-identical to the two launches)
+    const bool worth = BN <= 192 && patch_tiles * 4 <= generic_tiles * 5;      // <= 25 % more tiles
     if (legal && (mode == 2 || (mode == 1 && worth))) {
       k.patch = 1;
       k.TW = 8; k.TH = 16; k.NB = 1;
@@ -1242,6 +1273,9 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   k.residual = static_cast<const __nv_bfloat16*>(d->residual);
   k.upadd = static_cast<const __nv_bfloat16*>(d->upadd);
   k.y = d->y;
+  k.acc_scale = (split_mode && d->acc_scale > 0.f) ? d->acc_scale : 1.0f;
+  k.cout1 = two_dst ? d->Cout1 : 0;
+  k.dst_b_coff = two_dst ? d->dst_b_coff : 0;
 
   // ---- A: activations ----
   cuuint64_t gdim[4], gstr[3];
@@ -1366,6 +1400,22 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   }
   pl->tmB2 = pl->tmB;
   pl->tmY2 = pl->tmY;
+  if (two_dst) {
+    const cuuint64_t c2 = static_cast<cuuint64_t>(d->dst_b_C);
+    cuuint64_t ydim2[4] = {c2, static_cast<cuuint64_t>(d->Wout), static_cast<cuuint64_t>(d->Hout),
+                           static_cast<cuuint64_t>(d->B)};
+    cuuint64_t ystr2[3] = {c2 * 2, c2 * 2 * d->Wout, c2 * 2 * d->Wout * d->Hout};
+    cuuint32_t ybox2[4] = {64, static_cast<cuuint32_t>(k.TW), static_cast<cuuint32_t>(k.TH),
+                           static_cast<cuuint32_t>(k.NB)};
+    cuuint32_t one4[4] = {1, 1, 1, 1};
+    r = enc(&pl->tmY2, kActTmapType, 4, d->y_b, ydim2, ystr2, ybox2, one4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vd_set_error("cuTensorMapEncodeTiled(second destination) failed: CUresult %d", (int)r);
+      delete pl;
+      return VD_ERR_CUDA;
+    }
+  }
   if (chain) {
     cuuint64_t wdim2[2] = {static_cast<cuuint64_t>(d->Cout), static_cast<cuuint64_t>(d->chain_Cout)};
     cuuint64_t wstr2[1] = {static_cast<cuuint64_t>(d->Cout) * 2};
@@ -1402,6 +1452,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
       case 32: ok = plan_occ<32, false>(pl, sms); break;
       case 64: ok = res ? plan_occ<64, true>(pl, sms) : plan_occ<64, false>(pl, sms); break;
       case 128: ok = res ? plan_occ<128, true>(pl, sms) : plan_occ<128, false>(pl, sms); break;
+      case 192: ok = plan_occ<192, false>(pl, sms); break;
       default: ok = res ? plan_occ<256, true>(pl, sms) : plan_occ<256, false>(pl, sms); break;
     }
     if (!ok) {
@@ -1472,6 +1523,7 @@ extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
     case 32: return launch_conv<32, false>(plan, st);
     case 64: return res ? launch_conv<64, true>(plan, st) : launch_conv<64, false>(plan, st);
     case 128: return res ? launch_conv<128, true>(plan, st) : launch_conv<128, false>(plan, st);
+    case 192: return launch_conv<192, false>(plan, st);
     case 256: return res ? launch_conv<256, true>(plan, st) : launch_conv<256, false>(plan, st);
   }
   vd_set_error("vd_conv_run: bad BN");

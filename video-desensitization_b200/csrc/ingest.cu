@@ -88,48 +88,102 @@ ingest_x0_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__ x0, 
 }
 
 // fast path: frame size == network input (BASELINE configs 2-5): no resize, no pad.
-// One thread = one 16-byte store = two x0 columns (2j, 2j+1), i.e. pixels 2j-3 and 2j-2: every store instruction of a
-// warp writes 512 contiguous bytes (whole 32-byte sectors; the first version's 8-byte stores at a 32-byte lane stride
-// wrote a quarter of a sector per instruction and reached 41 % of the HBM peak).  The six source bytes of a pair are
-// fetched with byte loads — any frame pitch / alignment works, a warp's loads cover 192 contiguous bytes and hit L1
-// after the first touch — and all loads of the PAIRS pairs a thread owns are issued before the first conversion.
-// The pad columns (0..2 and W+3..Wp-1) are written as zero, so the kernel does not depend on a pre-zeroed tensor.
+//
+// One block = one run of ID_PAIRS_PER_BLOCK column pairs of one row.  Phase 1 moves the raw bytes those pairs need
+// into shared memory with 16-byte vector loads (`ld.global.nc.v4`, lane-contiguous: a warp load = 512 contiguous
+// bytes; 48 bytes = 16 pixels per three of them) — or, when the row segment is not 16-byte aligned (odd pitch,
+// sliced tensors), with byte loads.  With `copy_dst` the same staged bytes are also written to a second frame set
+// (the reference's `img.copy()`, combine_detect.py:247, fused: the frame is read from HBM once).  Phase 2: one thread
+// = one 16-byte store = two x0 columns (2j, 2j+1), i.e. pixels 2j-3 and 2j-2, whose six bytes start at byte 6j-9 of
+// the row: three aligned 32-bit shared-memory loads and two funnel shifts.  Every store instruction of a warp writes
+// 512 contiguous bytes.  The pad columns (0..2 and W+3..Wp-1) are written as zero, so the kernel does not depend on a
+// pre-zeroed tensor.
 constexpr int ID_THREADS = 256;
-constexpr int ID_PAIRS = 4;            // pairs per thread per row: 4 * 256 * 2 = 2048 columns per block pass
+constexpr int ID_PAIRS = 4;                                  // pairs per thread
+constexpr int ID_PAIRS_PER_BLOCK = ID_THREADS * ID_PAIRS;    // 1024 pairs = 2048 columns = 6144 source bytes
+constexpr int ID_SMEM_BYTES = 6 * ID_PAIRS_PER_BLOCK + 64;   // + alignment slack on both sides
 
 __global__ void __launch_bounds__(ID_THREADS)
-ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, uint4* __restrict__ x0, int H, int W, int Wp,
-                          float m0, float m1, float m2) {
+ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, const vd_frame_t* __restrict__ copy_dst,
+                          uint4* __restrict__ x0, int H, int W, int Wp, float m0, float m1, float m2) {
+  __shared__ __align__(16) uint8_t s_raw[ID_SMEM_BYTES];
   const int b = blockIdx.z;
   const int y = blockIdx.y;
   const vd_frame_t fr = frames[b];
   const uint8_t* __restrict__ src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
-  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * (Wp >> 1);
   const int npairs = Wp >> 1;
-  for (int j0 = blockIdx.x * (ID_THREADS * ID_PAIRS); j0 < npairs; j0 += gridDim.x * (ID_THREADS * ID_PAIRS)) {
-    uint32_t px[ID_PAIRS][6];
-#pragma unroll
-    for (int p = 0; p < ID_PAIRS; ++p) {
-      const int j = j0 + p * ID_THREADS + threadIdx.x;
-      const int xa = 2 * j - 3;                      // pixel of column 2j; xa + 1 is the pixel of column 2j + 1
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int x = xa + (i >= 3);
-        px[p][i] = (j < npairs && x >= 0 && x < W) ? __ldg(src + 3 * x + (i % 3)) : 0xFFFFFFFFu;   // marker: pad column
+  const int j0 = blockIdx.x * ID_PAIRS_PER_BLOCK;
+  const int j1 = min(j0 + ID_PAIRS_PER_BLOCK, npairs);
+  const int row_bytes = 3 * W;
+  // bytes [lo, hi) of the row feed pairs [j0, j1): pixels 2*j0 - 3 .. 2*j1 - 4 (clipped to the row); consecutive
+  // blocks' ranges tile the row, so with copy_dst every byte of it is copied
+  const int lo = max(0, 6 * j0 - 9), hi = min(row_bytes, 6 * j1 - 9);
+  // shared-memory byte i holds row byte s_base + i; s_base keeps the row's own 16-byte phase so that the vector
+  // loads are aligned on both sides
+  const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15);
+  const int s_base = ((lo + phase) & ~15) - phase;          // <= lo, and (src + s_base) is 16-byte aligned
+  uint8_t* dst_row = nullptr;
+  if (copy_dst) {
+    const vd_frame_t fd = copy_dst[b];
+    dst_row = const_cast<uint8_t*>(fd.ptr) + static_cast<size_t>(y) * fd.pitch;
+  }
+  if (hi > lo) {
+    const int v_lo = s_base < 0 ? s_base + 16 : s_base;     // first 16-byte vector fully inside the row
+    const int v_hi = s_base + ((hi - s_base) & ~15);        // end of the last one
+    // vectors
+    for (int o = v_lo + 16 * static_cast<int>(threadIdx.x); o < v_hi; o += 16 * ID_THREADS) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + o));
+      *reinterpret_cast<uint4*>(s_raw + (o - s_base)) = v;
+      if (dst_row) {
+        if ((reinterpret_cast<uintptr_t>(dst_row + o) & 15) == 0) {
+          *reinterpret_cast<uint4*>(dst_row + o) = v;
+        } else {
+          const uint8_t* vb = reinterpret_cast<const uint8_t*>(&v);
+          for (int k = 0; k < 16; ++k) dst_row[o + k] = vb[k];
+        }
       }
     }
-#pragma unroll
-    for (int p = 0; p < ID_PAIRS; ++p) {
-      const int j = j0 + p * ID_THREADS + threadIdx.x;
-      if (j >= npairs) continue;
-      uint4 o;
-      const bool va = px[p][0] != 0xFFFFFFFFu, vb = px[p][3] != 0xFFFFFFFFu;
-      o.x = va ? pack_bf16x2(static_cast<float>(px[p][0]) - m0, static_cast<float>(px[p][1]) - m1) : 0u;
-      o.y = va ? pack_bf16x2(static_cast<float>(px[p][2]) - m2, 0.f) : 0u;
-      o.z = vb ? pack_bf16x2(static_cast<float>(px[p][3]) - m0, static_cast<float>(px[p][4]) - m1) : 0u;
-      o.w = vb ? pack_bf16x2(static_cast<float>(px[p][5]) - m2, 0.f) : 0u;
-      row[j] = o;
+    // ragged head and tail of the segment (and everything, if v_hi <= v_lo)
+    const int head_end = min(max(v_lo, lo), hi), tail_begin = max(min(v_hi, hi), head_end);
+    for (int o = lo + static_cast<int>(threadIdx.x); o < head_end; o += ID_THREADS) {
+      const uint8_t v = __ldg(src + o);
+      s_raw[o - s_base] = v;
+      if (dst_row) dst_row[o] = v;
     }
+    for (int o = tail_begin + static_cast<int>(threadIdx.x); o < hi; o += ID_THREADS) {
+      const uint8_t v = __ldg(src + o);
+      s_raw[o - s_base] = v;
+      if (dst_row) dst_row[o] = v;
+    }
+  }
+  __syncthreads();
+  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * npairs;
+  const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_raw);
+#pragma unroll
+  for (int p = 0; p < ID_PAIRS; ++p) {
+    const int j = j0 + p * ID_THREADS + static_cast<int>(threadIdx.x);
+    if (j >= j1) continue;
+    const int xa = 2 * j - 3;                       // pixel of column 2j; xa + 1 is the pixel of column 2j + 1
+    const bool va = xa >= 0 && xa < W, vb = xa + 1 >= 0 && xa + 1 < W;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (va || vb) {
+      const int off = 3 * xa - s_base;              // shared-memory byte of the pair's first byte (may be < 0 if !va)
+      const int w = off >> 2;                       // arithmetic shift: floor
+      const uint32_t sh = static_cast<uint32_t>(off & 3) * 8u;
+      // words outside the staged range are never selected into a VALID pixel's bytes
+      const uint32_t w0 = w >= 0 ? s_w[w] : 0u, w1 = s_w[w + 1], w2 = (4 * (w + 2) < ID_SMEM_BYTES) ? s_w[w + 2] : 0u;
+      const uint32_t lo4 = __funnelshift_r(w0, w1, sh);     // bytes 0..3 of the pair
+      const uint32_t hi4 = __funnelshift_r(w1, w2, sh);     // bytes 4..7 (4, 5 used)
+      if (va) {
+        o.x = pack_bf16x2(static_cast<float>(lo4 & 0xFFu) - m0, static_cast<float>((lo4 >> 8) & 0xFFu) - m1);
+        o.y = pack_bf16x2(static_cast<float>((lo4 >> 16) & 0xFFu) - m2, 0.f);
+      }
+      if (vb) {
+        o.z = pack_bf16x2(static_cast<float>(lo4 >> 24) - m0, static_cast<float>(hi4 & 0xFFu) - m1);
+        o.w = pack_bf16x2(static_cast<float>((hi4 >> 8) & 0xFFu) - m2, 0.f);
+      }
+    }
+    row[j] = o;
   }
 }
 
@@ -167,16 +221,29 @@ extern "C" int vd_ingest_u8hwc(const vd_frame_t* frames, int B, void* x0, int H,
 }
 
 // identity fast path, selected by the host when every frame already has the network's size
-extern "C" int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x0, int H, int W,
-                                        const float mean[3], vd_stream_t stream) {
+static int ingest_identity(const vd_frame_t* frames, const vd_frame_t* copy_dst, int B, void* x0, int H, int W,
+                           const float mean[3], vd_stream_t stream) {
   VD_REQUIRE(frames && x0 && mean, "vd_ingest_u8hwc_identity: null argument");
   VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc_identity: bad extent");
   const int Wp = vd_x0_pitch(W);
-  dim3 grid(vd_cdiv(Wp / 2, ID_THREADS * ID_PAIRS), H, B);     // 1080p: one block per row (968 pairs)
+  dim3 grid(vd_cdiv(Wp / 2, ID_PAIRS_PER_BLOCK), H, B);        // 1080p: one block per row (968 pairs)
   ingest_x0_identity_kernel<<<grid, ID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
+      frames, copy_dst, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
   VD_LAUNCH_CHECK();
   return VD_OK;
+}
+
+extern "C" int vd_ingest_u8hwc_identity(const vd_frame_t* frames, int B, void* x0, int H, int W,
+                                        const float mean[3], vd_stream_t stream) {
+  return ingest_identity(frames, nullptr, B, x0, H, W, mean, stream);
+}
+
+// identity ingest that ALSO copies every frame into `frames_out` (same sizes; pitches may differ): the reference's
+// `img_with_mosaic = img.copy()` (combine_detect.py:247) without a second pass over the frame.
+extern "C" int vd_ingest_u8hwc_identity_copy(const vd_frame_t* frames, const vd_frame_t* frames_out, int B, void* x0,
+                                             int H, int W, const float mean[3], vd_stream_t stream) {
+  VD_REQUIRE(frames_out, "vd_ingest_u8hwc_identity_copy: null argument");
+  return ingest_identity(frames, frames_out, B, x0, H, W, mean, stream);
 }
 
 extern "C" int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H, int W,

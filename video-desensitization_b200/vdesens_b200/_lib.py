@@ -11,6 +11,7 @@ LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libvdesens_fp16.so")
 VD_CONV_RELU, VD_CONV_RESIDUAL, VD_CONV_UPADD, VD_CONV_OUT_F32 = 1, 2, 4, 8
 VD_CONV_IN_X0, VD_CONV_DUAL, VD_CONV_SPLIT, VD_CONV_POOL, VD_CONV_SLOPE, VD_CONV_CHAIN = 16, 32, 64, 128, 256, 512
 VD_CONV_REVERSE = 1024
+VD_CONV_TWO_DST = 2048
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
 VD_NMS_MAX_CAND = 8192
@@ -32,7 +33,9 @@ class VdConvDesc(C.Structure):
                 ("upadd", C.c_void_p), ("y", C.c_void_p),
                 ("x2", C.c_void_p), ("Cin2", C.c_int32), ("Hin2", C.c_int32), ("Win2", C.c_int32),
                 ("stride2", C.c_int32), ("slope", C.c_void_p),
-                ("chain_w", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_y", C.c_void_p), ("chain_Cout", C.c_int32)]
+                ("chain_w", C.c_void_p), ("chain_bias", C.c_void_p), ("chain_y", C.c_void_p), ("chain_Cout", C.c_int32),
+                ("acc_scale", C.c_float), ("y_b", C.c_void_p), ("Cout1", C.c_int32), ("dst_b_C", C.c_int32),
+                ("dst_b_coff", C.c_int32)]
 
 
 class VdJpegInfo(C.Structure):
@@ -50,6 +53,7 @@ _SIGS = {
     "vd_x0_pitch": (C.c_int, [C.c_int]),
     "vd_ingest_u8hwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "vd_ingest_u8hwc_identity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "vd_ingest_u8hwc_identity_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "vd_ingest_u8hwc_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "vd_conv_plan_create": (C.c_int, [C.POINTER(VdConvDesc), C.POINTER(C.c_void_p)]),
     "vd_conv_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -59,6 +59,9 @@ class Op:
     upsample_add: str = ""    # buffer (half resolution) nearest-upsampled and added AFTER ReLU (FPN top-down)
     pool: bool = False        # conv1 only: the 3x3/2 max-pool runs inside the convolution kernel, dst is the pooled tensor
     level: int = -1           # heads: pyramid level 0..2
+    sibling: Optional[ConvSpec] = None # VD_CONV_TWO_DST: a second layer reading the same tensor with the same geometry, run
+    sibling_dst: str = ""              # as extra output channels of this GEMM; its own destination buffer / slice
+    sibling_coff: int = 0
     chain: Optional[ConvSpec] = None   # VD_CONV_CHAIN: the NEXT 1x1 convolution, computed by the same kernel from the
     chain_dst: str = ""                # output tile while it is still in shared memory; chain_dst is its output buffer
 
@@ -98,7 +101,8 @@ def level_offsets(h: int, w: int) -> List[int]:
     return offs
 
 
-def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False, fuse_chain: bool = False):
+def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False, fuse_chain: bool = False,
+                fuse_siblings: bool = False):
     """Returns (convs, ops, bufs).  Buffer 'x0' is the ingested frame (3 real channels).
     With fuse_stem_pool conv1+bn1+relu+maxpool (retinaface.py:71-73) is one op writing 'p1' directly; the
     half-resolution 64-channel tensor 'c1' (4x the size of either neighbour) is never materialised.
@@ -106,7 +110,11 @@ def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False, fuse
     Bottleneck.downsample) is not a separate convolution: its 1x1 GEMM accumulates into conv3's
     accumulator (same output pixels), which removes one write and one read of the widest tensors.
     With fuse_chain a 256-channel conv3 also computes the 1x1 convolution that follows it (the next bottleneck's conv1,
-    64 or 128 outputs): layer1's three block outputs are written once and read back only as residuals."""
+    64 or 128 outputs): layer1's three block outputs are written once and read back only as residuals.
+    With fuse_siblings two consecutive 3x3 convolutions of an SSH module that read the SAME tensor (conv3X3 + conv5X5_1
+    on the FPN output, conv5X5_2 + conv7X7_2 on t5; reference nets/layers.py:54-62) run as one GEMM over the
+    concatenated filters (N = 192 / 128 instead of 128 + 64 / 64 + 64): the input is fetched once and the narrow
+    N = 64 GEMMs, which cannot feed the tensor pipe, disappear."""
     convs: List[ConvSpec] = []
     ops: List[Op] = []
     bufs: List[BufSpec] = []
@@ -196,6 +204,22 @@ def build_graph(fuse_downsample: bool = True, fuse_stem_pool: bool = False, fuse
         conv(f"{s}.conv7x7_3", f"{s}.conv7x7_3.0.weight", f"{s}.conv7x7_3.1", oc // 4, oc // 4, 3, 1, 1,
              True, t7, f_out, dst_coff=3 * oc // 4)
         ops.append(Op("heads", None, f_out, "heads", level=lvl))
+    if fuse_siblings:
+        fused, i = [], 0
+        while i < len(ops):
+            op = ops[i]
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            if (op.kind == "conv" and nxt is not None and nxt.kind == "conv" and nxt.src == op.src and op.conv.k == 3
+                    and (nxt.conv.k, nxt.conv.stride, nxt.conv.pad, nxt.conv.relu, nxt.conv.cin) ==
+                    (op.conv.k, op.conv.stride, op.conv.pad, op.conv.relu, op.conv.cin)
+                    and not (op.residual or nxt.residual or op.upsample_add or nxt.upsample_add or op.src2 or nxt.src2)
+                    and op.conv.cout % 64 == 0 and nxt.conv.cout % 64 == 0 and op.conv.cout + nxt.conv.cout in (128, 192)
+                    and op.conv.name.startswith("ssh")):
+                op.sibling, op.sibling_dst, op.sibling_coff = nxt.conv, nxt.dst, nxt.dst_coff
+                i += 1
+            fused.append(op)
+            i += 1
+        ops = fused
     if fuse_chain:
         fused, i = [], 0
         while i < len(ops):

@@ -42,7 +42,7 @@ def _on_device(fn):
 class DetectorEngine:
     def __init__(self, state_dict, batch, in_h, in_w, device="cuda:0", confidence=0.5, nms_iou=0.45,
                  cand_cap=4096, max_det=2048, max_ext=256, scratch_frames=8.0, precision="bf16",
-                 fuse_stem_pool=None, backbone="resnet50", fuse_chain=None, fuse_dwpw=True):
+                 fuse_stem_pool=None, backbone="resnet50", fuse_chain=None, fuse_dwpw=True, fuse_siblings=None):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectorEngine needs a CUDA device; there is no CPU fallback")
         # "bf16" (BASELINE's dtype), "fp16" (libvdesens_fp16.so) or "fp32x": fp32-class split precision — fp16 hi + lo
@@ -63,6 +63,10 @@ class DetectorEngine:
         if fuse_chain is None:
             fuse_chain = os.environ.get("VD_CHAIN", "1") != "0"
         self.fuse_chain = bool(fuse_chain) and not self.split
+        # SSH sibling convolutions (same input) as one GEMM with two destinations: VD_CONV_TWO_DST
+        if fuse_siblings is None:
+            fuse_siblings = os.environ.get("VD_SIBLINGS", "1") != "0"
+        self.fuse_siblings = bool(fuse_siblings) and not self.split
         self.fuse_dwpw = bool(fuse_dwpw)      # mobilenet: conv_dw blocks with Cin <= 32 as one kernel (vd_mnet_dwpw)
         storage = "fp16" if self.split else precision
         self.act_dtype = _lib.torch_dtype(storage)
@@ -157,12 +161,14 @@ class DetectorEngine:
     def _build_resnet(self, state_dict):
         dev, B, H, W = self.device, self.B, self.H, self.W
         convs, ops, bufs = arch.build_graph(fuse_downsample=not self.split, fuse_stem_pool=self.fuse_stem_pool,
-                                            fuse_chain=self.fuse_chain)
+                                            fuse_chain=self.fuse_chain, fuse_siblings=self.fuse_siblings)
         packed = weights.pack_all(state_dict, self.act_dtype, split=self.split)
+        acc_scale = getattr(packed, "acc_scale", {})
         P = 3 if self.split else 1            # channel planes per activation tensor
         self.w = {k: (w.to(dev), b.to(dev)) for k, (w, b) in packed.items()}
         self._alloc_buffers(bufs, P)
         self.n_chained = sum(1 for op in ops if op.kind == "conv" and op.chain is not None)
+        self.n_siblings = sum(1 for op in ops if op.kind == "conv" and op.sibling is not None)
 
         # tile-walk direction per layer (VD_CONV_REVERSE): a layer starts where its input was written LAST, so the
         # part of that tensor still in L2 is read before it is evicted.  wdir[buffer] = 1 if its writer walked backwards.
@@ -217,8 +223,19 @@ class DetectorEngine:
                     assert tuple(self.buf[op.chain_dst].shape) == (B, hout, wout, op.chain.cout)
                     d.chain_w, d.chain_bias, d.chain_y = w2.data_ptr(), b2.data_ptr(), self.buf[op.chain_dst].data_ptr()
                     d.chain_Cout = op.chain.cout
-                d.flags = flags
                 wt, bt = self.w[c.name]
+                if op.sibling is not None:    # one GEMM over [W_a ; W_b]: channels >= Cout_a go to the sibling's tensor
+                    w2, b2 = self.w[op.sibling.name]
+                    wt, bt = torch.cat([wt, w2], 0).contiguous(), torch.cat([bt, b2], 0).contiguous()
+                    self.w[c.name + "+" + op.sibling.name] = (wt, bt)
+                    flags |= _lib.VD_CONV_TWO_DST
+                    yb = self.buf[op.sibling_dst]
+                    assert tuple(yb.shape[:3]) == (B, hout, wout)
+                    d.Cout1, d.Cout = c.cout, c.cout + op.sibling.cout
+                    d.y_b, d.dst_b_C, d.dst_b_coff = yb.data_ptr(), yb.shape[3], op.sibling_coff
+                    wdir[op.sibling_dst] = 1 if rev else 0
+                d.flags = flags
+                d.acc_scale = float(acc_scale.get(c.name, 0.0))
                 d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
                 d.residual = res.data_ptr() if res is not None else None
                 d.upadd = up.data_ptr() if up is not None else None
@@ -235,6 +252,7 @@ class DetectorEngine:
                 d.stride, d.pad = 1, 0
                 d.dst_C, d.dst_coff = arch.HEAD_ROWS, 0
                 d.flags = _lib.VD_CONV_OUT_F32 | (_lib.VD_CONV_SPLIT if self.split else 0)
+                d.acc_scale = float(acc_scale.get(f"heads.{op.level}", 0.0))
                 if alternate and wdir.get(op.src, 0) == 0:
                     d.flags |= _lib.VD_CONV_REVERSE
                 wt, bt = self.w[f"heads.{op.level}"]
@@ -356,8 +374,19 @@ class DetectorEngine:
 
     # ------------------------------------------------------------------------------------------
     @_on_device
-    def enqueue_ingest(self):
+    def enqueue_ingest(self, src_desc=None):
+        """frames -> x0.  With `src_desc` (a (B,6) int32 device tensor of vd_frame_t records, ops.frame_descriptors) the
+        network reads THOSE frames, and the same pass copies them into the bound frame set (set_frames /
+        bind_frames_async) — the reference's img.copy() (combine_detect.py:247): compositing then runs in place on the
+        copy and the caller's frames stay pristine.  Frames of the network's own size only."""
         s = C.c_void_p(self.stream.cuda_stream)
+        if src_desc is not None:
+            if not self.identity:
+                raise RuntimeError("enqueue_ingest(src_desc=...) needs frames of the network's own size")
+            self._check(self.lib.vd_ingest_u8hwc_identity_copy(_ptr(src_desc), _ptr(self.frame_desc), self.B,
+                                                               _ptr(self.buf["x0"]), self.H, self.W, self._mean, s),
+                        "vd_ingest_u8hwc_identity_copy")
+            return
         fn = self.lib.vd_ingest_u8hwc_identity if self.identity else self.lib.vd_ingest_u8hwc
         self._check(fn(_ptr(self.frame_desc), self.B, _ptr(self.buf["x0"]), self.H, self.W, self._mean, s), "vd_ingest")
 

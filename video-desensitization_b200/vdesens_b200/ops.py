@@ -56,14 +56,21 @@ def x0_pitch(W):
 
 
 @_on_arg_device
-def ingest(frames, H, W, identity=None, precision="bf16"):
-    """-> x0 (B,H,Wp,4) in the library's activation type.  reference: Retinaface.preprocess (face.py:65-88)."""
+def ingest(frames, H, W, identity=None, precision="bf16", copy_to=None):
+    """-> x0 (B,H,Wp,4) in the library's activation type.  reference: Retinaface.preprocess (face.py:65-88).
+    copy_to: list of device uint8 (H,W,3) tensors that receive a copy of the frames in the same pass."""
     lib = _lib.lib(precision)
     B = len(frames)
     desc = frame_descriptors(frames)
     x0 = torch.zeros((B, H, x0_pitch(W), 4), dtype=_lib.torch_dtype(precision), device=frames[0].device)
     if identity is None:
         identity = all(f.shape[0] == H and f.shape[1] == W for f in frames)
+    if copy_to is not None:
+        assert identity and len(copy_to) == B
+        x0.fill_(float("nan"))            # the kernel writes every column, pad columns included
+        _lib.check(lib.vd_ingest_u8hwc_identity_copy(_p(desc), _p(frame_descriptors(copy_to)), B, _p(x0), H, W,
+                                                     (C.c_float * 3)(*MEAN), _stream()), "vd_ingest_u8hwc_identity_copy", lib)
+        return x0
     fn = lib.vd_ingest_u8hwc_identity if identity else lib.vd_ingest_u8hwc
     _lib.check(fn(_p(desc), B, _p(x0), H, W, (C.c_float * 3)(*MEAN), _stream()), "vd_ingest_u8hwc", lib)
     return x0
@@ -82,7 +89,8 @@ def ingest_nchw_f32(frames, H, W):
 
 @_on_arg_device
 def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=None, out=None, dst_coff=0,
-           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None, reverse=False):
+           out_f32=False, x0_hw=None, x2=None, stride2=1, split=False, pool=False, slope=None, chain=None, reverse=False,
+           acc_scale=0.0, two_dst=None):
     """x: bf16 NHWC (B,H,W,Cin) — or the ingest tensor with x0_hw=(H,W) for conv1.
     w_packed: same dtype (Cout, k*k*Cin) K order (r,s,cin) (weights.pack_all); bias fp32 (Cout).
     The activation dtype (torch.bfloat16 / torch.float16) selects libvdesens.so / libvdesens_fp16.so."""
@@ -136,6 +144,11 @@ def conv2d(x, w_packed, bias, k, stride, pad, relu=False, residual=None, upadd=N
         out2 = torch.empty((B, hout, wout, w2.shape[0]), dtype=x.dtype, device=x.device)
         flags |= _lib.VD_CONV_CHAIN
         d.chain_w, d.chain_bias, d.chain_y, d.chain_Cout = w2.data_ptr(), b2.data_ptr(), out2.data_ptr(), w2.shape[0]
+    if two_dst is not None:   # (cout1, out_b, dst_b_coff): channels >= cout1 are written to out_b[..., dst_b_coff:]
+        cout1, out_b, coff_b = two_dst
+        flags |= _lib.VD_CONV_TWO_DST
+        d.Cout1, d.y_b, d.dst_b_C, d.dst_b_coff = int(cout1), out_b.data_ptr(), out_b.shape[3], int(coff_b)
+    d.acc_scale = float(acc_scale)       # split mode: accumulators * acc_scale before the bias (weights packed as w / acc_scale)
     d.flags = flags
     d.x, d.w, d.bias = x.data_ptr(), w_packed.data_ptr(), bias.data_ptr()
     d.residual = residual.data_ptr() if residual is not None else None

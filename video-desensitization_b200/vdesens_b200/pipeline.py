@@ -75,9 +75,11 @@ class _Slot:
         self.rows = torch.zeros((B, eng.max_det, 16), dtype=torch.float32).pin_memory()
         self.counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
         self.status = torch.zeros((1,), dtype=torch.int32).pin_memory()
-        self.ev_in = torch.cuda.Event()
-        self.ev_done = torch.cuda.Event()
-        self.ev_out = torch.cuda.Event()
+        self.ev_in0 = torch.cuda.Event(enable_timing=True)     # H2D start / end, compute end, D2H start / end
+        self.ev_in = torch.cuda.Event(enable_timing=True)
+        self.ev_done = torch.cuda.Event(enable_timing=True)
+        self.ev_out0 = torch.cuda.Event(enable_timing=True)
+        self.ev_out = torch.cuda.Event(enable_timing=True)
         self.n = 0
         self.ext = None
         self.busy = False
@@ -95,7 +97,9 @@ class StreamingAnonymizer:
         self.mode, self.mosaic_level, self.ksize, self.sigma = mode, int(mosaic_level), int(ksize), float(sigma)
         self.depth = max(2, int(depth))
         self.slots = None
-        self.stats = {"submit_s": 0.0, "collect_wait_s": 0.0, "collect_host_s": 0.0, "batches": 0}
+        # host seconds per stage + device-timed copy durations (CUDA events on the copy streams) + yield timestamps
+        self.stats = {"submit_s": 0.0, "collect_wait_s": 0.0, "collect_host_s": 0.0, "batches": 0,
+                      "h2d_ms": 0.0, "d2h_ms": 0.0, "h2d_bytes": 0, "d2h_bytes": 0, "yield_t": []}
         self.s_in = torch.cuda.Stream(device=engine.device)
         self.s_out = torch.cuda.Stream(device=engine.device)
 
@@ -127,6 +131,7 @@ class StreamingAnonymizer:
             src = slot.pin_in
         slot.n = n
         with torch.cuda.stream(self.s_in):
+            slot.ev_in0.record(self.s_in)
             slot.dev.copy_(src, non_blocking=True)                # H2D
             slot.ev_in.record(self.s_in)
         eng.stream.wait_event(slot.ev_in)
@@ -152,6 +157,7 @@ class StreamingAnonymizer:
         slot.ev_done.record(eng.stream)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot.ev_done)
+            slot.ev_out0.record(self.s_out)
             slot.pin_out.copy_(slot.dev, non_blocking=True)       # D2H of the processed frames
             slot.ev_out.record(self.s_out)
         # (the slot is only refilled after _collect() has synchronised on ev_out, so the next H2D into it
@@ -164,8 +170,14 @@ class StreamingAnonymizer:
         slot.ev_out.synchronize()
         t1 = time.perf_counter()
         out = self._collect_impl(slot, copy_out)
-        self.stats["collect_wait_s"] += t1 - t0
-        self.stats["collect_host_s"] += time.perf_counter() - t1
+        st = self.stats
+        st["collect_wait_s"] += t1 - t0
+        st["collect_host_s"] += time.perf_counter() - t1
+        st["h2d_ms"] += slot.ev_in0.elapsed_time(slot.ev_in)
+        st["d2h_ms"] += slot.ev_out0.elapsed_time(slot.ev_out)
+        st["h2d_bytes"] += slot.dev.numel()
+        st["d2h_bytes"] += slot.dev.numel()
+        st["yield_t"].append(time.perf_counter())
         return out
 
     def _collect_impl(self, slot, copy_out):

@@ -16,6 +16,7 @@ from . import arch
 _DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 BN_CALIB_FILE = os.path.join(_DATA_DIR, "bn_calib_seed0.npz")
 BN_CALIB_FILE_MNET = os.path.join(_DATA_DIR, "bn_calib_mnet_seed0.npz")
+BN_CALIB_FILE_DEFAULT = os.path.join(_DATA_DIR, "bn_calib_default_seed0.npz")
 
 
 def synthetic_frame(h: int, w: int, seed: int) -> np.ndarray:
@@ -54,8 +55,15 @@ def synthetic_boxes(n: int, h: int, w: int, seed: int, min_size: int = 32, max_s
     return [(int(a), int(b), int(a + c), int(b + d)) for a, b, c, d in zip(x1, y1, bw, bh)]
 
 
-def _raw_state_dict(seed: int, backbone: str = "resnet50"):
-    """numpy state dict with identity BN statistics."""
+def _raw_state_dict(seed: int, backbone: str = "resnet50", init: str = "conditioned"):
+    """numpy state dict with identity BN statistics.
+    init="conditioned" (what every fixture of round 1 uses): random BN gamma/beta with SMALL residual gammas (bn3),
+    which keeps an untrained 50-layer net from amplifying rounding noise — see the comment at bn3 below.
+    init="default" (SURVEY §8d to the letter): the reference constructor's own initialisation — every BatchNorm
+    gamma = 1, beta = 0, nothing shrunk.  That network is in the chaotic regime of random deep ReLU nets: a relative
+    perturbation of 2^-12 anywhere is amplified ~100x by the heads; the parity test on these weights
+    (tests/test_gpu_kernels.py::test_default_init_weights_1080p) states what each precision mode achieves on them."""
+    assert init in ("conditioned", "default")
     rng = np.random.default_rng(seed + (0 if backbone == "resnet50" else 7919))
     sd = {}
     if backbone == "resnet50":
@@ -80,6 +88,10 @@ def _raw_state_dict(seed: int, backbone: str = "resnet50"):
         elif kind == "head_bias":
             b = 1.0 / np.sqrt(256.0 if backbone == "resnet50" else 64.0)
             sd[key] = rng.uniform(-b, b, size=shape).astype(np.float32)
+        elif kind == "bn_weight" and init == "default":
+            sd[key] = np.ones(shape, np.float32)
+        elif kind == "bn_bias" and init == "default":
+            sd[key] = np.zeros(shape, np.float32)
         elif kind == "bn_weight":        # non-trivial gamma/beta so BN folding is really exercised
             if key.endswith(".bn3.weight"):
                 # small residual branches (cf. torchvision's zero_init_residual recipe): with gamma ~ 1 on
@@ -101,16 +113,22 @@ def _raw_state_dict(seed: int, backbone: str = "resnet50"):
     return sd
 
 
-def synthetic_state_dict(seed: int = 0, calibrated: bool = True, face_rate: str = "r01", backbone: str = "resnet50"):
+def synthetic_state_dict(seed: int = 0, calibrated: bool = True, face_rate: str = "r01", backbone: str = "resnet50",
+                         init: str = "conditioned"):
     """Returns {key: np.ndarray}.  `calibrated` loads the committed BN statistics for seed 0;
     `face_rate` picks the class-bias shift stored with them ("r01" ~ 1 % of anchors >= 0.5,
     "r001" ~ 0.1 %, "dense" for the dense-ROI stress case, "" for no shift).
-    backbone "mobilenet" gives the cfg_mnet network (reference detect_face/utils/config.py:1-16)."""
-    sd = _raw_state_dict(seed, backbone)
+    backbone "mobilenet" gives the cfg_mnet network (reference detect_face/utils/config.py:1-16).
+    init: see _raw_state_dict ("default" = un-conditioned default initialisation, resnet50 only)."""
+    if init == "default" and backbone != "resnet50":
+        raise ValueError('init="default" is provided for the resnet50 backbone only')
+    sd = _raw_state_dict(seed, backbone, init)
     if calibrated:
         if seed != 0:
             raise ValueError("calibration statistics are committed for seed 0 only")
         calib_file = BN_CALIB_FILE if backbone == "resnet50" else BN_CALIB_FILE_MNET
+        if init == "default":
+            calib_file = BN_CALIB_FILE_DEFAULT
         if not os.path.isfile(calib_file):
             raise FileNotFoundError(calib_file + " (run oracle/make_golden.py in the build container)")
         cal = np.load(calib_file)

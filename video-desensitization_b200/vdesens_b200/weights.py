@@ -45,6 +45,25 @@ def _split(mat, dtype):
     return hi, lo
 
 
+class Packed(dict):
+    """{layer name: (w, bias)} plus `acc_scale` {layer name: float}: split mode packs w * 2^k (see _split_scale)"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.acc_scale = {}
+
+
+def _split_scale(mat):
+    """power of two 2^k with max|mat| * 2^k in [8192, 16384): BN-folded weights are O(1e-2), so the lo half of an
+    unscaled fp16 hi/lo pair is a SUBNORMAL (absolute resolution 6e-8, i.e. ~2^-18 of the weight, measured: heads 20x
+    further from fp32 than cuDNN's own fp32); scaled, it is a normal number and the pair carries 22 bits.  Exact (a
+    power of two), undone on the fp32 accumulator by acc_scale = 2^-k."""
+    m = float(np.abs(mat).max())
+    if not np.isfinite(m) or m <= 0.0:
+        return 1.0
+    return float(2.0 ** np.floor(np.log2(16384.0 / m)))
+
+
 def pack_all(sd, dtype=torch.bfloat16, split=False):
     """split=True (fp32-class mode, VD_CONV_SPLIT): activations are stored as planes [hi | lo | hi], so every tap's
     weight slice becomes [w_hi | w_hi | w_lo] (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo); the stem, whose input is exact,
@@ -53,7 +72,7 @@ def pack_all(sd, dtype=torch.bfloat16, split=False):
     conv of the graph plus 'heads.{0,1,2}' (the three 1x1 heads of a level fused to one N=32 GEMM)."""
     sd = to_numpy_sd(sd)
     convs, _, _ = arch.build_graph(fuse_downsample=not split)
-    packed = {}
+    packed = Packed()
     for c in convs:
         w, b = _fold(sd, c)
         if c.name == "body.conv1":
@@ -70,6 +89,9 @@ def pack_all(sd, dtype=torch.bfloat16, split=False):
             mat = np.concatenate([mat, w2.reshape(c.cout, -1)], axis=1)
             b = b + b2
         if split:
+            sc = _split_scale(mat)
+            packed.acc_scale[c.name] = 1.0 / sc
+            mat = mat * np.float32(sc)
             if c.name == "body.conv1":
                 hi, lo = _split(mat.reshape(c.cout, 7, 32), dtype)
                 wt = torch.cat([hi, lo], dim=2).reshape(c.cout, -1).contiguous()
@@ -88,7 +110,9 @@ def pack_all(sd, dtype=torch.bfloat16, split=False):
         mat = np.concatenate(ws, 0)
         assert mat.shape == (arch.HEAD_ROWS, 256)
         if split:
-            hi, lo = _split(mat, dtype)
+            sc = _split_scale(mat)
+            packed.acc_scale[f"heads.{lvl}"] = 1.0 / sc
+            hi, lo = _split(mat * np.float32(sc), dtype)
             packed[f"heads.{lvl}"] = (torch.cat([hi, hi, lo], dim=1).contiguous(), torch.from_numpy(np.concatenate(bs)))
         else:
             packed[f"heads.{lvl}"] = (torch.from_numpy(mat).to(dtype), torch.from_numpy(np.concatenate(bs)))
