@@ -1223,3 +1223,28 @@ def test_ingest_identity_with_fused_copy(ops, hw):
             assert np.array_equal(dst[i].cpu().numpy(), frames[i]) and np.array_equal(src[i].cpu().numpy(), frames[i])
     x, _ = ro.preprocess(frames, (H, W))
     assert torch.equal(want.cpu().float()[:, :, 3:3 + W, :3].permute(0, 3, 1, 2), x)
+
+
+@pytest.mark.parametrize("ksize", [3, 9, 31, 61, 99, 125, 127])
+def test_composite_gauss_packed_plane_path_shapes(ops, ksize):
+    """The dp4a path (byte planes packed along y, halo rows produced by the horizontal pass) on the shapes that stress its
+    index arithmetic: boxes just above the fused-box limit, narrower / shorter than the radius (multi-bounce
+    REFLECT_101), widths that are not multiples of 4 / 128, heights that are not multiples of 4 / 64, a box in the
+    bottom-right corner of an ODD-sized frame (the last group of the last row), a chain of large overlapping boxes, and a
+    frame that is a view with a pitch that is not a multiple of 4.  ksize 127 takes the generic (scalar) path."""
+    H, W = 301, 517
+    frame = synth.synthetic_frame(H, W, 900 + ksize)
+    boxes = [(3, 5, 53, 50), (60, 2, 66, 400), (2, 200, 500, 206), (100, 100, 229, 165), (90, 90, 350, 280),
+             (200, 150, 517, 301), (129, 64, 258, 129), (0, 0, 517, 301), (300, 10, 431, 75), (510, 290, 600, 400),
+             (256, 128, 385, 193), (255, 127, 384, 192)]
+    want = co.composite(frame, boxes, "gauss", 8, ksize)
+    for use_view in (False, True):
+        if use_view:                                     # pitch 3W + 7, offset 5: rows at every alignment
+            flat = torch.zeros(((H + 1) * (3 * W + 7),), dtype=torch.uint8, device=DEV)
+            f = torch.as_strided(flat, (H, W, 3), (3 * W + 7, 3, 1), storage_offset=5)
+            f.copy_(torch.from_numpy(frame))
+        else:
+            f = torch.from_numpy(frame.copy()).to(DEV)
+        ops.composite([f], [boxes], "gauss", ksize=ksize)
+        got = f.cpu().numpy()
+        assert np.array_equal(got, want), f"view={use_view}: {(got != want).sum()} bytes differ"

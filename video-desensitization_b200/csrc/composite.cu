@@ -35,8 +35,17 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int MA_PIX = 256;               // mosaic phase A: small pixels per tile
 constexpr int MB_W = 64, MB_H = 16;       // mosaic phase B tile
-constexpr int GA_W = 128, GA_H = 8;       // Gaussian phase A tile (horizontal pass), pixels
-constexpr int GB_E = 64, GB_H = 64;       // Gaussian phase B tile (vertical pass): 64 flat u16 elements x 64 rows
+// Gaussian, dp4a path (every tap <= 255, ksize <= 125 — all of BASELINE's kernels).  The intermediate of the separable
+// blur is stored as BYTE PLANES PACKED ALONG y: word (c, yg, x) of the HI (LO) plane holds the high (low) bytes of the
+// u16 horizontal sums of rows 4yg..4yg+3 at column x, channel c — i.e. exactly the operand word the vertical pass
+// feeds to dp4a, so that pass stages plain words instead of transposing bytes.  Rows are VIRTUAL rows v = y + r4
+// (r4 = radius rounded up to 4): the horizontal pass also produces the REFLECT_101 halo rows above and below the box
+// (source row reflect101(v - r4)), so the vertical pass never reflects and never leaves word alignment.
+constexpr int GA_W = 128, GA_H = 32;      // phase A tile (horizontal pass): 128 pixels x 32 virtual rows
+constexpr int GB_E = 128, GB_H = 64;      // phase B tile (vertical pass): 128 flat (pixel*3 + channel) elements x 64 rows
+// Gaussian, generic path (a tap > 255 or ksize > 125): u16 scratch [y][x*3+c], scalar taps
+constexpr int GA_W0 = 128, GA_H0 = 8;
+constexpr int GB_E0 = 64, GB_H0 = 64;
 constexpr int FUSE_MAX_PX = 2048;         // fused Gaussian box: 3 B (u8) + 6 B (u16) per pixel in smem (18 KB)
 constexpr int kMaxDynSmem = 64 * 1024;
 constexpr int KW_MAX = 32;                // dp4a fast path: ceil((ksize + 3) / 4) <= KW_MAX  (ksize <= 125)
@@ -44,7 +53,7 @@ constexpr int KW_MAX = 32;                // dp4a fast path: ceil((ksize + 3) / 
 struct BoxMeta {
   int x1, y1, x2, y2;      // clipped; empty boxes have tA = tB = 0
   int tA, tB;              // fused box: tA = 1, tB = 0
-  int sw, sh;              // mosaic: down-sampled size
+  int sw, sh;              // mosaic: down-sampled size.  Gaussian dp4a path: sw = packed row groups (YG), sh = padded width
   unsigned int item_base;  // first item of this box inside its frame
   int fused;
   unsigned long long scratch_off;   // in u16 elements inside the frame's scratch region
@@ -67,7 +76,8 @@ struct Ws {
 
 struct Taps {
   uint16_t q[256];
-  // dp4a fast path: taps shifted by a = 0..3 bytes and packed 4 per word: qa[a][j] byte b = q[4j + b - a]
+  // dp4a fast path: taps shifted by a = 0..3 bytes and packed 4 per word: qa[a][j] byte b = q[4j + b - a], so that
+  // out[4m + a] = sum_j dp4a(S[m + j], qa[a][j]) for a byte sequence S packed 4 per word
   uint32_t qa[4][KW_MAX];
   int kw;                  // words per shifted tap vector, 0 = fast path not applicable (a tap > 255 or ksize > 125)
 };
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(1024)
 composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float* __restrict__ det_rows,
                       const int* __restrict__ det_count, int max_det, const int* __restrict__ ext_boxes,
                       const int* __restrict__ ext_count, int max_ext, int maxb, int mode, int mosaic_level,
-                      uint32_t* __restrict__ status, Ws ws) {
+                      int ksize, int fast, uint32_t* __restrict__ status, Ws ws) {
   __shared__ unsigned int s_items[1024];
   __shared__ unsigned long long s_scr[1024];
   __shared__ unsigned int s_total;
@@ -164,9 +174,16 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
             scr = (static_cast<unsigned long long>(m.sw) * m.sh * 3 + 1) / 2;
           } else if (static_cast<long long>(bw) * bh <= FUSE_MAX_PX) {
             m.fused = 1; m.tA = 1; m.tB = 0;
-          } else {
-            m.tA = ((bw + GA_W - 1) / GA_W) * ((bh + GA_H - 1) / GA_H);
+          } else if (fast) {
+            const int r4 = ((ksize >> 1) + 3) & ~3;
+            const int YG = (bh + 2 * r4 + 3) >> 2, bwp = (bw + 3) & ~3;
+            m.sw = YG; m.sh = bwp;
+            m.tA = ((bw + GA_W - 1) / GA_W) * ((4 * YG + GA_H - 1) / GA_H);
             m.tB = ((bw * 3 + GB_E - 1) / GB_E) * ((bh + GB_H - 1) / GB_H);
+            scr = 12ull * YG * bwp;            // u16 units: 2 byte planes x 3 channels x YG x bwp words
+          } else {
+            m.tA = ((bw + GA_W0 - 1) / GA_W0) * ((bh + GA_H0 - 1) / GA_H0);
+            m.tB = ((bw * 3 + GB_E0 - 1) / GB_E0) * ((bh + GB_H0 - 1) / GB_H0);
             scr = static_cast<unsigned long long>(bw) * bh * 3;
           }
           scr = (scr + 7) & ~7ull;
@@ -248,7 +265,7 @@ __device__ __forceinline__ void spin_flag(const int* flag, uint32_t* status) {
 
 // wait until every B / fused tile of an earlier box that writes into [rx1,rx2) x [ry1,ry2) is done
 __device__ __forceinline__ void wait_writers(const BoxMeta* fm, const int* done, int k, int rx1, int ry1, int rx2,
-                                             int ry2, int mode, uint32_t* status) {
+                                             int ry2, int mode, int gb_e, int gb_h, uint32_t* status) {
   for (int j = threadIdx.x; j < k; j += kThreads) {
     const BoxMeta o = fm[j];
     if (o.tA + o.tB == 0) continue;
@@ -263,10 +280,10 @@ __device__ __forceinline__ void wait_writers(const BoxMeta* fm, const int* done,
       th = MB_H;
       tiles_x = (o.x2 - o.x1 + MB_W - 1) / MB_W;
       tx0 = (ix1 - o.x1) / MB_W; tx1 = (ix2 - 1 - o.x1) / MB_W;
-    } else {                      // Gaussian B tiles span GB_E flat (pixel*3 + channel) elements
-      th = GB_H;
-      tiles_x = ((o.x2 - o.x1) * 3 + GB_E - 1) / GB_E;
-      tx0 = ((ix1 - o.x1) * 3) / GB_E; tx1 = ((ix2 - o.x1) * 3 - 1) / GB_E;
+    } else {                      // Gaussian B tiles span gb_e flat (pixel*3 + channel) elements
+      th = gb_h;
+      tiles_x = ((o.x2 - o.x1) * 3 + gb_e - 1) / gb_e;
+      tx0 = ((ix1 - o.x1) * 3) / gb_e; tx1 = ((ix2 - o.x1) * 3 - 1) / gb_e;
     }
     const int ty0 = (iy1 - o.y1) / th, ty1 = (iy2 - 1 - o.y1) / th;
     const int* base = done + o.item_base + o.tA;
@@ -275,54 +292,32 @@ __device__ __forceinline__ void wait_writers(const BoxMeta* fm, const int* done,
   }
 }
 
-// ---- dp4a building blocks --------------------------------------------------------------------
-// out[4m + a] = sum_j dp4a(S[m + j], QA_a[j]) for M consecutive m; S = byte row packed 4 per word.
-template <int M>
-__device__ __forceinline__ void dp4a_run(const uint32_t* __restrict__ S, const uint32_t* __restrict__ qa, int kw,
-                                         uint32_t (&acc)[M]) {
-  // register window of M + 3 words, advanced four tap-words per iteration (the tap vectors are zero padded
-  // up to KW_MAX, so running kw up to the next multiple of four is harmless)
-  uint32_t win[M + 3];
-#pragma unroll
-  for (int i = 0; i < M; ++i) acc[i] = 0;
-#pragma unroll
-  for (int i = 0; i < M + 3; ++i) win[i] = S[i];
-  for (int j = 0; j < kw; j += 4) {
-    const uint32_t q0 = qa[j], q1 = qa[j + 1], q2 = qa[j + 2], q3 = qa[j + 3];
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      acc[i] = __dp4a(win[i], q0, acc[i]);
-      acc[i] = __dp4a(win[i + 1], q1, acc[i]);
-      acc[i] = __dp4a(win[i + 2], q2, acc[i]);
-      acc[i] = __dp4a(win[i + 3], q3, acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i + 4 < M + 3; ++i) win[i] = win[i + 4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) win[M - 1 + i] = S[M + 3 + j + i];
-  }
-}
-
-// Both passes of a fused (whole box in shared memory) Gaussian item with the taps in registers: KT >= ksize taps,
-// the ones beyond ksize are zero and read table entry 0.  out = (sum_j q[j] * (sum_i q[i] * src[refl]) + 32768) >> 16.
+// Both passes of a fused (whole box in shared memory) Gaussian item.  The taps are symmetric (q[t] == q[ksize-1-t],
+// vd_gaussian_taps_q8), so only the first half lives in registers and every multiply serves two samples:
+// KT / 2 >= ksize / 2 registers, the ones beyond ksize / 2 are zero.  out = (sum_j q[j] * (sum_i q[i] * src[refl]) + 32768) >> 16.
 template <int KT>
 __device__ __forceinline__ void fused_passes(const uint8_t* __restrict__ src, uint16_t* __restrict__ mid,
                                              const uint16_t* __restrict__ xtab, const uint16_t* __restrict__ ytab,
-                                             const uint16_t* __restrict__ s_q, int bw, int bh, uint8_t* img, int pitch,
-                                             int x1, int y1) {
+                                             const uint16_t* __restrict__ s_q, int ksize, int bw, int bh, uint8_t* img,
+                                             int pitch, int x1, int y1) {
   const int tid = threadIdx.x;
   const int row3 = bw * 3, n = bh * row3;
-  uint32_t q[KT];
+  const int hk = ksize >> 1;
+  uint32_t qh[KT / 2];
 #pragma unroll
-  for (int t = 0; t < KT; ++t) q[t] = s_q[t];
+  for (int t = 0; t < KT / 2; ++t) qh[t] = t < hk ? s_q[t] : 0u;
+  const uint32_t qc = s_q[hk];
   for (int i = tid; i < n; i += kThreads) {
     const int y = i / row3, e = i - y * row3;
     const int x = e / 3, c = e - x * 3;
     const uint8_t* srow = src + y * row3 + c;
     const uint16_t* tb = xtab + x;
-    uint32_t acc = 0;
+    uint32_t acc = qc * srow[tb[hk]];
 #pragma unroll
-    for (int t = 0; t < KT; ++t) acc += q[t] * srow[tb[t]];
+    for (int t = 0; t < KT / 2; ++t) {
+      const int t2 = max(ksize - 1 - t, 0);              // mirror sample (a zero tap for t >= hk: any valid index will do)
+      acc += qh[t] * (static_cast<uint32_t>(srow[tb[t]]) + srow[tb[t2]]);
+    }
     mid[i] = static_cast<uint16_t>(min(acc, 65535u));
   }
   __syncthreads();
@@ -330,9 +325,12 @@ __device__ __forceinline__ void fused_passes(const uint8_t* __restrict__ src, ui
     const int y = i / row3, e = i - y * row3;
     const uint16_t* tb = ytab + y;
     const uint16_t* col = mid + e;
-    uint32_t acc = 0;
+    uint32_t acc = qc * col[tb[hk] * row3];
 #pragma unroll
-    for (int t = 0; t < KT; ++t) acc += q[t] * col[tb[t] * row3];
+    for (int t = 0; t < KT / 2; ++t) {
+      const int t2 = max(ksize - 1 - t, 0);
+      acc += qh[t] * (static_cast<uint32_t>(col[tb[t] * row3]) + col[tb[t2] * row3]);
+    }
     img[static_cast<size_t>(y1 + y) * pitch + x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
   }
 }
@@ -345,17 +343,20 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
   __shared__ int s_box;
   __shared__ unsigned int s_fprefix[130];
   __shared__ uint16_t s_q[256];
-  __shared__ uint32_t s_qa[4][KW_MAX];
+  __shared__ uint4 s_qt[KW_MAX];                  // s_qt[j] = (qa[0][j], qa[1][j], qa[2][j], qa[3][j]): one LDS.128 per tap word
+  __shared__ int s_mx[MB_W], s_my[MB_H];          // mosaic phase B: nearest-neighbour source index of the tile's columns / rows
   const int tid = threadIdx.x;
   for (int i = tid; i < B; i += kThreads) s_fprefix[i] = ws.hdr->frame_prefix[i + 1];   // items of frame i
   s_q[tid] = taps.q[tid];
-  if (tid < 4 * KW_MAX) s_qa[tid / KW_MAX][tid % KW_MAX] = taps.qa[tid / KW_MAX][tid % KW_MAX];
+  if (tid < KW_MAX) s_qt[tid] = make_uint4(taps.qa[0][tid], taps.qa[1][tid], taps.qa[2][tid], taps.qa[3][tid]);
   __syncthreads();
   unsigned int max_items = 0;
   for (int i = 0; i < B; ++i) max_items = max(max_items, s_fprefix[i]);
   const unsigned int total = max_items * static_cast<unsigned int>(B);
   const int r = ksize >> 1;
   const int kw = taps.kw;
+  const int r4 = (r + 3) & ~3;                               // dp4a path: halo rows above / below the box
+  const int gb_e = kw > 0 ? GB_E : GB_E0, gb_h = kw > 0 ? GB_H : GB_H0;   // B tile geometry of the active Gaussian path
 
   while (true) {
     __syncthreads();
@@ -414,29 +415,47 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     int tx = 0, ty = 0;
     if (mode == VD_MODE_MOSAIC) {
       if (phaseA) {
-        wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, status);
+        wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
       } else {
         const int tiles_x = (bw + MB_W - 1) / MB_W;
         ty = tile / tiles_x; tx = tile - ty * tiles_x;
         for (int a = tid; a < m.tA; a += kThreads) spin_flag(done + m.item_base + a, status);
       }
     } else if (m.fused) {
-      wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, status);
+      wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
+    } else if (kw > 0) {
+      if (phaseA) {
+        // reads frame pixels: columns x0 - r .. x0 + cols + r (reflected ones stay inside that range), source rows of
+        // its virtual rows — the whole box height for a tile that contains halo (reflected) rows
+        const int tiles_x = (bw + GA_W - 1) / GA_W;
+        ty = tile / tiles_x; tx = tile - ty * tiles_x;
+        const int x0 = tx * GA_W, v0 = ty * GA_H;
+        const int cx1 = max(0, x0 - r), cx2 = min(bw, x0 + GA_W + r);
+        int cy1 = v0 - r4, cy2 = v0 + GA_H - r4;
+        if (cy1 < 0 || cy2 > bh) { cy1 = 0; cy2 = bh; }
+        wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
+      } else {
+        // overwrites frame pixels the horizontal pass reads and consumes its planes: every A tile of this box first
+        // (all of them hold smaller tickets; other frames' items fill the wait)
+        const int tiles_x = (row3 + GB_E - 1) / GB_E;
+        ty = tile / tiles_x; tx = tile - ty * tiles_x;
+        for (int a = tid; a < m.tA; a += kThreads) spin_flag(done + m.item_base + a, status);
+      }
     } else if (phaseA) {
-      const int tiles_x = (bw + GA_W - 1) / GA_W;
+      const int tiles_x = (bw + GA_W0 - 1) / GA_W0;
       ty = tile / tiles_x; tx = tile - ty * tiles_x;
-      const int cx1 = max(0, tx * GA_W - r), cx2 = min(bw, tx * GA_W + GA_W + r);
-      const int cy1 = ty * GA_H, cy2 = min(bh, ty * GA_H + GA_H);
-      wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, status);
+      const int cx1 = max(0, tx * GA_W0 - r), cx2 = min(bw, tx * GA_W0 + GA_W0 + r);
+      const int cy1 = ty * GA_H0, cy2 = min(bh, ty * GA_H0 + GA_H0);
+      wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
     } else {
-      const int tiles_x = (row3 + GB_E - 1) / GB_E;
+      const int tiles_x = (row3 + GB_E0 - 1) / GB_E0;
       ty = tile / tiles_x; tx = tile - ty * tiles_x;
       // A tiles of this box with rows in (tile rows +- r) and pixel columns in (tile columns +- r)
-      const int px1 = (tx * GB_E) / 3, px2 = min(bw, (tx * GB_E + GB_E + 2) / 3);
+      const int px1 = (tx * GB_E0) / 3, px2 = min(bw, (tx * GB_E0 + GB_E0 + 2) / 3);
       const int cx1 = max(0, px1 - r), cx2 = min(bw, px2 + r);
-      const int cy1 = max(0, ty * GB_H - r), cy2 = min(bh, ty * GB_H + GB_H + r);
-      const int atx = (bw + GA_W - 1) / GA_W;
-      const int ax0 = cx1 / GA_W, ax1 = (cx2 - 1) / GA_W, ay0 = cy1 / GA_H, ay1 = (cy2 - 1) / GA_H;
+      const int cy1 = max(0, ty * GB_H0 - r), cy2 = min(bh, ty * GB_H0 + GB_H0 + r);
+      const int atx = (bw + GA_W0 - 1) / GA_W0;
+      const int ax0 = cx1 / GA_W0, ax1 = (cx2 - 1) / GA_W0, ay0 = cy1 / GA_H0, ay1 = (cy2 - 1) / GA_H0;
       const int nax = ax1 - ax0 + 1, n = nax * (ay1 - ay0 + 1);
       for (int i = tid; i < n; i += kThreads)
         spin_flag(done + m.item_base + (ay0 + i / nax) * atx + ax0 + i % nax, status);
@@ -462,12 +481,15 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           small[idx * 3 + 2] = __ldcg(p + 2);
         }
       } else {
+        // cv2's INTER_NEAREST map (double arithmetic) once per tile column / row, not per pixel
+        if (tid < MB_W) s_mx[tid] = nearest_src(min(tx * MB_W + tid, bw - 1), bw, m.sw);
+        else if (tid < MB_W + MB_H) s_my[tid - MB_W] = nearest_src(min(ty * MB_H + (tid - MB_W), bh - 1), bh, m.sh);
+        __syncthreads();
         for (int i = tid; i < MB_W * MB_H; i += kThreads) {
           const int ly = i / MB_W, lx = i - ly * MB_W;
           const int y = ty * MB_H + ly, x = tx * MB_W + lx;
           if (y < bh && x < bw) {
-            const int sy = nearest_src(y, bh, m.sh), sx = nearest_src(x, bw, m.sw);
-            const uint8_t* s = small + (sy * m.sw + sx) * 3;
+            const uint8_t* s = small + (s_my[ly] * m.sw + s_mx[lx]) * 3;
             uint8_t* d = img + static_cast<size_t>(m.y1 + y) * fr.pitch + (m.x1 + x) * 3;
             d[0] = __ldcg(s);
             d[1] = __ldcg(s + 1);
@@ -505,9 +527,9 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       for (int i = tid; i < bh + 2 * r + 32; i += kThreads)
         ytab[i] = static_cast<uint16_t>(i < bh + 2 * r ? reflect101(i - r, bh) : 0);
       __syncthreads();
-      if (ksize <= 8) fused_passes<8>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
-      else if (ksize <= 16) fused_passes<16>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
-      else if (ksize <= 32) fused_passes<32>(src, mid, xtab, ytab, s_q, bw, bh, img, fr.pitch, m.x1, m.y1);
+      if (ksize <= 8) fused_passes<8>(src, mid, xtab, ytab, s_q, ksize, bw, bh, img, fr.pitch, m.x1, m.y1);
+      else if (ksize <= 16) fused_passes<16>(src, mid, xtab, ytab, s_q, ksize, bw, bh, img, fr.pitch, m.x1, m.y1);
+      else if (ksize <= 32) fused_passes<32>(src, mid, xtab, ytab, s_q, ksize, bw, bh, img, fr.pitch, m.x1, m.y1);
       else {
         for (int i = tid; i < n; i += kThreads) {
           const int y = i / row3, e = i - y * row3;
@@ -527,65 +549,182 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           img[static_cast<size_t>(m.y1 + y) * fr.pitch + m.x1 * 3 + e] = static_cast<uint8_t>((acc + 32768u) >> 16);
         }
       }
-    } else if (phaseA) {
-      // ---------------- horizontal pass: GA_H rows x GA_W pixels ----------------
-      const int x0 = tx * GA_W, y0 = ty * GA_H;
-      const int rows = min(GA_H, bh - y0);
+    } else if (kw > 0 && phaseA) {
+      // ---------------- horizontal pass (dp4a): GA_W pixels x GA_H virtual rows -> packed byte planes ----------------
+      const int YG = m.sw, bwp = m.sh;
+      const int x0 = tx * GA_W, v0 = ty * GA_H;
       const int cols = min(GA_W, bw - x0);
-      if (kw > 0) {
-        // planar staging: plane c, row ly: bytes s[i] = pixel(x0 - r + i) (REFLECT_101), word-aligned rows
-        const int span = GA_W + 2 * r;                       // bytes used per plane row
-        const int spanw = (span + 3 + 4 * KW_MAX) / 4;       // words per row incl. slack read by the last window
-        uint32_t* planes = reinterpret_cast<uint32_t*>(dsm); // [3][GA_H][spanw]
-        uint8_t* pb = dsm;
-        const int total = rows * span;
-        for (int base = 0; base < total; base += 6 * kThreads) {       // 6 x 3 loads in flight per thread
-          uint8_t v[6][3];
+      const int vrows = min(GA_H, 4 * YG - v0);              // a multiple of 4
+      const int spanw = GA_W / 4 + kw;                       // words per plane row: byte i = pixel x0 - r + i
+      uint32_t* planes = reinterpret_cast<uint32_t*>(dsm);   // [3][GA_H][spanw]
+      const int ngroups = (cols + 2 * r + 3) >> 2;           // 4-pixel groups per row that feed valid outputs
+      const int total = vrows * ngroups;
+      for (int base = 0; base < total; base += 4 * kThreads) {
+        uint32_t w[4][4];
+        int sh8[4];                                          // 8 * misalignment of the group, -1 = slow path
 #pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int i = base + u * kThreads + tid;
-            if (i < total) {
-              const int ly = i / span, c = i - ly * span;
-              int xs = x0 - r + c;
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kThreads + tid;
+          sh8[u] = -1;
+          if (i < total) {
+            const int ly = i / ngroups, g = i - ly * ngroups;
+            const int px = x0 - r + 4 * g;                   // box-local pixel of the group's first byte
+            int ys = v0 + ly - r4;
+            if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+            const int gy = m.y1 + ys;
+            // fast: four in-range pixels, read as four aligned words; the last word may reach 3 bytes past the group,
+            // which must still be inside the frame buffer
+            if (px >= 0 && px + 3 < bw && (m.x1 + px + 4 < fr.w || gy < fr.h - 1)) {
+              const uint8_t* p = img + static_cast<size_t>(gy) * fr.pitch + (m.x1 + px) * 3;
+              const uint32_t a0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 3);
+              const uint32_t* pa = reinterpret_cast<const uint32_t*>(p - a0);
+              w[u][0] = __ldcg(pa);
+              w[u][1] = __ldcg(pa + 1);
+              w[u][2] = __ldcg(pa + 2);
+              w[u][3] = a0 ? __ldcg(pa + 3) : 0u;
+              sh8[u] = static_cast<int>(a0 * 8);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kThreads + tid;
+          if (i >= total) continue;
+          const int ly = i / ngroups, g = i - ly * ngroups;
+          uint32_t p0, p1, p2;
+          if (sh8[u] >= 0) {
+            const uint32_t a = __funnelshift_r(w[u][0], w[u][1], sh8[u]), b = __funnelshift_r(w[u][1], w[u][2], sh8[u]),
+                           c = __funnelshift_r(w[u][2], w[u][3], sh8[u]);
+            p0 = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);     // bytes 0, 3, 6, 9 of the 12-byte group
+            p1 = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);     // bytes 1, 4, 7, 10
+            p2 = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);     // bytes 2, 5, 8, 11
+          } else {                                                       // box border: REFLECT_101 per pixel
+            int ys = v0 + ly - r4;
+            if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+            const uint8_t* rowp = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + m.x1 * 3;
+            p0 = p1 = p2 = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              int xs = x0 - r + 4 * g + q;
               if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
-              const uint8_t* p = img + static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + (m.x1 + xs) * 3;
-              v[u][0] = __ldcg(p);
-              v[u][1] = __ldcg(p + 1);
-              v[u][2] = __ldcg(p + 2);
+              const uint8_t* p = rowp + xs * 3;
+              p0 |= static_cast<uint32_t>(__ldcg(p)) << (8 * q);
+              p1 |= static_cast<uint32_t>(__ldcg(p + 1)) << (8 * q);
+              p2 |= static_cast<uint32_t>(__ldcg(p + 2)) << (8 * q);
+            }
+          }
+          planes[(0 * GA_H + ly) * spanw + g] = p0;
+          planes[(1 * GA_H + ly) * spanw + g] = p1;
+          planes[(2 * GA_H + ly) * spanw + g] = p2;
+        }
+      }
+      __syncthreads();
+      // task = (channel, group of 4 virtual rows, word of 4 pixels): 16 sums h[rr][a] = sum_t q[t] * pixel(x0 + 4mm + a - r + t)
+      uint32_t* HI = reinterpret_cast<uint32_t*>(scr16);
+      uint32_t* LO = HI + static_cast<size_t>(3) * YG * bwp;
+      for (int t = tid; t < 3 * (GA_H / 4) * (GA_W / 4); t += kThreads) {
+        const int c = t >> 8, ygl = (t >> 5) & 7, mm = t & 31;
+        if (4 * ygl >= vrows || 4 * mm >= cols) continue;
+        uint32_t acc[4][4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[rr][a] = 0u;
+        const uint32_t* prow = planes + (c * GA_H + 4 * ygl) * spanw + mm;
+        for (int j = 0; j < kw; ++j) {
+          const uint4 q4 = s_qt[j];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t wv = prow[rr * spanw + j];
+            acc[rr][0] = __dp4a(wv, q4.x, acc[rr][0]);
+            acc[rr][1] = __dp4a(wv, q4.y, acc[rr][1]);
+            acc[rr][2] = __dp4a(wv, q4.z, acc[rr][2]);
+            acc[rr][3] = __dp4a(wv, q4.w, acc[rr][3]);
+          }
+        }
+        // (taps sum to 256: a sum never exceeds 65280, cv2's saturation to 65535 is a no-op)
+        uint4 hi, lo;
+        uint32_t* hp = &hi.x;
+        uint32_t* lp = &lo.x;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const uint32_t h01 = __byte_perm(acc[0][a], acc[1][a], 0x0051), h23 = __byte_perm(acc[2][a], acc[3][a], 0x0051);
+          const uint32_t l01 = __byte_perm(acc[0][a], acc[1][a], 0x0040), l23 = __byte_perm(acc[2][a], acc[3][a], 0x0040);
+          hp[a] = __byte_perm(h01, h23, 0x5410);
+          lp[a] = __byte_perm(l01, l23, 0x5410);
+        }
+        const size_t wofs = (static_cast<size_t>(c) * YG + (v0 >> 2) + ygl) * bwp + x0 + 4 * mm;
+        *reinterpret_cast<uint4*>(HI + wofs) = hi;
+        *reinterpret_cast<uint4*>(LO + wofs) = lo;
+      }
+    } else if (kw > 0) {
+      // ---------------- vertical pass (dp4a): GB_E flat elements x GB_H rows, operands = the packed planes ----------------
+      const int YG = m.sw, bwp = m.sh;
+      const int d = r4 - r;                                  // output row y sits at packed-sequence index y + d
+      const int e0 = tx * GB_E, y0 = ty * GB_H;
+      const int ne = min(GB_E, row3 - e0);
+      const int rows = min(GB_H, bh - y0);
+      const int W0 = y0 >> 2;                                // first staged word row (y0 is a multiple of 4)
+      const int NW = GB_H / 4 + 1 + kw;                      // staged word rows
+      uint32_t* Shi = reinterpret_cast<uint32_t*>(dsm);      // [NW][GB_E]
+      uint32_t* Slo = Shi + NW * GB_E;
+      const uint32_t* HI = reinterpret_cast<const uint32_t*>(scr16);
+      const uint32_t* LO = HI + static_cast<size_t>(3) * YG * bwp;
+      const int e = tid & (GB_E - 1);
+      if (e < ne) {
+        const int ea = e0 + e, x = ea / 3, c = ea - 3 * x;
+        const size_t col = static_cast<size_t>(c) * YG * bwp + x;
+        for (int wr0 = tid >> 7; wr0 < NW; wr0 += 16) {      // 8 + 8 loads in flight per thread
+          uint32_t vh[8], vl[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int wr = wr0 + 2 * u;
+            if (wr < NW) {
+              const size_t o = col + static_cast<size_t>(min(W0 + wr, YG - 1)) * bwp;
+              vh[u] = __ldcg(HI + o);
+              vl[u] = __ldcg(LO + o);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int i = base + u * kThreads + tid;
-            if (i < total) {
-              const int ly = i / span, c = i - ly * span;
-              pb[(0 * GA_H + ly) * spanw * 4 + c] = v[u][0];
-              pb[(1 * GA_H + ly) * spanw * 4 + c] = v[u][1];
-              pb[(2 * GA_H + ly) * spanw * 4 + c] = v[u][2];
+          for (int u = 0; u < 8; ++u) {
+            const int wr = wr0 + 2 * u;
+            if (wr < NW) {
+              Shi[wr * GB_E + e] = vh[u];
+              Slo[wr * GB_E + e] = vl[u];
             }
           }
         }
-        __syncthreads();
-        // thread -> (channel, a, row, half): 16 outputs x = 64*half + 4m + a
-        constexpr int M = 16;
-        if (tid < 3 * 4 * GA_H * 2) {
-          const int c = tid % 3, a = (tid / 3) & 3, rest = tid / 12;
-          const int half = rest & 1, ly = rest >> 1;
-          if (ly < rows) {
-            const uint32_t* S = planes + (c * GA_H + ly) * spanw + half * (GA_W / 8);
-            uint32_t acc[M];
-            dp4a_run<M>(S, s_qa[a], kw, acc);
-            uint16_t* orow = scr16 + (static_cast<size_t>(y0 + ly) * bw + x0) * 3 + c;
+      }
+      __syncthreads();
+      if (e < ne) {
+        uint8_t* ocol = img + static_cast<size_t>(m.y1 + y0) * fr.pitch + m.x1 * 3 + e0 + e;
+        for (int mq = tid >> 7; mq < GB_H / 4 + 1; mq += 2) {
+          uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
+          for (int j = 0; j < kw; ++j) {
+            const uint4 q4 = s_qt[j];
+            const uint32_t wh = Shi[(mq + j) * GB_E + e], wl = Slo[(mq + j) * GB_E + e];
+            ah[0] = __dp4a(wh, q4.x, ah[0]); al[0] = __dp4a(wl, q4.x, al[0]);
+            ah[1] = __dp4a(wh, q4.y, ah[1]); al[1] = __dp4a(wl, q4.y, al[1]);
+            ah[2] = __dp4a(wh, q4.z, ah[2]); al[2] = __dp4a(wl, q4.z, al[2]);
+            ah[3] = __dp4a(wh, q4.w, ah[3]); al[3] = __dp4a(wl, q4.w, al[3]);
+          }
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-              const int lx = half * (GA_W / 2) + 4 * i + a;
-              if (lx < cols) orow[lx * 3] = static_cast<uint16_t>(acc[i]);
-            }
+          for (int a = 0; a < 4; ++a) {
+            const int ly = 4 * mq + a - d;
+            if (ly >= 0 && ly < rows)
+              ocol[static_cast<size_t>(ly) * fr.pitch] = static_cast<uint8_t>(((ah[a] << 8) + al[a] + 32768u) >> 16);
           }
         }
-      } else {
-        const int span = GA_W + 2 * r;
-        uint8_t* st = dsm;                             // [GA_H][span*3]
+      }
+    } else if (phaseA) {
+      // ---------------- horizontal pass: GA_H0 rows x GA_W0 pixels ----------------
+      const int x0 = tx * GA_W0, y0 = ty * GA_H0;
+      const int rows = min(GA_H0, bh - y0);
+      const int cols = min(GA_W0, bw - x0);
+      {
+        // (generic path: scalar taps; the dp4a path above handles every kernel whose taps fit a byte)
+        const int span = GA_W0 + 2 * r;
+        uint8_t* st = dsm;                             // [GA_H0][span*3]
         for (int i = tid; i < rows * span; i += kThreads) {
           const int ly = i / span, c = i - ly * span;
           const int xs = reflect101(x0 - r + c, bw);
@@ -603,74 +742,24 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         }
       }
     } else {
-      // ---------------- vertical pass: GB_H rows x GB_E flat elements ----------------
-      const int e0 = tx * GB_E, y0 = ty * GB_H;
-      const int ne = min(GB_E, row3 - e0);
-      const int rows = min(GB_H, bh - y0);
+      // ---------------- vertical pass: GB_H0 rows x GB_E0 flat elements ----------------
+      const int e0 = tx * GB_E0, y0 = ty * GB_H0;
+      const int ne = min(GB_E0, row3 - e0);
+      const int rows = min(GB_H0, bh - y0);
       const int span = rows + 2 * r;                       // staged rows
-      if (kw > 0) {
-        // transposed byte planes: hi[e][i], lo[e][i] with i = staged row (REFLECT_101); word-aligned columns;
-        // an odd word pitch keeps the byte stores of consecutive e on different banks
-        int colw = (GB_H + 2 * r + 3 + 4 * KW_MAX) / 4;
-        colw |= 1;
-        uint8_t* hi = dsm;                                  // [GB_E][colw*4]
-        uint8_t* lo = dsm + GB_E * colw * 4;
-        {
-          const int e = tid & (GB_E - 1);
-          if (e < ne) {
-            uint8_t* hcol = hi + e * colw * 4;
-            uint8_t* lcol = lo + e * colw * 4;
-            constexpr int LSTEP = kThreads / GB_E;
-            for (int l0 = tid / GB_E; l0 < span; l0 += 8 * LSTEP) {     // 8 loads in flight per thread
-              uint16_t v[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int ly = l0 + u * LSTEP;
-                if (ly < span) {
-                  int ys = y0 - r + ly;
-                  if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
-                  v[u] = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int ly = l0 + u * LSTEP;
-                if (ly < span) {
-                  hcol[ly] = static_cast<uint8_t>(v[u] >> 8);
-                  lcol[ly] = static_cast<uint8_t>(v[u] & 0xFF);
-                }
-              }
-            }
-          }
-        }
-        __syncthreads();
-        // thread -> (e, a): 16 outputs y = 4m + a
-        constexpr int M = GB_H / 4;
-        const int e = tid & (GB_E - 1), a = tid / GB_E;
-        if (e < ne) {
-          uint32_t ah[M], al[M];
-          dp4a_run<M>(reinterpret_cast<const uint32_t*>(hi) + e * colw, s_qa[a], kw, ah);
-          dp4a_run<M>(reinterpret_cast<const uint32_t*>(lo) + e * colw, s_qa[a], kw, al);
-          uint8_t* ocol = img + static_cast<size_t>(m.y1 + y0) * fr.pitch + m.x1 * 3 + e0 + e;
-#pragma unroll
-          for (int i = 0; i < M; ++i) {
-            const int ly = 4 * i + a;
-            if (ly < rows) ocol[static_cast<size_t>(ly) * fr.pitch] = static_cast<uint8_t>(((ah[i] << 8) + al[i] + 32768u) >> 16);
-          }
-        }
-      } else {
-        uint16_t* st = reinterpret_cast<uint16_t*>(dsm);   // [span][GB_E]
+      {
+        uint16_t* st = reinterpret_cast<uint16_t*>(dsm);   // [span][GB_E0]
         for (int i = tid; i < span * ne; i += kThreads) {
           const int ly = i / ne, e = i - ly * ne;
           const int ys = reflect101(y0 - r + ly, bh);
-          st[ly * GB_E + e] = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
+          st[ly * GB_E0 + e] = __ldcg(scr16 + static_cast<size_t>(ys) * row3 + e0 + e);
         }
         __syncthreads();
         for (int i = tid; i < rows * ne; i += kThreads) {
           const int ly = i / ne, e = i - ly * ne;
-          const uint16_t* s = st + ly * GB_E + e;
+          const uint16_t* s = st + ly * GB_E0 + e;
           uint32_t acc = 0;
-          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * GB_E];
+          for (int tt = 0; tt < ksize; ++tt) acc += static_cast<uint32_t>(s_q[tt]) * s[tt * GB_E0];
           img[static_cast<size_t>(m.y1 + y0 + ly) * fr.pitch + m.x1 * 3 + e0 + e] =
               static_cast<uint8_t>((acc + 32768u) >> 16);
         }
@@ -771,16 +860,16 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   const Ws ws = carve(workspace, B, maxb, workspace_bytes, &flag_bytes);
   VD_CHECK_CUDA(cudaMemsetAsync(ws.done, 0, flag_bytes, st));
   composite_plan_kernel<<<B, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
-                                            maxb, mode, mosaic_level, status, ws);
+                                            maxb, mode, mosaic_level, ksize, taps.kw > 0 ? 1 : 0, status, ws);
   VD_LAUNCH_CHECK();
   const int r = ksize >> 1;
   size_t smem = 0;
   if (mode == VD_MODE_GAUSS) {
-    size_t a = static_cast<size_t>(GA_H) * (GA_W + 2 * r) * 3;
-    size_t b = static_cast<size_t>(GB_H + 2 * r) * GB_E * 2;
+    size_t a = static_cast<size_t>(GA_H0) * (GA_W0 + 2 * r) * 3;
+    size_t b = static_cast<size_t>(GB_H0 + 2 * r) * GB_E0 * 2;
     if (taps.kw > 0) {
-      a = static_cast<size_t>(3) * GA_H * ((GA_W + 2 * r + 3 + 4 * KW_MAX) / 4) * 4;
-      b = static_cast<size_t>(2) * GB_E * ((((GB_H + 2 * r + 3 + 4 * KW_MAX) / 4) | 1)) * 4;
+      a = static_cast<size_t>(3) * GA_H * (GA_W / 4 + taps.kw) * 4;          // byte planes of the A tile
+      b = static_cast<size_t>(2) * (GB_H / 4 + 1 + taps.kw) * GB_E * 4;      // HI / LO word rows of the B tile
     }
     // fused item: u8 source + u16 intermediate + the two reflect tables (bw + bh <= FUSE_MAX_PX + 1)
     const size_t fz = static_cast<size_t>(FUSE_MAX_PX) * 9 + 64 + 2 * (static_cast<size_t>(FUSE_MAX_PX) + 1 + 4 * r + 64 + 16);
