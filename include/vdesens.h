@@ -49,6 +49,7 @@ enum vd_status {
 #define VD_STAT_DET_OVERFLOW 2u    /* more kept boxes than `max_det` */
 #define VD_STAT_WORK_OVERFLOW 4u   /* composite workspace too small */
 #define VD_STAT_WATCHDOG 8u        /* a device-side wait timed out */
+#define VD_STAT_JPEG_OVERFLOW 16u  /* an encoded frame did not fit its stream / output buffer (its size is reported as -1) */
 
 int vd_abi_version(void);
 /* storage type of activations and weights this build computes in: 0 = bf16 (libvdesens.so),
@@ -276,6 +277,19 @@ int vd_jpeg_read_header(const uint8_t* data, size_t size, vd_jpeg_info_t* info);
 /* coefK [host]: blocks_y[K] * blocks_x[K] * 64 int16, blocks in raster order, coefficients in natural order, still
  * quantised (multiply by info.quant[K] to de-quantise).  coef1 / coef2 may be NULL for a grey image. */
 int vd_jpeg_decode_coefficients(const uint8_t* data, size_t size, int16_t* coef0, int16_t* coef1, int16_t* coef2);
+
+/* ---- N1, far end: baseline JPEG encode of resident frames (csrc/jpeg_enc.cu) ----
+ * Replaces cv2.imwrite(path, bgr) of the reference frame loop (combine_detect.py:176-180) for frames that are already
+ * in HBM.  The files are BYTE-IDENTICAL to cv2.imwrite's (libjpeg-turbo: 4:2:0, the Annex K Huffman tables, no restart
+ * markers, JFIF 1.01 header) for the same pixels and quality; cv2's default quality is 95.
+ * frames: [dev] B descriptors of RGB (caller channel order = the order cv2 would be given after its BGR swap) frames,
+ * all H x W.  out: [dev] B * out_pitch bytes; frame i's file starts at out + i * out_pitch and is out_sizes[i] bytes long
+ * (out_sizes: [dev] int32[B]; -1 and status bit VD_STAT_JPEG_OVERFLOW if it did not fit out_pitch or the workspace).
+ * Never allocates, never synchronises. */
+size_t vd_jpeg_encode_workspace_bytes(int B, int H, int W);
+int vd_jpeg_encode_batch(const vd_frame_t* frames, int B, int H, int W, int quality, uint8_t* out, size_t out_pitch,
+                         int32_t* out_sizes, uint32_t* status, void* workspace, size_t workspace_bytes,
+                         vd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,8 @@ constexpr int MB_W = 64, MB_H = 16;       // mosaic phase B tile
 // (r4 = radius rounded up to 4): the horizontal pass also produces the REFLECT_101 halo rows above and below the box
 // (source row reflect101(v - r4)), so the vertical pass never reflects and never leaves word alignment.
 constexpr int GA_W = 128, GA_H = 32;      // phase A tile (horizontal pass): 128 pixels x 32 virtual rows
-constexpr int GB_E = 128, GB_H = 64;      // phase B tile (vertical pass): 128 flat (pixel*3 + channel) elements x 64 rows
+constexpr int GB_E = 128, GB_H = 60;      // phase B tile (vertical pass): 128 flat (pixel*3 + channel) elements x 60 rows
+                                          // (60 rows + the 0..3 rows of word alignment = 16 packed words = 4 groups of 4)
 // Gaussian, generic path (a tap > 255 or ksize > 125): u16 scratch [y][x*3+c], scalar taps
 constexpr int GA_W0 = 128, GA_H0 = 8;
 constexpr int GB_E0 = 64, GB_H0 = 64;
@@ -435,11 +436,30 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         if (cy1 < 0 || cy2 > bh) { cy1 = 0; cy2 = bh; }
         wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
       } else {
-        // overwrites frame pixels the horizontal pass reads and consumes its planes: every A tile of this box first
-        // (all of them hold smaller tickets; other frames' items fill the wait)
+        // a B tile (rows [y0, y0 + rows), pixels [px1, px2)) waits for the A tiles of its own box that
+        //   (RAW) produce the packed rows it consumes: virtual rows [y0 + d, y0 + rows + d + 2r), same pixel columns;
+        //   (WAR) still have to READ frame pixels it is about to overwrite: A tiles whose source rows (reflected ones
+        //         included) meet [y0, y0 + rows) and whose columns +- r meet [px1, px2).
         const int tiles_x = (row3 + GB_E - 1) / GB_E;
         ty = tile / tiles_x; tx = tile - ty * tiles_x;
-        for (int a = tid; a < m.tA; a += kThreads) spin_flag(done + m.item_base + a, status);
+        const int y0 = ty * GB_H, rows = min(GB_H, bh - y0), d = r4 - r;
+        const int px1 = (tx * GB_E) / 3, px2 = min(bw, (tx * GB_E + GB_E + 2) / 3);
+        const int atx = (bw + GA_W - 1) / GA_W, aty = (4 * m.sw + GA_H - 1) / GA_H;
+        const int ax0 = max(0, (px1 - r - (GA_W - 1) + GA_W * 4) / GA_W - 4), ax1 = min(atx - 1, (px2 - 1 + r) / GA_W);
+        const int nax = ax1 - ax0 + 1;
+        for (int i = tid; i < aty * nax; i += kThreads) {
+          const int ay = i / nax, ax = ax0 + (i - ay * nax);
+          const int v0 = ay * GA_H, v1 = v0 + GA_H;
+          bool need = v0 < y0 + rows + d + 2 * r && v1 > y0 + d;                // RAW
+          if (!need) {                                                          // WAR: conservative source-row interval
+            int lo = v0 - r4, hi = v1 - r4;
+            if (bh <= 2 * r4 + GA_H) { lo = 0; hi = bh; }                       // short boxes: reflections may land anywhere
+            else if (lo < 0) { hi = max(hi, 1 - lo); lo = 0; }                  // rows -lo .. 1 mirrored at the top
+            else if (hi > bh) { lo = min(lo, 2 * (bh - 1) - (hi - 1)); hi = bh; }
+            need = lo < y0 + rows && hi > y0;
+          }
+          if (need) spin_flag(done + m.item_base + ay * atx + ax, status);
+        }
       }
     } else if (phaseA) {
       const int tiles_x = (bw + GA_W0 - 1) / GA_W0;
@@ -674,10 +694,10 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       if (e < ne) {
         const int ea = e0 + e, x = ea / 3, c = ea - 3 * x;
         const size_t col = static_cast<size_t>(c) * YG * bwp + x;
-        for (int wr0 = tid >> 7; wr0 < NW; wr0 += 16) {      // 8 + 8 loads in flight per thread
-          uint32_t vh[8], vl[8];
+        for (int wr0 = tid >> 7; wr0 < NW; wr0 += 12) {      // 6 + 6 loads in flight per thread
+          uint32_t vh[6], vl[6];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 6; ++u) {
             const int wr = wr0 + 2 * u;
             if (wr < NW) {
               const size_t o = col + static_cast<size_t>(min(W0 + wr, YG - 1)) * bwp;
@@ -686,7 +706,7 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
             }
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 6; ++u) {
             const int wr = wr0 + 2 * u;
             if (wr < NW) {
               Shi[wr * GB_E + e] = vh[u];
@@ -697,23 +717,48 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       }
       __syncthreads();
       if (e < ne) {
+        // task = (element, group of 4 packed output words = 16 rows): the four words' operand windows overlap, so every
+        // staged word is loaded once per task and used four times (registers w0..w3 slide down the column); the HI plane's
+        // sums are shifted into place before the LO plane's are added: 16 accumulators, sum = sum_t q[t] * (256 hi + lo)
         uint8_t* ocol = img + static_cast<size_t>(m.y1 + y0) * fr.pitch + m.x1 * 3 + e0 + e;
-        for (int mq = tid >> 7; mq < GB_H / 4 + 1; mq += 2) {
-          uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
-          for (int j = 0; j < kw; ++j) {
-            const uint4 q4 = s_qt[j];
-            const uint32_t wh = Shi[(mq + j) * GB_E + e], wl = Slo[(mq + j) * GB_E + e];
-            ah[0] = __dp4a(wh, q4.x, ah[0]); al[0] = __dp4a(wl, q4.x, al[0]);
-            ah[1] = __dp4a(wh, q4.y, ah[1]); al[1] = __dp4a(wl, q4.y, al[1]);
-            ah[2] = __dp4a(wh, q4.z, ah[2]); al[2] = __dp4a(wl, q4.z, al[2]);
-            ah[3] = __dp4a(wh, q4.w, ah[3]); al[3] = __dp4a(wl, q4.w, al[3]);
+        for (int grp = tid >> 7; grp < (GB_H / 4 + 1) / 4; grp += 2) {
+          uint32_t acc[4][4];
+#pragma unroll
+          for (int mm = 0; mm < 4; ++mm)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[mm][a] = 0u;
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            const uint32_t* col = (plane ? Slo : Shi) + (4 * grp) * GB_E + e;
+            uint32_t w0 = col[0], w1 = col[GB_E], w2 = col[2 * GB_E], w3;
+            for (int j = 0; j < kw; ++j) {
+              const uint4 q4 = s_qt[j];
+              w3 = col[(j + 3) * GB_E];
+              acc[0][0] = __dp4a(w0, q4.x, acc[0][0]); acc[0][1] = __dp4a(w0, q4.y, acc[0][1]);
+              acc[0][2] = __dp4a(w0, q4.z, acc[0][2]); acc[0][3] = __dp4a(w0, q4.w, acc[0][3]);
+              acc[1][0] = __dp4a(w1, q4.x, acc[1][0]); acc[1][1] = __dp4a(w1, q4.y, acc[1][1]);
+              acc[1][2] = __dp4a(w1, q4.z, acc[1][2]); acc[1][3] = __dp4a(w1, q4.w, acc[1][3]);
+              acc[2][0] = __dp4a(w2, q4.x, acc[2][0]); acc[2][1] = __dp4a(w2, q4.y, acc[2][1]);
+              acc[2][2] = __dp4a(w2, q4.z, acc[2][2]); acc[2][3] = __dp4a(w2, q4.w, acc[2][3]);
+              acc[3][0] = __dp4a(w3, q4.x, acc[3][0]); acc[3][1] = __dp4a(w3, q4.y, acc[3][1]);
+              acc[3][2] = __dp4a(w3, q4.z, acc[3][2]); acc[3][3] = __dp4a(w3, q4.w, acc[3][3]);
+              w0 = w1; w1 = w2; w2 = w3;
+            }
+            if (plane == 0) {
+#pragma unroll
+              for (int mm = 0; mm < 4; ++mm)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) acc[mm][a] <<= 8;
+            }
           }
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int ly = 4 * mq + a - d;
-            if (ly >= 0 && ly < rows)
-              ocol[static_cast<size_t>(ly) * fr.pitch] = static_cast<uint8_t>(((ah[a] << 8) + al[a] + 32768u) >> 16);
-          }
+          for (int mm = 0; mm < 4; ++mm)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int ly = 16 * grp + 4 * mm + a - d;
+              if (ly >= 0 && ly < rows)
+                ocol[static_cast<size_t>(ly) * fr.pitch] = static_cast<uint8_t>((acc[mm][a] + 32768u) >> 16);
+            }
         }
       }
     } else if (phaseA) {

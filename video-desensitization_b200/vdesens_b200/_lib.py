@@ -14,6 +14,7 @@ VD_CONV_REVERSE = 1024
 VD_CONV_TWO_DST = 2048
 VD_MODE_MOSAIC, VD_MODE_GAUSS = 0, 1
 VD_STAT_CAND_OVERFLOW, VD_STAT_DET_OVERFLOW, VD_STAT_WORK_OVERFLOW, VD_STAT_WATCHDOG = 1, 2, 4, 8
+VD_STAT_JPEG_OVERFLOW = 16
 VD_NMS_MAX_CAND = 8192
 VD_MAX_BOXES_PER_FRAME = 4096
 
@@ -81,6 +82,9 @@ _SIGS = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "vd_jpeg_read_header": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegInfo)]),
     "vd_jpeg_decode_coefficients": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vd_jpeg_encode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vd_jpeg_encode_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 EXPORTED = tuple(_SIGS)
