@@ -278,6 +278,52 @@ int vd_jpeg_read_header(const uint8_t* data, size_t size, vd_jpeg_info_t* info);
  * quantised (multiply by info.quant[K] to de-quantise).  coef1 / coef2 may be NULL for a grey image. */
 int vd_jpeg_decode_coefficients(const uint8_t* data, size_t size, int16_t* coef0, int16_t* coef1, int16_t* coef2);
 
+/* ---- N1, near end: baseline JPEG decode on the device (csrc/jpeg_dec.cu) ----
+ * Replaces cv2.imread + BGR->RGB of the reference frame loop (combine_detect.py:167-173): the FILE bytes go to the GPU
+ * (~0.9 MB per 1080p frame instead of 6.2 MB of pixels), and Huffman decoding (parallel, self-synchronising),
+ * de-quantisation, jpeg_idct_islow, fancy up-sampling and YCbCr->RGB all run there.  The pixels are IDENTICAL to
+ * cv2.imread's (libjpeg-turbo defaults) — checked against oracle/jpeg_oracle.py, which is pinned on cv2.imdecode.
+ * vd_jpeg_prepare_device (host, ~0.1 ms) parses one file into the record the kernels read. */
+typedef struct vd_jpeg_huff_dev {
+  uint16_t fast[512];          /* 9-bit look-ahead: (length << 8) | symbol, 0 = longer code */
+  int32_t maxcode[18];         /* largest code of each length 1..16 (-1 = none), [17] = INT32_MAX */
+  int32_t valoff[18];          /* symbol index = valoff[length] + code */
+  uint8_t symbols[256];
+} vd_jpeg_huff_dev_t;
+
+typedef struct vd_jpeg_dev_hdr {
+  int32_t width, height, ncomp;            /* ncomp 1 (grey) or 3 (YCbCr) */
+  int32_t h[3], v[3];                      /* sampling factors: luma 1x1, 2x1 or 2x2, chroma 1x1 */
+  int32_t blocks_x[3], blocks_y[3];        /* block grid per component (whole MCUs) */
+  int32_t mcux, mcuy, blocks_per_mcu;
+  uint8_t blk_comp[12], blk_bx[12], blk_by[12];   /* per block of an MCU, in scan order: component, position in its footprint */
+  uint8_t td[3], ta[3], pad_[2];           /* Huffman table of each component: dc[td], ac[ta] (0 or 1) */
+  uint16_t quant[3][64];                   /* natural order */
+  uint32_t scan_offset;                    /* where the entropy-coded segment starts inside the caller's byte buffer */
+  uint32_t scan_bytes;                     /* its length, up to (not including) the marker that ends it */
+  vd_jpeg_huff_dev_t dc[2], ac[2];
+} vd_jpeg_dev_hdr_t;
+
+/* Parses one file.  VD_ERR_UNSUPPORTED for anything the device path does not take (progressive, restart markers, more
+ * than two table ids, other sampling patterns): the caller falls back to its CPU decoder for that file.
+ * hdr->scan_offset is relative to `data`; the caller adds the file's offset inside its staging buffer. */
+int vd_jpeg_prepare_device(const uint8_t* data, size_t size, vd_jpeg_dev_hdr_t* hdr);
+
+/* Decodes B files of ONE geometry (same width, height, components and sampling; Huffman and quantisation tables may
+ * differ per file) into B RGB frames.  hdrs: [dev] B records; bytes: [dev] the buffer their scan_offset refers to;
+ * frames_out: [dev] B descriptors of width x height uint8 HWC frames.  result: [dev] int32[B], 0 = ok, else a bit mask
+ * (1 = the parallel entropy decoder did not converge, 2 = block count mismatch, 4 = state mismatch while writing:
+ * decode that file on the CPU).  sub_bytes: bytes of entropy data per decoder thread (0 = default 1024).  Never allocates, never synchronises. */
+size_t vd_jpeg_decode_workspace_bytes(int B, const vd_jpeg_dev_hdr_t* geometry, size_t max_scan_bytes);
+int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg_dev_hdr_t* geometry_host, const uint8_t* bytes,
+                         int B, size_t max_scan_bytes, const vd_frame_t* frames_out, int32_t* result, int sub_bytes,
+                         void* workspace, size_t workspace_bytes, vd_stream_t stream);
+/* test hook: the same de-quantisation / IDCT / up-sampling / colour kernels fed with coefficient planes produced
+ * elsewhere (vd_jpeg_decode_coefficients): coef c is [dev] int16 [B][blocks_y[c]*blocks_x[c]*64], natural order */
+int vd_jpeg_reconstruct_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg_dev_hdr_t* geometry_host, int B,
+                              const int16_t* coef0, const int16_t* coef1, const int16_t* coef2,
+                              const vd_frame_t* frames_out, void* workspace, size_t workspace_bytes, vd_stream_t stream);
+
 /* ---- N1, far end: baseline JPEG encode of resident frames (csrc/jpeg_enc.cu) ----
  * Replaces cv2.imwrite(path, bgr) of the reference frame loop (combine_detect.py:176-180) for frames that are already
  * in HBM.  The files are BYTE-IDENTICAL to cv2.imwrite's (libjpeg-turbo: 4:2:0, the Annex K Huffman tables, no restart

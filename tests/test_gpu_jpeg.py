@@ -78,3 +78,90 @@ def test_encoder_reports_a_frame_that_does_not_fit():
         enc.encode([torch.from_numpy(im).to(DEV)])
     enc2 = JpegEncoder(1, 64, 64, device=DEV, max_bytes_per_frame=64 * 64 * 4)
     assert enc2.encode([torch.from_numpy(im).to(DEV)])[0] == _cv2(im)
+
+
+# ------------------------------------------------------------------------------------------------
+# device decoder (csrc/jpeg_dec.cu; reference combine_detect.py:167-173 cv2.imread + BGR->RGB)
+# ------------------------------------------------------------------------------------------------
+S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+SF = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+      "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420}
+
+
+def _file(rgb, params=()):
+    src = rgb if rgb.ndim == 2 else cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)
+    ok, buf = cv2.imencode(".jpg", src, list(params))
+    assert ok
+    return buf.tobytes()
+
+
+def _cv2_decode(data):
+    return cv2.cvtColor(cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+
+
+@pytest.mark.parametrize("sampling", ["420", "422", "444"])
+@pytest.mark.parametrize("hw", [(48, 64), (45, 77), (135, 241), (8, 3), (1, 1), (17, 5), (270, 480), (33, 47)])
+def test_device_reconstruction_from_host_coefficients_equals_cv2(sampling, hw):
+    """de-quantisation, jpeg_idct_islow, fancy up-sampling (edge columns / rows, tiny planes) and colour conversion on
+    the device, entropy decoding still on the host: pixels identical to cv2.imread's"""
+    from vdesens_b200 import jpeg
+    for kind, q in (("smooth", 95), ("noise", 60)):
+        data = _file(_image(hw[0], hw[1], kind, hw[0] + 3 * hw[1]), [S, SF[sampling], cv2.IMWRITE_JPEG_QUALITY, q])
+        got = jpeg.reconstruct_from_coefficients(data, DEV)
+        want = _cv2_decode(data)
+        assert np.array_equal(got, want), f"{sampling} {hw} {kind}: {(got != want).sum()} bytes differ"
+    grey = _file(_image(hw[0], hw[1], "smooth", 7)[..., 0].copy())
+    assert np.array_equal(jpeg.reconstruct_from_coefficients(grey, DEV), _cv2_decode(grey))
+
+
+@pytest.mark.parametrize("sub_bytes", [512, 1024, 4096])
+@pytest.mark.parametrize("hw,params", [((135, 241), ()), ((270, 480), (cv2.IMWRITE_JPEG_OPTIMIZE, 1)), ((48, 64), (cv2.IMWRITE_JPEG_QUALITY, 30)),
+                                       ((45, 77), (S, SF["444"])), ((50, 70), (S, SF["422"])), ((8, 3), ()), ((540, 960), (cv2.IMWRITE_JPEG_QUALITY, 100))])
+def test_device_decoder_equals_cv2(hw, params, sub_bytes):
+    """the whole device path, parallel Huffman decoding included (custom 'optimised' tables like ffmpeg's mjpeg encoder
+    writes, several subsequence sizes): pixels identical to cv2.imread's, no file falls back to the CPU.
+    The one exception is by construction: white noise at quality 100 has 63 non-zero AC coefficients in almost EVERY
+    block, so hardly any block ends with an EOB code and a decoder that starts with a wrong zig-zag index keeps that
+    offset for tens of kilobytes: with 512-byte subsequences the 32 rounds are not enough (they are with 1 KB).  The
+    decoder must notice (result flag) and the file takes the CPU path; the pixels are right either way."""
+    from vdesens_b200.jpeg import JpegDecoder
+    files = [_file(_image(hw[0], hw[1], kind, 11 * i + hw[1]), params) for i, kind in enumerate(("smooth", "noise", "smooth"))]
+    dec = JpegDecoder(3, device=DEV, max_file_bytes=max(len(f) for f in files) + 1024, sub_bytes=sub_bytes)
+    frames, on_cpu = dec.decode(files)
+    never_syncs = cv2.IMWRITE_JPEG_QUALITY in params and params[-1] == 100
+    assert on_cpu == [] or (never_syncs and on_cpu == [1]), (on_cpu, dec.result_host.tolist())
+    for i, f in enumerate(files):
+        got, want = frames[i].cpu().numpy(), _cv2_decode(f)
+        assert np.array_equal(got, want), f"file {i}: {(got != want).sum()} bytes differ"
+    # a short batch on the same decoder, and a grey file (its own geometry)
+    frames, on_cpu = dec.decode(files[:1])
+    assert on_cpu == [] and np.array_equal(frames[0].cpu().numpy(), _cv2_decode(files[0]))
+    print("sync rounds used (first round in which no exit state changed):", dec.sync_rounds())
+
+
+def test_device_decoder_full_hd_and_fallbacks():
+    """1080p files (the frame loop's size; ~0.9 MB of entropy data each -> ~1800 decoder threads per file); a progressive
+    file and a file with restart markers in the same batch take the CPU fallback and still come out right"""
+    from vdesens_b200.jpeg import JpegDecoder
+    H, W = 1080, 1920
+    imgs = [synth.synthetic_frame(H, W, 3000 + i) for i in range(4)]
+    files = [_file(imgs[0]), _file(imgs[1], (cv2.IMWRITE_JPEG_OPTIMIZE, 1)), _file(imgs[2], (cv2.IMWRITE_JPEG_PROGRESSIVE, 1)),
+             _file(imgs[3], (cv2.IMWRITE_JPEG_RST_INTERVAL, 7))]
+    dec = JpegDecoder(4, device=DEV)
+    frames, on_cpu = dec.decode(files)
+    assert on_cpu == [2, 3]
+    for i, f in enumerate(files):
+        assert np.array_equal(frames[i].cpu().numpy(), _cv2_decode(f)), i
+    assert dec.stats == {"files": 4, "device": 2, "fallback": 2}
+
+
+def test_decode_detect_encode_round_trip_matches_the_cv2_loop(tmp_path):
+    """files in -> device decode -> (no boxes) -> device encode -> files out == cv2.imread -> cv2.imwrite on the host"""
+    from vdesens_b200.jpeg import JpegDecoder
+    H, W = 270, 480
+    files = [_file(synth.synthetic_frame(H, W, 60 + i)) for i in range(2)]
+    dec, enc = JpegDecoder(2, device=DEV), JpegEncoder(2, H, W, device=DEV)
+    frames, _ = dec.decode(files)
+    out = enc.encode(frames)
+    for f, o in zip(files, out):
+        assert o == _cv2(_cv2_decode(f))

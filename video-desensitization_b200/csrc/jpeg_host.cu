@@ -279,6 +279,70 @@ extern "C" int vd_jpeg_read_header(const uint8_t* data, size_t size, vd_jpeg_inf
   return VD_OK;
 }
 
+// the record the device decoder reads (csrc/jpeg_dec.cu): geometry, per-file quantisation and Huffman tables, scan extent
+extern "C" int vd_jpeg_prepare_device(const uint8_t* data, size_t size, vd_jpeg_dev_hdr_t* hdr) {
+  VD_REQUIRE(data && hdr, "vd_jpeg_prepare_device: null argument");
+  static thread_local Parsed P;
+  const int rc = parse(data, size, P);
+  if (rc != VD_OK) return rc;
+  const vd_jpeg_info_t& I = P.info;
+  memset(hdr, 0, sizeof(*hdr));
+  if (I.restart_interval != 0) {
+    vd_set_error("vd_jpeg_prepare_device: restart markers are decoded on the CPU path");
+    return VD_ERR_UNSUPPORTED;
+  }
+  for (int c = 0; c < I.ncomp; ++c) {
+    const bool ok = c == 0 ? true : (I.h[c] == 1 && I.v[c] == 1);
+    if (!ok || P.td[c] > 1 || P.ta[c] > 1 || (c == 0 && I.ncomp == 3 && I.h[0] == 1 && I.v[0] == 2)) {
+      vd_set_error("vd_jpeg_prepare_device: sampling / table layout not taken by the device path");
+      return VD_ERR_UNSUPPORTED;
+    }
+  }
+  hdr->width = I.width; hdr->height = I.height; hdr->ncomp = I.ncomp;
+  int nb = 0;
+  for (int c = 0; c < I.ncomp; ++c) {
+    hdr->h[c] = I.h[c]; hdr->v[c] = I.v[c];
+    hdr->blocks_x[c] = I.blocks_x[c]; hdr->blocks_y[c] = I.blocks_y[c];
+    hdr->td[c] = static_cast<uint8_t>(P.td[c]); hdr->ta[c] = static_cast<uint8_t>(P.ta[c]);
+    memcpy(hdr->quant[c], I.quant[c], sizeof(hdr->quant[c]));
+    for (int by = 0; by < I.v[c]; ++by)
+      for (int bx = 0; bx < I.h[c]; ++bx, ++nb) {
+        hdr->blk_comp[nb] = static_cast<uint8_t>(c);
+        hdr->blk_bx[nb] = static_cast<uint8_t>(bx);
+        hdr->blk_by[nb] = static_cast<uint8_t>(by);
+      }
+  }
+  hdr->blocks_per_mcu = nb;
+  hdr->mcux = I.blocks_x[0] / I.h[0];
+  hdr->mcuy = I.blocks_y[0] / I.v[0];
+  for (int t = 0; t < 2; ++t)
+    for (int kind = 0; kind < 2; ++kind) {
+      const HuffTable& src = kind ? P.ac[t] : P.dc[t];
+      vd_jpeg_huff_dev_t& dst = kind ? hdr->ac[t] : hdr->dc[t];
+      if (!src.present) continue;
+      memcpy(dst.fast, src.fast, sizeof(dst.fast));
+      memcpy(dst.symbols, src.symbols, sizeof(dst.symbols));
+      for (int len = 0; len < 18; ++len) {
+        dst.maxcode[len] = (len >= 1 && len <= 16) ? src.maxcode[len] : (len == 17 ? 0x7FFFFFFF : -1);
+        dst.valoff[len] = (len >= 1 && len <= 16) ? src.valptr[len] - src.mincode[len] : 0;
+      }
+    }
+  // extent of the entropy-coded segment: up to the first marker (0xFF followed by anything but a stuffed zero)
+  const uint8_t* s = P.scan;
+  const uint8_t* end = P.scan + P.scan_size;
+  const uint8_t* q = s;
+  while (q < end) {
+    q = static_cast<const uint8_t*>(memchr(q, 0xFF, static_cast<size_t>(end - q)));
+    if (!q) { q = end; break; }
+    if (q + 1 >= end || q[1] != 0x00) break;
+    q += 2;
+  }
+  hdr->scan_offset = static_cast<uint32_t>(s - data);
+  hdr->scan_bytes = static_cast<uint32_t>(q - s);
+  VD_REQUIRE(hdr->scan_bytes > 0, "vd_jpeg_prepare_device: empty scan");
+  return VD_OK;
+}
+
 extern "C" int vd_jpeg_decode_coefficients(const uint8_t* data, size_t size, int16_t* coef0, int16_t* coef1,
                                            int16_t* coef2) {
   VD_REQUIRE(data && coef0, "vd_jpeg_decode_coefficients: null argument");

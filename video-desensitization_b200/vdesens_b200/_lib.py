@@ -45,6 +45,20 @@ class VdJpegInfo(C.Structure):
                 ("restart_interval", C.c_int32), ("quant", (C.c_uint16 * 64) * 3)]
 
 
+class VdJpegHuffDev(C.Structure):
+    _fields_ = [("fast", C.c_uint16 * 512), ("maxcode", C.c_int32 * 18), ("valoff", C.c_int32 * 18), ("symbols", C.c_uint8 * 256)]
+
+
+class VdJpegDevHdr(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32),
+                ("h", C.c_int32 * 3), ("v", C.c_int32 * 3), ("blocks_x", C.c_int32 * 3), ("blocks_y", C.c_int32 * 3),
+                ("mcux", C.c_int32), ("mcuy", C.c_int32), ("blocks_per_mcu", C.c_int32),
+                ("blk_comp", C.c_uint8 * 12), ("blk_bx", C.c_uint8 * 12), ("blk_by", C.c_uint8 * 12),
+                ("td", C.c_uint8 * 3), ("ta", C.c_uint8 * 3), ("pad_", C.c_uint8 * 2),
+                ("quant", (C.c_uint16 * 64) * 3), ("scan_offset", C.c_uint32), ("scan_bytes", C.c_uint32),
+                ("dc", VdJpegHuffDev * 2), ("ac", VdJpegHuffDev * 2)]
+
+
 _SIGS = {
     "vd_abi_version": (C.c_int, []),
     "vd_act_is_fp16": (C.c_int, []),
@@ -82,6 +96,12 @@ _SIGS = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "vd_jpeg_read_header": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegInfo)]),
     "vd_jpeg_decode_coefficients": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vd_jpeg_prepare_device": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegDevHdr)]),
+    "vd_jpeg_decode_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(VdJpegDevHdr), C.c_size_t]),
+    "vd_jpeg_decode_batch": (C.c_int, [C.c_void_p, C.POINTER(VdJpegDevHdr), C.c_void_p, C.c_int, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vd_jpeg_reconstruct_batch": (C.c_int, [C.c_void_p, C.POINTER(VdJpegDevHdr), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vd_jpeg_encode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vd_jpeg_encode_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
