@@ -165,3 +165,38 @@ def test_decode_detect_encode_round_trip_matches_the_cv2_loop(tmp_path):
     out = enc.encode(frames)
     for f, o in zip(files, out):
         assert o == _cv2(_cv2_decode(f))
+
+
+def test_directory_loop_with_the_codec_on_the_device_equals_the_host_loop(tmp_path):
+    """combine_detect.batch_process_images on a directory of JPEG frames (what the reference's ffmpeg stage leaves behind,
+    combine_detect.py:279-476): io="device" (decode + encode on the GPU) writes the SAME files, byte for byte, as
+    io="host" (cv2.imread / cv2.imwrite), and returns the same counts; plates come from a host provider"""
+    import os
+    from detect_face.face import Retinaface
+    import combine_detect
+    H, W = 160, 224
+    sd = synth.synthetic_state_dict(0, face_rate="r01")
+    det = Retinaface(state_dict=sd, input_shape=[H, W, 3], confidence=0.5, nms_iou=0.4, letterbox_image=True, cuda=True,
+                     batch_size=4)
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(10):                                    # batches of 4: 4 + 4 + 2
+        cv2.imwrite(str(src / f"frame_{i:06d}.jpg"), cv2.cvtColor(synth.synthetic_frame(H, W, 4200 + i), cv2.COLOR_RGB2BGR))
+
+    def plates(batch, verbose=False, conf=0.5):
+        assert all(isinstance(b, np.ndarray) and b.shape == (H, W, 3) for b in batch)
+        return [(None, [[10 + k, 20, 90, 70]]) for k, _ in enumerate(batch)]
+
+    outs = {}
+    for io in ("host", "device"):
+        dst = tmp_path / io
+        outs[io] = combine_detect.batch_process_images(str(src), str(dst), det, plates, batch_size=4, mode="gauss", ksize=15, io=io)
+        assert sorted(os.listdir(dst)) == [f"processed_frame_{i:06d}.jpg" for i in range(10)]
+    assert outs["host"] == outs["device"] and outs["host"][0] == 10 and outs["host"][2] == 10 and outs["host"][1] > 0
+    for i in range(10):
+        a = (tmp_path / "host" / f"processed_frame_{i:06d}.jpg").read_bytes()
+        b = (tmp_path / "device" / f"processed_frame_{i:06d}.jpg").read_bytes()
+        assert a == b, f"frame {i}: files differ ({len(a)} vs {len(b)} bytes)"
+    # "auto" picks the device codec for such a directory; a PNG directory keeps the host codec
+    assert combine_detect.batch_process_images(str(src), str(tmp_path / "auto"), det, None, batch_size=4, mode="gauss", ksize=15) == \
+        combine_detect.batch_process_images(str(src), str(tmp_path / "host2"), det, None, batch_size=4, mode="gauss", ksize=15, io="host")

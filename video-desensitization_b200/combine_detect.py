@@ -181,8 +181,112 @@ def _one_shape(frames):
     return next(iter(shapes)) if len(shapes) == 1 else None
 
 
+def _read_bytes(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def _write_bytes(path, blob):
+    with open(path, "wb") as f:
+        f.write(blob)
+
+
+def _device_jpeg_loop(groups, output_dir, face_detector, plate_detector, batch_size, mode, mosaic_level, ksize, sigma,
+                      quality, failed):
+    """The frame loop with the JPEG codec on the device: file bytes -> GPU (Huffman decode, IDCT,
+    up-sampling, colour) -> detect + composite on the resident frames -> GPU (DCT, quantisation, Huffman encode) -> file
+    bytes.  Pixels equal cv2.imread's and files equal cv2.imwrite's byte for byte, so the output directory is identical
+    to the host loop's.  Three batches are in flight: batch i+1 decodes and batch i-1 encodes (each on its own stream
+    and worker thread) while batch i is in the detector.  Returns (frames, faces, plates) or None when the first file is
+    not something the device decoder takes (the caller then runs the host loop)."""
+    from vdesens_b200 import jpeg as vjpeg
+    first = _read_bytes(groups[0][0])
+    try:
+        hdr = vjpeg.prepare_device(first)
+    except RuntimeError:
+        return None
+    H, W = hdr.height, hdr.width
+    n_total = sum(len(g) for g in groups)
+    eng = face_detector._engine_for(min(batch_size, n_total))
+    if (eng.H, eng.W) != (H, W):
+        return None                      # letterboxed input: the host path handles it (generic ingest)
+    B, dev = eng.B, eng.device
+    groups = [g[s:s + B] for g in groups for s in range(0, len(g), B)]
+    dec = vjpeg.JpegDecoder(B, device=dev, max_file_bytes=max(4 << 20, 2 * len(first)))
+    enc = vjpeg.JpegEncoder(B, H, W, device=dev, quality=quality)
+    slots = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
+    n_frames = n_faces = n_plates = 0
+    scale = np.array([W, H, W, H], np.float32)
+
+    def host_batch(files):
+        """one batch through the host codec (a file the device decoder cannot take alongside the others, an oversized
+        file, ...): same results, cv2 does the JPEG work"""
+        frames = [load_image_rgb(p) for p in files]
+        plates = _plates_of(plate_detector, frames)
+        res = face_detector.detect_images(frames)
+        allb = [[tuple(int(v) for v in b) for b in r[1]] + plates[j] for j, r in enumerate(res)]
+        for pth, img in zip(files, composite_frames(frames, allb, mode, mosaic_level, ksize, sigma)):
+            save_output_image(img, os.path.join(output_dir, "processed_" + os.path.basename(pth)))
+        return len(files), sum(len(r[1]) for r in res), sum(len(p) for p in plates)
+
+    with ThreadPoolExecutor(max_workers=_io_workers()) as fpool, ThreadPoolExecutor(max_workers=1) as dpool, \
+            ThreadPoolExecutor(max_workers=1) as epool, ThreadPoolExecutor(max_workers=1) as plate_pool:
+
+        def stage_in(k):
+            files = groups[k]
+            blobs = list(fpool.map(_read_bytes, files))
+            with torch.cuda.device(dev):
+                frames, _ = dec.decode(blobs, out=slots[k % 3])
+            return frames
+
+        def stage_out(k, n):
+            files = groups[k]
+            with torch.cuda.device(dev):
+                blobs = enc.encode(slots[k % 3][:n])
+            list(fpool.map(_write_bytes, [os.path.join(output_dir, "processed_" + os.path.basename(p)) for p in files], blobs))
+
+        pending_out = []                                  # encode futures, oldest first
+        fut_in = dpool.submit(stage_in, 0)
+        for k, files in enumerate(groups):
+            n = len(files)
+            try:
+                frames = fut_in.result()
+            except Exception:                             # noqa: BLE001: this batch goes through the host codec
+                frames = None
+            # slot (k+1) % 3 was last used by batch k-2: its encode must have finished before batch k+1 decodes into it
+            while len(pending_out) > 1:
+                pending_out.pop(0).result()
+            if k + 1 < len(groups):
+                fut_in = dpool.submit(stage_in, k + 1)
+            try:
+                if frames is None:
+                    a, b, c = host_batch(files)
+                    n_frames, n_faces, n_plates = n_frames + a, n_faces + b, n_plates + c
+                    continue
+                with torch.cuda.device(dev):
+                    pf = None
+                    if plate_detector is not None:        # the provider wants host frames: one D2H of the decoded batch
+                        host_frames = list(frames.cpu().numpy())
+                        pf = plate_pool.submit(_plates_of, plate_detector, host_frames)
+                    eng.set_frames(slots[k % 3])
+                    eng.forward()
+                    plates = pf.result() if pf is not None else [[] for _ in range(n)]
+                    eng.set_ext_boxes(plates + [[] for _ in range(B - n)])
+                    eng.enqueue_composite(mode, mosaic_level, ksize, sigma)
+                    rows, counts = eng.fetch_results()
+                pending_out.append(epool.submit(stage_out, k, n))
+                n_frames += n
+                n_faces += int(counts[:n].sum())
+                n_plates += sum(len(p) for p in plates)
+            except Exception as e:                        # noqa: BLE001 (reference :226)
+                failed(f"batch of {n} frames", e)
+        for f in pending_out:
+            f.result()
+    return n_frames, n_faces, n_plates
+
+
 def batch_process_images(input_dir, output_dir, face_detector, plate_detector, batch_size=16, mode="mosaic",
-                         mosaic_level=8, ksize=31, sigma=0.0, sort=True, on_error="raise"):
+                         mosaic_level=8, ksize=31, sigma=0.0, sort=True, on_error="raise", io="auto", jpeg_quality=95):
     """Same signature and return value as the reference (:183-277): (n_frames, n_faces, n_plates).
 
     What changes is the schedule: the reference loads a batch, waits for both detectors,
@@ -197,13 +301,20 @@ def batch_process_images(input_dir, output_dir, face_detector, plate_detector, b
                         which is arbitrary); sort=False restores that.
       on_error="raise"  a failing batch raises (the reference logs and silently DROPS the batch, :226-228, so frames
                         go missing from the output video); on_error="skip" restores that: the batches in flight when
-                        the error surfaced are dropped with a warning and the loop continues with the next one."""
+                        the error surfaced are dropped with a warning and the loop continues with the next one.
+    io: where the JPEG codec runs.  "device": files are decoded and re-encoded on the GPU
+    (vdesens_b200.jpeg: pixels identical to cv2.imread's, files byte-identical to cv2.imwrite's at `jpeg_quality`, cv2's
+    default 95) — what crosses PCIe is the file, not the pixels; "host": cv2 thread pools as in the reference; "auto"
+    (default): "device" when every input is a .jpg / .jpeg file and the first one is something the device decoder
+    takes at the network's own size, else "host"."""
     from collections import deque
     from vdesens_b200 import _lib
     from vdesens_b200.pipeline import StreamingAnonymizer
     _lib.mode_id(mode)
     if on_error not in ("raise", "skip"):
         raise ValueError(f"on_error must be 'raise' or 'skip', got {on_error!r}")
+    if io not in ("auto", "device", "host"):
+        raise ValueError(f"io must be 'auto', 'device' or 'host', got {io!r}")
     names = [f for f in os.listdir(input_dir) if f.lower().endswith((".png", ".jpg", ".jpeg"))]
     if sort:
         names.sort()
@@ -217,6 +328,16 @@ def batch_process_images(input_dir, output_dir, face_detector, plate_detector, b
             raise exc
         import warnings
         warnings.warn(f"batch_process_images: {what} dropped after {type(exc).__name__}: {exc}", RuntimeWarning)
+
+    if io != "host" and groups and all(p.lower().endswith((".jpg", ".jpeg")) for p in paths):
+        done = _device_jpeg_loop(groups, output_dir, face_detector, plate_detector, batch_size, mode, mosaic_level,
+                                 ksize, sigma, jpeg_quality, failed)
+        if done is not None:
+            return done
+        if io == "device":
+            raise RuntimeError("io='device': the first file is not a baseline JPEG of the network's input size")
+    elif io == "device":
+        raise RuntimeError("io='device' needs a directory of .jpg / .jpeg files")
 
     with ThreadPoolExecutor(max_workers=_io_workers()) as savers, ThreadPoolExecutor(max_workers=1) as plate_pool:
         saves = []
