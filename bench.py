@@ -402,6 +402,18 @@ def gpu_baseline(dev, wl, sd, frames, plates, steps=3):
             "network_only_frames_per_s": B / (acc["network_cudnn_tf32"] / steps)}
 
 
+def dir_loop_extra(n_frames=192):
+    """SURVEY §8f rows N1 + N2: the directory frame loop (JPEG files in -> detect + blur -> JPEG files out) with the codec on
+    the GPU against the same loop with cv2 thread pools and against the reference's schedule; tools/dir_loop_bench.py in
+    its own process (its engine and files are gone when it returns)"""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dir_loop_bench.py"), str(n_frames)],
+                           capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                                    # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     rank, world, local = dist_env()
@@ -436,7 +448,8 @@ def run_ours(args):
     # frames from pinned host memory to the device, runs detect + blur, and copies the processed frames
     # and the boxes back to pinned host memory; copies of neighbouring batches overlap the compute.
     from vdesens_b200.pipeline import StreamingAnonymizer
-    sa = StreamingAnonymizer(eng, wl["mode"], ksize=wl["ksize"] or 31, depth=int(os.environ.get("VD_E2E_DEPTH", "3")))
+    d2h_mode = os.environ.get("VD_E2E_D2H", "dirty")
+    sa = StreamingAnonymizer(eng, wl["mode"], ksize=wl["ksize"] or 31, depth=int(os.environ.get("VD_E2E_DEPTH", "3")), d2h=d2h_mode)
     NB = run.NB
     pinned = [torch.from_numpy(np.stack(hb)).pin_memory() for hb in run.host_batches]
     for _ in sa.run([pinned[i % NB] for i in range(4)], [run.plates[i % NB] for i in range(4)]):
@@ -493,10 +506,14 @@ def run_ours(args):
         "data": "synthetic", "config": workload_config(args.config, world, precision),
         "host_affinity": (f"each rank bound to the CPUs local to its GPU (NVML; rank 0: {len(numa_cpus)} CPUs)" if numa_cpus else "unbound"),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
-                "d2h_bytes_per_step": B * H * W * 3 + int(rows.nbytes) + int(counts.nbytes) + 4,
-                "steps": e2e_steps, **e2e_detail,
-                "timing": "wall clock around StreamingAnonymizer.run over the steps, pinned H2D + D2H of frames and boxes every step "
-                          "(pipelined), max over ranks; h2d_gbs / d2h_gbs from CUDA events on the copy streams of rank 0"},
+                "d2h_bytes_per_step": int(st["d2h_bytes"] / nb_done) + int(rows.nbytes) + int(counts.nbytes) + 4,
+                "d2h_mode": d2h_mode, "steps": e2e_steps, **e2e_detail,
+                "timing": "wall clock around StreamingAnonymizer.run over the steps: every step copies its 16 frames from pinned host "
+                          "memory to the device and brings the result back — d2h_mode 'dirty': the GPU writes the 64x16-pixel tiles a "
+                          "box touched straight into the pinned frames the batch came from (the yielded frames ARE that buffer, patched in "
+                          "place; bytes counted on the device), 'full': whole frames into a second pinned buffer — plus the box rows; "
+                          "pipelined, max over ranks; h2d_gbs / d2h_gbs from CUDA events on the copy streams of rank 0.  The three pinned "
+                          "input batches are cycled, so in 'dirty' mode a batch carries the previous pass's blur from its second use on"},
         "gpu_launches": run.launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor",
@@ -538,6 +555,7 @@ def run_ours(args):
             line["precisions"] = {p: short_summary(args.config, p, dev, 5 if p != "fp32x" else 3)
                                   for p in ("bf16", "fp16", "fp32x") if p != precision}
             line["other_configs"] = {c: short_summary(c, precision, dev, 5) for c in ("c3", "c5") if c != args.config}
+            line["dir_loop"] = dir_loop_extra()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -278,6 +278,16 @@ int vd_jpeg_read_header(const uint8_t* data, size_t size, vd_jpeg_info_t* info);
  * quantised (multiply by info.quant[K] to de-quantise).  coef1 / coef2 may be NULL for a grey image. */
 int vd_jpeg_decode_coefficients(const uint8_t* data, size_t size, int16_t* coef0, int16_t* coef1, int16_t* coef2);
 
+/* After vd_composite_rois only the pixels under a box differ from the frame the caller still holds.  Copies every
+ * 64 x 16-pixel tile that a (truncated, clipped — same rules as the compositing pass) box touches from frames[i] to
+ * dst_frames[i] (same sizes).  dst_frames may describe PINNED HOST memory (device-accessible under unified addressing):
+ * the tiles are then written over PCIe by the kernel itself, and the device->host traffic of a batch shrinks from the
+ * whole frames to the changed tiles.  bytes_copied: [dev] counter, incremented by the bytes written. */
+int vd_copy_dirty_tiles(const vd_frame_t* frames, const vd_frame_t* dst_frames, int B, int max_h, int max_w,
+                        const float* det_rows, const int32_t* det_count, int max_det,
+                        const int32_t* ext_boxes, const int32_t* ext_count, int max_ext,
+                        unsigned long long* bytes_copied, vd_stream_t stream);
+
 /* ---- N1, near end: baseline JPEG decode on the device (csrc/jpeg_dec.cu) ----
  * Replaces cv2.imread + BGR->RGB of the reference frame loop (combine_detect.py:167-173): the FILE bytes go to the GPU
  * (~0.9 MB per 1080p frame instead of 6.2 MB of pixels), and Huffman decoding (parallel, self-synchronising),
@@ -313,7 +323,7 @@ int vd_jpeg_prepare_device(const uint8_t* data, size_t size, vd_jpeg_dev_hdr_t* 
  * differ per file) into B RGB frames.  hdrs: [dev] B records; bytes: [dev] the buffer their scan_offset refers to;
  * frames_out: [dev] B descriptors of width x height uint8 HWC frames.  result: [dev] int32[B], 0 = ok, else a bit mask
  * (1 = the parallel entropy decoder did not converge, 2 = block count mismatch, 4 = state mismatch while writing:
- * decode that file on the CPU).  sub_bytes: bytes of entropy data per decoder thread (0 = default 1024).  Never allocates, never synchronises. */
+ * decode that file on the CPU).  sub_bytes: bytes of entropy data per decoder thread (0 = default 512).  Never allocates, never synchronises. */
 size_t vd_jpeg_decode_workspace_bytes(int B, const vd_jpeg_dev_hdr_t* geometry, size_t max_scan_bytes);
 int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg_dev_hdr_t* geometry_host, const uint8_t* bytes,
                          int B, size_t max_scan_bytes, const vd_frame_t* frames_out, int32_t* result, int sub_bytes,

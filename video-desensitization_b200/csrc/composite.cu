@@ -935,3 +935,79 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// dirty tiles: after compositing, only the tiles a box touched differ from the frame the caller still holds
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int DT_W = 64, DT_H = 16;       // tile: 64 x 16 pixels = 3 KB, 192 contiguous bytes per row
+
+// One CTA per tile: does any clipped box of the frame intersect it (same int() truncation and clipping as the
+// compositing pass, reference combine_detect.py:243, 145-150)?  If so its rows are copied from the device frame into the
+// destination frame — the caller's PINNED HOST frame, written over PCIe by the SMs (zero copy), so the host never touches
+// the unchanged ~56 % of the pixels and no per-box copy is issued.
+__global__ void __launch_bounds__(128)
+dirty_tiles_kernel(const vd_frame_t* __restrict__ frames, const vd_frame_t* __restrict__ dst_frames,
+                   const float* __restrict__ det_rows, const int* __restrict__ det_count, int max_det,
+                   const int* __restrict__ ext_boxes, const int* __restrict__ ext_count, int max_ext,
+                   unsigned long long* __restrict__ bytes_copied) {
+  __shared__ int s_hit;
+  const int f = blockIdx.z, tid = threadIdx.x;
+  const vd_frame_t fr = frames[f];
+  const int tx0 = blockIdx.x * DT_W, ty0 = blockIdx.y * DT_H;
+  if (tx0 >= fr.w || ty0 >= fr.h) return;
+  const int tx1 = min(tx0 + DT_W, fr.w), ty1 = min(ty0 + DT_H, fr.h);
+  if (tid == 0) s_hit = 0;
+  __syncthreads();
+  const int nd = det_rows ? min(det_count[f], max_det) : 0;
+  const int ne = ext_boxes ? min(ext_count[f], max_ext) : 0;
+  for (int k = tid; k < nd + ne && !s_hit; k += 128) {
+    int x1, y1, x2, y2;
+    if (k < nd) {
+      const float* r = det_rows + (static_cast<size_t>(f) * max_det + k) * 16;
+      x1 = static_cast<int>(__fmul_rn(r[0], static_cast<float>(fr.w)));
+      y1 = static_cast<int>(__fmul_rn(r[1], static_cast<float>(fr.h)));
+      x2 = static_cast<int>(__fmul_rn(r[2], static_cast<float>(fr.w)));
+      y2 = static_cast<int>(__fmul_rn(r[3], static_cast<float>(fr.h)));
+    } else {
+      const int* e = ext_boxes + (static_cast<size_t>(f) * max_ext + (k - nd)) * 4;
+      x1 = e[0]; y1 = e[1]; x2 = e[2]; y2 = e[3];
+    }
+    x1 = max(0, x1); y1 = max(0, y1); x2 = min(fr.w, x2); y2 = min(fr.h, y2);
+    if (x2 > x1 && y2 > y1 && x1 < tx1 && x2 > tx0 && y1 < ty1 && y2 > ty0) s_hit = 1;
+  }
+  __syncthreads();
+  if (!s_hit) return;
+  const vd_frame_t fd = dst_frames[f];
+  const int row_bytes = (tx1 - tx0) * 3;
+  for (int ly = 0; ly < ty1 - ty0; ++ly) {
+    const uint8_t* src = fr.ptr + static_cast<size_t>(ty0 + ly) * fr.pitch + tx0 * 3;
+    uint8_t* dst = const_cast<uint8_t*>(fd.ptr) + static_cast<size_t>(ty0 + ly) * fd.pitch + tx0 * 3;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (row_bytes & 15) == 0) {
+      if (tid * 16 < row_bytes) *reinterpret_cast<uint4*>(dst + tid * 16) = __ldcg(reinterpret_cast<const uint4*>(src + tid * 16));
+    } else {
+      for (int i = tid; i < row_bytes; i += 128) dst[i] = __ldcg(src + i);
+    }
+  }
+  if (tid == 0) atomicAdd(bytes_copied, static_cast<unsigned long long>(row_bytes) * (ty1 - ty0));
+}
+
+}  // namespace
+
+extern "C" int vd_copy_dirty_tiles(const vd_frame_t* frames, const vd_frame_t* dst_frames, int B, int max_h, int max_w,
+                                   const float* det_rows, const int32_t* det_count, int max_det,
+                                   const int32_t* ext_boxes, const int32_t* ext_count, int max_ext,
+                                   unsigned long long* bytes_copied, vd_stream_t stream) {
+  VD_REQUIRE(frames && dst_frames && bytes_copied, "vd_copy_dirty_tiles: null argument");
+  VD_REQUIRE(B > 0 && B <= 65535 && max_h > 0 && max_w > 0, "vd_copy_dirty_tiles: bad extent");
+  VD_REQUIRE((det_rows == nullptr) == (det_count == nullptr), "vd_copy_dirty_tiles: det_rows/det_count mismatch");
+  VD_REQUIRE((ext_boxes == nullptr) == (ext_count == nullptr), "vd_copy_dirty_tiles: ext_boxes/ext_count mismatch");
+  VD_REQUIRE(vd_cdiv(max_h, DT_H) <= 65535, "vd_copy_dirty_tiles: frame too tall");
+  dim3 grid(vd_cdiv(max_w, DT_W), vd_cdiv(max_h, DT_H), B);
+  dirty_tiles_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(frames, dst_frames, det_rows, det_count, max_det,
+                                                                            ext_boxes, ext_count, max_ext, bytes_copied);
+  VD_LAUNCH_CHECK();
+  return VD_OK;
+}

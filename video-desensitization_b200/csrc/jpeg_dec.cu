@@ -34,7 +34,7 @@ __constant__ uint8_t kZig[80] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25,
 constexpr int kChunk = 1024;          // unstuff: raw bytes per CTA
 constexpr int kRounds = 32;           // synchronisation rounds (the work of a round is skipped where nothing changed):
                                       // exit state i is exact once a wrong-start decoder has run (rounds + 1) x sub_bytes,
-                                      // i.e. 32 KB at the default subsequence size, ~10x what noise images need
+                                      // i.e. 16 KB at the default subsequence size of 512 bytes (photographic frames need 1-4 KB)
 constexpr int kSubThreads = 128;      // decoder threads per CTA
 constexpr int kPad = 64;              // zero bytes behind the unstuffed stream (the bit reader looks 8 bytes ahead)
 
@@ -287,30 +287,16 @@ __device__ __forceinline__ uint32_t decode_range(const uint8_t* __restrict__ U, 
   return done;
 }
 
-__device__ __forceinline__ void load_tables(const vd_jpeg_dev_hdr_t* __restrict__ hdr, HuffS* s_dc, HuffS* s_ac, uint8_t* s_t) {
-  const uint32_t* src_dc = reinterpret_cast<const uint32_t*>(hdr->dc);
-  const uint32_t* src_ac = reinterpret_cast<const uint32_t*>(hdr->ac);
-  uint32_t* d0 = reinterpret_cast<uint32_t*>(s_dc);
-  uint32_t* d1 = reinterpret_cast<uint32_t*>(s_ac);
-  constexpr int N = 2 * sizeof(HuffS) / 4;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    d0[i] = __ldg(src_dc + i);
-    d1[i] = __ldg(src_ac + i);
-  }
-  if (threadIdx.x < 3) {
-    s_t[threadIdx.x] = hdr->td[threadIdx.x];
-    s_t[4 + threadIdx.x] = hdr->ta[threadIdx.x];
-  }
-}
-
 // one synchronisation round (see the header comment); `first` = every thread starts from its guess
 __global__ void __launch_bounds__(kSubThreads)
 huff_sync_kernel(const vd_jpeg_dev_hdr_t* __restrict__ hdrs, const __grid_constant__ Geo G, DecWs ws, int round) {
-  __shared__ __align__(16) HuffS s_dc[2], s_ac[2];
-  __shared__ uint8_t s_t[8];
+  // The Huffman tables are read straight from the file's record in global memory (5.7 KB, L1-resident): the kernel
+  // uses NO shared memory, so its CTAs can co-reside with the detector's 227 KB convolution CTAs and decode the next
+  // batch in their shadow instead of queueing between them.
   const int f = blockIdx.y;
-  load_tables(hdrs + f, s_dc, s_ac, s_t);
-  __syncthreads();
+  const HuffS* s_dc = reinterpret_cast<const HuffS*>(hdrs[f].dc);
+  const HuffS* s_ac = reinterpret_cast<const HuffS*>(hdrs[f].ac);
+  const uint8_t* s_t = hdrs[f].td;                 // td[3] is followed by ta[3]
   const uint32_t total_bits = ws.ulen[f] * 8u;
   const int i = blockIdx.x * kSubThreads + threadIdx.x;
   const uint32_t start_bit = static_cast<uint32_t>(i) * static_cast<uint32_t>(ws.sub_bits);
@@ -324,7 +310,7 @@ huff_sync_kernel(const vd_jpeg_dev_hdr_t* __restrict__ hdrs, const __grid_consta
   uint32_t p = static_cast<uint32_t>(entry & 0xFFFFFFFFull);
   int b = static_cast<int>((entry >> 32) & 0xFF), k = static_cast<int>((entry >> 40) & 0xFF);
   const uint32_t end_bit = min(start_bit + static_cast<uint32_t>(ws.sub_bits), total_bits);
-  const uint32_t done = decode_range<false>(ws.U + static_cast<size_t>(f) * ws.ucap, s_dc, s_ac, s_t, s_t + 4, G, p, b, k,
+  const uint32_t done = decode_range<false>(ws.U + static_cast<size_t>(f) * ws.ucap, s_dc, s_ac, s_t, s_t + 3, G, p, b, k,
                                             end_bit, 0u, f, ws, nullptr);
   const unsigned long long ex = pack_state(p, b, k);
   if (round == 0 || ex != ws.exit_state[idx]) atomicAdd(ws.changed + static_cast<size_t>(f) * kRounds + round, 1u);
@@ -374,11 +360,10 @@ huff_scan_kernel(const __grid_constant__ Geo G, DecWs ws, int32_t* __restrict__ 
 __global__ void __launch_bounds__(kSubThreads)
 huff_write_kernel(const vd_jpeg_dev_hdr_t* __restrict__ hdrs, const __grid_constant__ Geo G, DecWs ws,
                   int32_t* __restrict__ result) {
-  __shared__ __align__(16) HuffS s_dc[2], s_ac[2];
-  __shared__ uint8_t s_t[8];
   const int f = blockIdx.y;
-  load_tables(hdrs + f, s_dc, s_ac, s_t);
-  __syncthreads();
+  const HuffS* s_dc = reinterpret_cast<const HuffS*>(hdrs[f].dc);
+  const HuffS* s_ac = reinterpret_cast<const HuffS*>(hdrs[f].ac);
+  const uint8_t* s_t = hdrs[f].td;
   if (result[f] != 0) return;
   const uint32_t total_bits = ws.ulen[f] * 8u;
   const int i = blockIdx.x * kSubThreads + threadIdx.x;
@@ -390,7 +375,7 @@ huff_write_kernel(const vd_jpeg_dev_hdr_t* __restrict__ hdrs, const __grid_const
   int b = static_cast<int>((entry >> 32) & 0xFF), k = static_cast<int>((entry >> 40) & 0xFF);
   const uint32_t end_bit = min(start_bit + static_cast<uint32_t>(ws.sub_bits), total_bits);
   uint32_t bad = 0;
-  decode_range<true>(ws.U + static_cast<size_t>(f) * ws.ucap, s_dc, s_ac, s_t, s_t + 4, G, p, b, k, end_bit,
+  decode_range<true>(ws.U + static_cast<size_t>(f) * ws.ucap, s_dc, s_ac, s_t, s_t + 3, G, p, b, k, end_bit,
                      ws.blk_base[idx], f, ws, reinterpret_cast<uint32_t*>(result + f));
   (void)bad;
 }
@@ -615,7 +600,7 @@ extern "C" int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg
   VD_REQUIRE(hdrs && bytes && frames_out && result && workspace, "vd_jpeg_decode_batch: null argument");
   VD_REQUIRE(B > 0 && B <= 65535 && max_scan_bytes > 0 && max_scan_bytes < (1ull << 28), "vd_jpeg_decode_batch: bad extent");
   if (check_geometry(geometry_host) != VD_OK) return VD_ERR_INVALID;
-  if (sub_bytes <= 0) sub_bytes = 1024;
+  if (sub_bytes <= 0) sub_bytes = 512;
   VD_REQUIRE(sub_bytes >= 256 && sub_bytes <= 65536 && sub_bytes % 4 == 0, "vd_jpeg_decode_batch: sub_bytes must be a multiple of 4 in [256, 65536]");
   VD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vd_jpeg_decode_batch: workspace must be 256-B aligned");
   const Geo G = make_geo(*geometry_host);

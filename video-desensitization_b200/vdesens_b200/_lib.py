@@ -94,6 +94,8 @@ _SIGS = {
     "vd_composite_rois": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vd_copy_dirty_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vd_jpeg_read_header": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegInfo)]),
     "vd_jpeg_decode_coefficients": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vd_jpeg_prepare_device": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(VdJpegDevHdr)]),
