@@ -15,7 +15,7 @@ try:
     hbm, tf, src = float(pk["hbm_gbs"]) * 1e9, float(pk["bf16_tflops_sustained"]) * 1e12, "MEASURED_PEAKS.json"
 except Exception:
     hbm, tf, src = 6547.8e9, 1375.9e12, "SURVEY 8(d) copy of MEASURED_PEAKS.json"
-convs, ops, bufs = arch.build_graph(fuse_stem_pool=True, fuse_chain=True)
+convs, ops, bufs = arch.build_graph(fuse_stem_pool=True, fuse_chain=True, fuse_siblings=(tag != "r01"))
 flops_px = {c.name: 2.0 * c.cout * (c.cin * c.k * c.k + c.cin2) for c in convs}
 hw = {b.name: arch.feature_hw(H, W, b.stride) for b in bufs}
 launches = []                                  # (label, flops) in plan order = launch order
@@ -29,11 +29,14 @@ for op in ops:
         if op.chain is not None:
             f += flops_px[op.chain.name] * h * w * B
             label += " + " + op.chain.name
+        if op.sibling is not None:
+            f += flops_px[op.sibling.name] * h * w * B
+            label += " + " + op.sibling.name.split(".")[-1]
         launches.append((label, f))
     elif op.kind == "heads":
         h, w = hw[op.src]
         launches.append((f"heads.{op.level}", 2.0 * 256 * 32 * h * w * B))
-rows = list(csv.DictReader(open(os.path.join(ROOT, "profiles", f"{tag}_conv_step_dram.csv"))))
+rows = list(csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", f"{tag}_conv_step_dram.csv")) if not l.startswith("#")))
 assert len(rows) == len(launches), (len(rows), len(launches))
 print(f"# Per-launch roofline of one bench step ({B} x {H}x{W}), peaks from {src}: HBM {hbm / 1e12:.3f} TB/s, bf16 {tf / 1e12:.1f} TFLOP/s\n")
 print("ncu durations are serialised and cold-cache (`profiles/%s_ncu_summary.md` §2); `bound` = max(DRAM-time, tensor-time), `eff` = bound / measured.\n" % tag)

@@ -25,8 +25,9 @@ def val(r):
     return float(r["Metric Value"].replace(",", ""))
 
 
-out = [f"# Round 1 ncu evidence (B200, driver 580, CUDA 12.9) — final state of the round\n",
-       "Command profiled (each ncu pass only after the same command exited 0 without ncu): `python bench.py --steps 2 --warmup 3`.",
+PREC = os.environ.get("VD_BENCH_PRECISION", "fp16")
+out = [f"# ncu evidence {tag} (B200, driver 580, CUDA 12.9) — final state of the round, precision {PREC}\n",
+       "Command profiled (each ncu pass only after the same command exited 0 without ncu): `python bench.py --no-extras --steps 2 --warmup 3`.",
        "Recipe: `tools/gpu_profile.sh`; this file: `tools/summarize_profile.py`.  Numbers printed by runs under ncu are never bench values.\n"]
 
 # ---- 1. launch list ----
@@ -44,6 +45,7 @@ out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / tot:.1f} % |")
 conv = sum(t for k, (n, t) in agg.items() if "conv_igemm" in k or "stem_pool" in k or "maxpool" in k)
+# warm-up + timed + end-to-end steps all run the same kernels, so shares over the whole list are shares of a step
 comp = sum(t for k, (n, t) in agg.items() if "composite" in k)
 out.append(f"\nconvolution (conv_igemm + stem_pool) share: {100 * conv / tot:.1f} %; compositing share: {100 * comp / tot:.1f} %.")
 out.append(f"Raw list: `profiles/{tag}_launches_bench_steps2.csv`.\n")
@@ -74,6 +76,7 @@ for i, d in enumerate(L):
                f"{d['dram__bytes_write.sum'] / 1e6:.1f} | {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']:.1f} |")
 out.append(f"\nRaw: `profiles/{tag}_conv_step_dram.csv`.\n")
 with open(os.path.join(P, f"{tag}_conv_step_dram.csv"), "w") as f:
+    f.write(f"# ncu capture of the {len(L)} convolution launches of one timed step of `python bench.py --no-extras --steps 2 --warmup 3`, precision={PREC}\n")
     f.write("launch,kernel,us,dram_read_bytes,dram_write_bytes,tensor_pipe_active_pct\n")
     for i, d in enumerate(L):
         f.write(f'{i},"{d["kernel"]}",{d["gpu__time_duration.sum"] / 1e3:.2f},{d["dram__bytes_read.sum"]:.0f},{d["dram__bytes_write.sum"]:.0f},'
