@@ -321,9 +321,9 @@ int vd_jpeg_prepare_device(const uint8_t* data, size_t size, vd_jpeg_dev_hdr_t* 
 
 /* Decodes B files of ONE geometry (same width, height, components and sampling; Huffman and quantisation tables may
  * differ per file) into B RGB frames.  hdrs: [dev] B records; bytes: [dev] the buffer their scan_offset refers to;
- * frames_out: [dev] B descriptors of width x height uint8 HWC frames.  result: [dev] int32[B], 0 = ok, else a bit mask
- * (1 = the parallel entropy decoder did not converge, 2 = block count mismatch, 4 = state mismatch while writing:
- * decode that file on the CPU).  sub_bytes: bytes of entropy data per decoder thread (0 = default 512).  Never allocates, never synchronises. */
+ * frames_out: [dev] B descriptors of width x height uint8 HWC frames.  result: [dev] int32[B]; bits 0..7: 0 = ok, else a
+ * bit mask (1 = the parallel entropy decoder did not converge, 2 = block count mismatch, 4 = state mismatch while
+ * writing: decode that file on the CPU); bits 8..15: the synchronisation round after which nothing changed (diagnostic).  sub_bytes: bytes of entropy data per decoder thread (0 = default 512).  Never allocates, never synchronises. */
 size_t vd_jpeg_decode_workspace_bytes(int B, const vd_jpeg_dev_hdr_t* geometry, size_t max_scan_bytes);
 int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg_dev_hdr_t* geometry_host, const uint8_t* bytes,
                          int B, size_t max_scan_bytes, const vd_frame_t* frames_out, int32_t* result, int sub_bytes,

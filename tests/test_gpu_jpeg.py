@@ -129,7 +129,7 @@ def test_device_decoder_equals_cv2(hw, params, sub_bytes):
     dec = JpegDecoder(3, device=DEV, max_file_bytes=max(len(f) for f in files) + 1024, sub_bytes=sub_bytes)
     frames, on_cpu = dec.decode(files)
     never_syncs = cv2.IMWRITE_JPEG_QUALITY in params and params[-1] == 100
-    assert on_cpu == [] or (never_syncs and on_cpu == [1]), (on_cpu, dec.result_host.tolist())
+    assert on_cpu == [] or (never_syncs and on_cpu == [1]), (on_cpu, [hex(v) for v in dec.result_host.tolist()])
     for i, f in enumerate(files):
         got, want = frames[i].cpu().numpy(), _cv2_decode(f)
         assert np.array_equal(got, want), f"file {i}: {(got != want).sum()} bytes differ"

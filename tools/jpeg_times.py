@@ -21,6 +21,7 @@ for sub in (512, 1024, 2048, 4096):
     torch.cuda.synchronize()
     res[f"decode_wall_ms_sub{sub}"] = (time.perf_counter() - t0) / 5 * 1e3
     assert cpu == []
+    res[f"sync_rounds_sub{sub}"] = dec.sync_rounds()
     # GPU time of the kernels alone: re-enqueue on the already staged bytes
     import ctypes as C
     from vdesens_b200 import _lib

@@ -353,7 +353,11 @@ huff_scan_kernel(const __grid_constant__ Geo G, DecWs ws, int32_t* __restrict__ 
     const uint32_t tot = s_carry;
     const bool count_ok = tot == static_cast<uint32_t>(G.total_blocks) || tot == static_cast<uint32_t>(G.total_blocks) + 1u;
     const bool converged = ws.changed[static_cast<size_t>(f) * kRounds + (kRounds - 1)] == 0;
-    result[f] = (converged ? 0 : 1) | (count_ok ? 0 : 2);      // 1 = not converged, 2 = block count off (4 = desync, write pass)
+    int first_quiet = kRounds;                                  // first round in which no exit state changed
+    for (int r = kRounds - 1; r >= 1; --r)
+      if (ws.changed[static_cast<size_t>(f) * kRounds + r] == 0) first_quiet = r;
+    // bits 0..7: 1 = not converged, 2 = block count off (4 = desync, write pass); bits 8..15: rounds it took
+    result[f] = (converged ? 0 : 1) | (count_ok ? 0 : 2) | (first_quiet << 8);
   }
 }
 
@@ -364,7 +368,7 @@ huff_write_kernel(const vd_jpeg_dev_hdr_t* __restrict__ hdrs, const __grid_const
   const HuffS* s_dc = reinterpret_cast<const HuffS*>(hdrs[f].dc);
   const HuffS* s_ac = reinterpret_cast<const HuffS*>(hdrs[f].ac);
   const uint8_t* s_t = hdrs[f].td;
-  if (result[f] != 0) return;
+  if ((result[f] & 0xFF) != 0) return;
   const uint32_t total_bits = ws.ulen[f] * 8u;
   const int i = blockIdx.x * kSubThreads + threadIdx.x;
   const uint32_t start_bit = static_cast<uint32_t>(i) * static_cast<uint32_t>(ws.sub_bits);
