@@ -575,7 +575,28 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-        run_ours(args)
+        # rank 0 prints ONE JSON line on stdout: anything a library writes to file descriptor 1 on the way (NCCL prints
+        # its version banner there when the communicator comes up) goes to stderr instead
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        buf = []
+        real_print = print
+
+        def capture(*a, **k):
+            buf.append(" ".join(str(x) for x in a))
+
+        globals()["print"] = capture
+        try:
+            run_ours(args)
+        finally:
+            globals()["print"] = real_print
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+        for line in buf:
+            real_print(line)
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
