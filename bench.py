@@ -402,6 +402,37 @@ def gpu_baseline(dev, wl, sd, frames, plates, steps=3):
             "network_only_frames_per_s": B / (acc["network_cudnn_tf32"] / steps)}
 
 
+def letterbox_ingest_extra(dev, precision):
+    """the GENERIC ingest kernel (cv2's fixed-point bilinear letterbox, reference utils/utils.py:8-18) on a real down-scale:
+    16 resident 4K frames -> the 1080p network input; bytes = 4 source pixels x 3 B read per output pixel (upper bound of
+    what the 2x2 taps touch at scale 2) + 8 B written"""
+    import ctypes as C
+    from vdesens_b200 import _lib, ops, synth
+    H, W, B, ih, iw = 1080, 1920, 16, 2160, 3840
+    lib = _lib.lib(precision)
+    frames = torch.from_numpy(np.stack([synth.synthetic_frame(ih, iw, 9100 + i) for i in range(2)])).to(dev)
+    fl = [frames[i % 2] for i in range(B)]
+    desc = ops.frame_descriptors(fl)
+    x0 = torch.zeros((B, H, ops.x0_pitch(W), 4), dtype=_lib.torch_dtype(precision), device=dev)
+    mean = (C.c_float * 3)(104.0, 117.0, 123.0)
+    st = torch.cuda.current_stream(dev)
+    s = C.c_void_p(st.cuda_stream)
+    with torch.cuda.device(dev):
+        for _ in range(3):
+            _lib.check(lib.vd_ingest_u8hwc(C.c_void_p(desc.data_ptr()), B, C.c_void_p(x0.data_ptr()), H, W, mean, s), "vd_ingest_u8hwc", lib)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10):
+            _lib.check(lib.vd_ingest_u8hwc(C.c_void_p(desc.data_ptr()), B, C.c_void_p(x0.data_ptr()), H, W, mean, s), "vd_ingest_u8hwc", lib)
+        e1.record(st)
+        st.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    nbytes = B * H * W * (12 + 8)
+    hbm_peak, _, _ = load_peaks()
+    return {"what": "vd_ingest_u8hwc: 16 x 2160x3840 -> 1080x1920 letterbox (scale 0.5), bilinear bit-exact with cv2",
+            "ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / hbm_peak}
+
+
 def dir_loop_extra(n_frames=192):
     """SURVEY §8f rows N1 + N2: the directory frame loop (JPEG files in -> detect + blur -> JPEG files out) with the codec on
     the GPU against the same loop with cv2 thread pools and against the reference's schedule; tools/dir_loop_bench.py in
@@ -555,6 +586,7 @@ def run_ours(args):
             line["precisions"] = {p: short_summary(args.config, p, dev, 5 if p != "fp32x" else 3)
                                   for p in ("bf16", "fp16", "fp32x") if p != precision}
             line["other_configs"] = {c: short_summary(c, precision, dev, 5) for c in ("c3", "c5") if c != args.config}
+            line["ingest_letterbox"] = letterbox_ingest_extra(dev, precision)
             line["dir_loop"] = dir_loop_extra()
     print(json.dumps(line))
     if world > 1:

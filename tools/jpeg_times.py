@@ -12,7 +12,7 @@ W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
 imgs = [synth.synthetic_frame(H, W, 8000 + i) for i in range(B)]
 files = [cv2.imencode(".jpg", cv2.cvtColor(im, cv2.COLOR_RGB2BGR))[1].tobytes() for im in imgs]
 res = {"B": B, "frame": [H, W], "file_MB": sum(len(f) for f in files) / B / 1e6}
-for sub in (512, 1024, 2048, 4096):
+for sub in (256, 512, 1024, 2048):
     dec = JpegDecoder(B, sub_bytes=sub)
     dec.decode(files); dec.decode(files)
     t0 = time.perf_counter()
@@ -20,7 +20,7 @@ for sub in (512, 1024, 2048, 4096):
         frames, cpu = dec.decode(files)
     torch.cuda.synchronize()
     res[f"decode_wall_ms_sub{sub}"] = (time.perf_counter() - t0) / 5 * 1e3
-    assert cpu == []
+    res[f"on_cpu_sub{sub}"] = cpu
     res[f"sync_rounds_sub{sub}"] = dec.sync_rounds()
     # GPU time of the kernels alone: re-enqueue on the already staged bytes
     import ctypes as C

@@ -244,38 +244,50 @@ __device__ __forceinline__ uint32_t decode_range(const uint8_t* __restrict__ U, 
     }
   };
   locate();
-  while (p < end_bit) {
-    const uint32_t w = peek32(U, p);
-    const int c = G.blk_comp[b];
-    int len;
-    if (k == 0) {
-      const int t = huff_symbol(dc[comp_td[c]], w, len);
-      if (t < 0 || t > 15) { p += 1; continue; }
-      if (WRITE && dst && t) {
-        const uint32_t v = (w << len) >> (32 - t);
-        const int m = static_cast<int>(v >> (t - 1)) - 1;                // T.81 EXTEND
-        dst[0] = static_cast<int16_t>(static_cast<int>(v) + (m & (1 - (1 << t))));
-      }
-      p += len + t;
-      k = 1;
-    } else {
-      const int rs = huff_symbol(ac[comp_ta[c]], w, len);
-      if (rs < 0) { p += 1; continue; }
-      const int r = rs >> 4, s = rs & 15;
-      if (s == 0) {
-        k = (r == 15) ? k + 16 : 64;
-        p += len;
-      } else {
-        k += r;
-        if (WRITE && dst && k < 64) {
-          const uint32_t v = (w << len) >> (32 - s);
-          const int m = static_cast<int>(v >> (s - 1)) - 1;
-          dst[kZig[k]] = static_cast<int16_t>(static_cast<int>(v) + (m & (1 - (1 << s))));
-        }
-        ++k;
-        p += len + s;
-      }
+  // Bit reader: a 64-bit window that always holds >= 32 valid bits starting at bit p, refilled one big-endian word at a
+  // time; the NEXT word is loaded as soon as the previous one has been merged, so its latency hides behind the ~5
+  // symbols a word carries.  (The first version read two words from memory for every symbol: ncu showed the decoder
+  // threads — ~6 warps per SM, nothing to hide latency with — stalled on those loads 5x as long as they issued.)
+  const uint32_t* U32 = reinterpret_cast<const uint32_t*>(U);
+  uint32_t nextw = (p >> 5) + 2;
+  unsigned long long buf = (static_cast<unsigned long long>(__byte_perm(U32[p >> 5], 0, 0x0123)) << 32) |
+                           __byte_perm(U32[(p >> 5) + 1], 0, 0x0123);
+  buf <<= (p & 31);
+  int valid = 64 - static_cast<int>(p & 31);
+  uint32_t ahead = __byte_perm(U32[nextw], 0, 0x0123);
+  auto consume = [&](int n) {
+    buf <<= n;
+    valid -= n;
+    p += static_cast<uint32_t>(n);
+    if (valid <= 32) {
+      buf |= static_cast<unsigned long long>(ahead) << (32 - valid);
+      valid += 32;
+      ++nextw;
+      ahead = p < end_bit ? __byte_perm(U32[nextw], 0, 0x0123) : 0u;
     }
+  };
+  // One code path for DC and AC symbols (selects instead of branches): the threads of a warp decode unrelated streams.
+  // Only the long-code path of huff_symbol, block ends and stores still diverge.
+  while (p < end_bit) {
+    const uint32_t w = static_cast<uint32_t>(buf >> 32);
+    const int c = G.blk_comp[b];
+    const bool isdc = k == 0;
+    const HuffS& tbl = isdc ? dc[comp_td[c]] : ac[comp_ta[c]];
+    int len;
+    const int sym = huff_symbol(tbl, w, len);
+    if (sym < 0 || (isdc && sym > 15)) { consume(1); continue; }     // no code matches (a desynchronised decoder): step one bit
+    const int run = isdc ? 0 : (sym >> 4);
+    const int size = isdc ? sym : (sym & 15);
+    const bool eob = !isdc && size == 0 && run != 15;
+    const bool zrl = !isdc && size == 0 && run == 15;
+    const int kc = isdc ? 0 : k + run;                                 // coefficient this symbol carries (if size > 0)
+    if (WRITE && dst && size > 0 && kc < 64) {
+      const uint32_t v = (w << len) >> (32 - size);
+      const int m = static_cast<int>(v >> (size - 1)) - 1;            // T.81 EXTEND
+      dst[kZig[kc]] = static_cast<int16_t>(static_cast<int>(v) + (m & (1 - (1 << size))));
+    }
+    consume(len + size);
+    k = eob ? 64 : (zrl ? k + 16 : kc + 1);
     if (k >= 64) {
       k = 0;
       b = b + 1 == G.nb ? 0 : b + 1;
@@ -594,7 +606,7 @@ int reconstruct(const vd_jpeg_dev_hdr_t* hdrs, const Geo& G, const DecWs& ws, in
 extern "C" size_t vd_jpeg_decode_workspace_bytes(int B, const vd_jpeg_dev_hdr_t* geometry, size_t max_scan_bytes) {
   if (B <= 0 || !geometry || check_geometry(geometry) != VD_OK) return 0;
   const Geo G = make_geo(*geometry);
-  return carve(nullptr, B, G, max_scan_bytes, 256, nullptr) + 4096;      // sized for the smallest subsequence allowed
+  return carve(nullptr, B, G, max_scan_bytes, 64, nullptr) + 4096;       // sized for the smallest subsequence allowed
 }
 
 extern "C" int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg_dev_hdr_t* geometry_host,
@@ -605,7 +617,7 @@ extern "C" int vd_jpeg_decode_batch(const vd_jpeg_dev_hdr_t* hdrs, const vd_jpeg
   VD_REQUIRE(B > 0 && B <= 65535 && max_scan_bytes > 0 && max_scan_bytes < (1ull << 28), "vd_jpeg_decode_batch: bad extent");
   if (check_geometry(geometry_host) != VD_OK) return VD_ERR_INVALID;
   if (sub_bytes <= 0) sub_bytes = 512;
-  VD_REQUIRE(sub_bytes >= 256 && sub_bytes <= 65536 && sub_bytes % 4 == 0, "vd_jpeg_decode_batch: sub_bytes must be a multiple of 4 in [256, 65536]");
+  VD_REQUIRE(sub_bytes >= 64 && sub_bytes <= 65536 && sub_bytes % 4 == 0, "vd_jpeg_decode_batch: sub_bytes must be a multiple of 4 in [64, 65536]");
   VD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vd_jpeg_decode_batch: workspace must be 256-B aligned");
   const Geo G = make_geo(*geometry_host);
   VD_REQUIRE(G.H <= 65535, "vd_jpeg_decode_batch: frame too tall");
