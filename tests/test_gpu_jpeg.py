@@ -200,3 +200,35 @@ def test_directory_loop_with_the_codec_on_the_device_equals_the_host_loop(tmp_pa
     # "auto" picks the device codec for such a directory; a PNG directory keeps the host codec
     assert combine_detect.batch_process_images(str(src), str(tmp_path / "auto"), det, None, batch_size=4, mode="gauss", ksize=15) == \
         combine_detect.batch_process_images(str(src), str(tmp_path / "host2"), det, None, batch_size=4, mode="gauss", ksize=15, io="host")
+
+
+def test_device_decoder_survives_corrupt_entropy_data():
+    """random damage inside the entropy-coded segment (bit flips, zeroed runs, a truncated tail): the decoder kernels
+    must neither fault nor hang — they either flag the file (CPU fallback) or produce SOME frame of the right shape — and
+    the decoder object keeps working for the next, intact batch"""
+    from vdesens_b200.jpeg import JpegDecoder, prepare_device
+    rng = np.random.default_rng(99)
+    img = _image(135, 241, "smooth", 1)
+    good = _file(img)
+    h = prepare_device(good)
+    s0, s1 = h.scan_offset, h.scan_offset + h.scan_bytes
+    dec = JpegDecoder(4, device=DEV, max_file_bytes=len(good) + 4096,
+                      fallback=lambda data: np.zeros((135, 241, 3), np.uint8))         # never hand corrupt data to cv2 here
+    for trial in range(6):
+        files = []
+        for i in range(4):
+            b = bytearray(good)
+            if trial % 3 == 0:
+                for _ in range(1 + 5 * i):
+                    b[int(rng.integers(s0, s1))] ^= 1 << int(rng.integers(0, 8))
+            elif trial % 3 == 1:
+                a = int(rng.integers(s0, s1 - 64))
+                b[a:a + 16 * (i + 1)] = bytes(16 * (i + 1))
+            else:
+                del b[s1 - 50 * (i + 1):s1]
+            files.append(bytes(b))
+        frames, on_cpu = dec.decode(files)
+        torch.cuda.synchronize()
+        assert tuple(frames.shape) == (4, 135, 241, 3)
+    frames, on_cpu = dec.decode([good] * 4)
+    assert on_cpu == [] and np.array_equal(frames[0].cpu().numpy(), _cv2_decode(good))

@@ -11,6 +11,8 @@ Everything outside the per-frame arithmetic (record unpacking, ffmpeg extraction
 logging: reference :21-89, :279-990) is out of scope.
 """
 import os
+import queue
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -196,9 +198,11 @@ def _device_jpeg_loop(groups, output_dir, face_detector, plate_detector, batch_s
     """The frame loop with the JPEG codec on the device: file bytes -> GPU (Huffman decode, IDCT,
     up-sampling, colour) -> detect + composite on the resident frames -> GPU (DCT, quantisation, Huffman encode) -> file
     bytes.  Pixels equal cv2.imread's and files equal cv2.imwrite's byte for byte, so the output directory is identical
-    to the host loop's.  Three batches are in flight: batch i+1 decodes and batch i-1 encodes (each on its own stream
-    and worker thread) while batch i is in the detector.  Returns (frames, faces, plates) or None when the first file is
-    not something the device decoder takes (the caller then runs the host loop)."""
+    to the host loop's.  Three batches are in flight: a decode thread (files -> resident frames, plate provider), the
+    caller's thread (enqueues ingest / network / NMS / compositing and never synchronises: batch k+1 queues right behind
+    batch k on the detector's stream) and an encode thread (its stream waits for the batch's event), each stage on its own
+    CUDA stream.  Returns (frames, faces, plates) or None when the first file is not something the device decoder takes
+    (the caller then runs the host loop)."""
     from vdesens_b200 import jpeg as vjpeg
     first = _read_bytes(groups[0][0])
     try:
@@ -214,9 +218,25 @@ def _device_jpeg_loop(groups, output_dir, face_detector, plate_detector, batch_s
     groups = [g[s:s + B] for g in groups for s in range(0, len(g), B)]
     dec = vjpeg.JpegDecoder(B, device=dev, max_file_bytes=max(4 << 20, 2 * len(first)))
     enc = vjpeg.JpegEncoder(B, H, W, device=dev, quality=quality)
-    slots = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
-    n_frames = n_faces = n_plates = 0
-    scale = np.array([W, H, W, H], np.float32)
+    DEPTH = 3
+
+    class Slot:                                   # one in-flight batch: resident frames + everything that refers to them
+        def __init__(self):
+            self.frames = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+            self.desc, self.unlb, self.identity = eng.frame_records(self.frames)
+            self.eb = torch.zeros((B, eng.max_ext, 4), dtype=torch.int32).pin_memory()
+            self.ec = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            self.rows = torch.zeros((B, eng.max_det, 16), dtype=torch.float32).pin_memory()
+            self.counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            self.status = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self.ev_done = torch.cuda.Event()
+            self.free = threading.Event()
+            self.free.set()
+
+    with torch.cuda.device(dev):
+        slots = [Slot() for _ in range(DEPTH)]
+    totals = [0, 0, 0]                            # frames, faces, plates
+    errors = []
 
     def host_batch(files):
         """one batch through the host codec (a file the device decoder cannot take alongside the others, an oversized
@@ -229,60 +249,103 @@ def _device_jpeg_loop(groups, output_dir, face_detector, plate_detector, batch_s
             save_output_image(img, os.path.join(output_dir, "processed_" + os.path.basename(pth)))
         return len(files), sum(len(r[1]) for r in res), sum(len(p) for p in plates)
 
-    with ThreadPoolExecutor(max_workers=_io_workers()) as fpool, ThreadPoolExecutor(max_workers=1) as dpool, \
-            ThreadPoolExecutor(max_workers=1) as epool, ThreadPoolExecutor(max_workers=1) as plate_pool:
+    q_in, q_out = queue.Queue(maxsize=DEPTH), queue.Queue(maxsize=DEPTH)
+    with ThreadPoolExecutor(max_workers=_io_workers()) as fpool:
 
-        def stage_in(k):
-            files = groups[k]
-            blobs = list(fpool.map(_read_bytes, files))
-            with torch.cuda.device(dev):
-                frames, _ = dec.decode(blobs, out=slots[k % 3])
-            return frames
-
-        def stage_out(k, n):
-            files = groups[k]
-            with torch.cuda.device(dev):
-                blobs = enc.encode(slots[k % 3][:n])
-            list(fpool.map(_write_bytes, [os.path.join(output_dir, "processed_" + os.path.basename(p)) for p in files], blobs))
-
-        pending_out = []                                  # encode futures, oldest first
-        fut_in = dpool.submit(stage_in, 0)
-        for k, files in enumerate(groups):
-            n = len(files)
+        def decode_stage():
+            """files -> resident frames (+ the plate boxes: the provider wants HOST frames, so it gets one D2H of the decoded
+            batch here, off the detector's thread)"""
             try:
-                frames = fut_in.result()
-            except Exception:                             # noqa: BLE001: this batch goes through the host codec
-                frames = None
-            # slot (k+1) % 3 was last used by batch k-2: its encode must have finished before batch k+1 decodes into it
-            while len(pending_out) > 1:
-                pending_out.pop(0).result()
-            if k + 1 < len(groups):
-                fut_in = dpool.submit(stage_in, k + 1)
-            try:
-                if frames is None:
-                    a, b, c = host_batch(files)
-                    n_frames, n_faces, n_plates = n_frames + a, n_faces + b, n_plates + c
+                for k, files in enumerate(groups):
+                    slot = slots[k % DEPTH]
+                    slot.free.wait()
+                    slot.free.clear()
+                    item = (k, None, None)
+                    try:
+                        blobs = list(fpool.map(_read_bytes, files))
+                        with torch.cuda.device(dev):
+                            frames, _ = dec.decode(blobs, out=slot.frames)
+                            plates = [[] for _ in files]
+                            if plate_detector is not None:
+                                plates = _plates_of(plate_detector, list(frames.cpu().numpy()))
+                        item = (k, plates, None)
+                    except Exception as e:        # noqa: BLE001: this batch goes through the host codec
+                        item = (k, None, e)
+                    q_in.put(item)
+            finally:
+                q_in.put(None)
+
+        def encode_stage():
+            """resident, composited frames -> files; nothing here waits for the detector's stream on the host: the encoder's
+            stream waits for the batch's event"""
+            while True:
+                item = q_out.get()
+                if item is None:
+                    return
+                k, n, n_plates = item
+                slot, files = slots[k % DEPTH], groups[k]
+                try:
+                    with torch.cuda.device(dev):
+                        enc.stream.wait_event(slot.ev_done)
+                        enc.enqueue(slot.desc)
+                        blobs = enc.fetch(n)
+                        eng.check_status(int(slot.status[0]))       # ev_done precedes the encoder's work: the rows are here
+                    list(fpool.map(_write_bytes, [os.path.join(output_dir, "processed_" + os.path.basename(p)) for p in files], blobs))
+                    totals[0] += n
+                    totals[1] += int(slot.counts[:n].sum())
+                    totals[2] += n_plates
+                except Exception as e:            # noqa: BLE001 (reference :226)
+                    errors.append((f"batch of {n} frames", e))
+                finally:
+                    slot.free.set()
+
+        td, te = threading.Thread(target=decode_stage, daemon=True), threading.Thread(target=encode_stage, daemon=True)
+        td.start()
+        te.start()
+        try:
+            while True:
+                item = q_in.get()
+                if item is None:
+                    break
+                k, plates, err = item
+                slot, files = slots[k % DEPTH], groups[k]
+                n = len(files)
+                if err is not None:
+                    # the host path reuses the engine: let the batches already queued on it finish first
+                    try:
+                        eng.stream.synchronize()
+                        a, b, c = host_batch(files)
+                        totals[0] += a
+                        totals[1] += b
+                        totals[2] += c
+                    except Exception as e:        # noqa: BLE001 (reference :226)
+                        errors.append((f"batch of {n} frames", e))
+                    slot.free.set()
                     continue
+                # detector: enqueue only — no host synchronisation on this thread, batch k+1 queues right behind batch k
                 with torch.cuda.device(dev):
-                    pf = None
-                    if plate_detector is not None:        # the provider wants host frames: one D2H of the decoded batch
-                        host_frames = list(frames.cpu().numpy())
-                        pf = plate_pool.submit(_plates_of, plate_detector, host_frames)
-                    eng.set_frames(slots[k % 3])
+                    eb, ec = slot.eb.numpy(), slot.ec.numpy()
+                    ec[:] = 0
+                    for i, bl in enumerate(plates):
+                        if len(bl) > eng.max_ext:
+                            raise RuntimeError(f"{len(bl)} external boxes exceed max_ext={eng.max_ext}")
+                        ec[i] = len(bl)
+                        for j, bx in enumerate(bl):
+                            eb[i, j] = bx
+                    eng.bind_frames_async(slot.desc, slot.unlb, slot.identity)
+                    eng.upload_ext_async(slot.eb, slot.ec)
                     eng.forward()
-                    plates = pf.result() if pf is not None else [[] for _ in range(n)]
-                    eng.set_ext_boxes(plates + [[] for _ in range(B - n)])
                     eng.enqueue_composite(mode, mosaic_level, ksize, sigma)
-                    rows, counts = eng.fetch_results()
-                pending_out.append(epool.submit(stage_out, k, n))
-                n_frames += n
-                n_faces += int(counts[:n].sum())
-                n_plates += sum(len(p) for p in plates)
-            except Exception as e:                        # noqa: BLE001 (reference :226)
-                failed(f"batch of {n} frames", e)
-        for f in pending_out:
-            f.result()
-    return n_frames, n_faces, n_plates
+                    eng.download_results_async(slot.rows, slot.counts, slot.status)
+                    slot.ev_done.record(eng.stream)
+                q_out.put((k, n, sum(len(p) for p in plates)))
+        finally:
+            q_out.put(None)
+            te.join()
+            td.join(timeout=5.0)
+    for what, e in errors:
+        failed(what, e)
+    return tuple(totals)
 
 
 def batch_process_images(input_dir, output_dir, face_detector, plate_detector, batch_size=16, mode="mosaic",
