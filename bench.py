@@ -433,6 +433,35 @@ def letterbox_ingest_extra(dev, precision):
             "ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / hbm_peak}
 
 
+def tensor_peak_probe(dev, seconds=1.5):
+    """context for `roofline.frac` of the fp16 headline: MEASURED_PEAKS.json holds the sustained cuBLAS peak for BF16 only.
+    Under the 1 kW software power cap fp16 operands (three more mantissa bits toggling in every multiplier) run at lower SM
+    clocks than bf16 ones — for cuBLAS exactly as for this repo's kernels.  Same recipe as the driver's (8192^3 matmul back
+    to back), both dtypes, a couple of seconds each."""
+    out = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        a = torch.randn((8192, 8192), device=dev, dtype=dt)
+        b = torch.randn((8192, 8192), device=dev, dtype=dt)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                a @ b
+            n += 20
+            torch.cuda.synchronize(dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name + "_tflops_sustained"] = n * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+    torch.cuda.empty_cache()
+    out["note"] = "torch.matmul 8192^3 back to back on this box, this process (library kernel, for context only)"
+    return out
+
+
 def dir_loop_extra(n_frames=192):
     """SURVEY §8f rows N1 + N2: the directory frame loop (JPEG files in -> detect + blur -> JPEG files out) with the codec on
     the GPU against the same loop with cv2 thread pools and against the reference's schedule; tools/dir_loop_bench.py in
@@ -587,6 +616,10 @@ def run_ours(args):
                                   for p in ("bf16", "fp16", "fp32x") if p != precision}
             line["other_configs"] = {c: short_summary(c, precision, dev, 5) for c in ("c3", "c5") if c != args.config}
             line["ingest_letterbox"] = letterbox_ingest_extra(dev, precision)
+            line["tensor_peak_probe"] = tensor_peak_probe(dev)
+            pk = line["tensor_peak_probe"].get({"fp16": "fp16", "bf16": "bf16"}.get(precision, "bf16") + "_tflops_sustained")
+            if pk:
+                line["roofline"]["frac_vs_same_dtype_probe"] = line["roofline"]["achieved"] / pk
             line["dir_loop"] = dir_loop_extra()
     print(json.dumps(line))
     if world > 1:
