@@ -578,65 +578,84 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       const int spanw = GA_W / 4 + kw;                       // words per plane row: byte i = pixel x0 - r + i
       uint32_t* planes = reinterpret_cast<uint32_t*>(dsm);   // [3][GA_H][spanw]
       const int ngroups = (cols + 2 * r + 3) >> 2;           // 4-pixel groups per row that feed valid outputs
+      // Stage 1: the raw bytes of every source row, 16 bytes per load.  (The first packed-plane version fetched every
+      // 4-pixel group with four 4-byte ld.global.cg: 48 L2 sector requests per 384 useful bytes, the SMs spent more time
+      // waiting for those than computing.)  Row ly of the tile reads frame bytes [b0, b1) of source row ys(ly); they land
+      // in s_raw[ly] at the row's own 16-byte phase, so every vector load is aligned on both sides.
+      const int px_lo = max(0, x0 - r), px_hi = min(bw, x0 + cols + r);     // box-local pixel range the tile reads
+      const int raw_pitch = ((GA_W + 2 * r) * 3 + 15 + 15) & ~15;            // bytes per staged row
+      uint8_t* s_raw = dsm + 3 * GA_H * spanw * 4;                           // [GA_H][raw_pitch]
+      const uint8_t* fr_end = fr.ptr + static_cast<size_t>(fr.h - 1) * fr.pitch + static_cast<size_t>(fr.w) * 3;
+      const int row_len = (px_hi - px_lo) * 3;
+      const int chunks = (row_len + 15 + 15) >> 4;                           // 16-byte chunks per row incl. both ragged ends
+      for (int base = 0; base < vrows * chunks; base += 4 * kThreads) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kThreads + tid;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < vrows * chunks) {
+            const int ly = i / chunks, ch = i - ly * chunks;
+            int ys = v0 + ly - r4;
+            if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+            const uint8_t* p0 = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + (m.x1 + px_lo) * 3;
+            const uint8_t* pc = p0 - (reinterpret_cast<uintptr_t>(p0) & 15) + 16 * ch;      // aligned chunk
+            if (pc >= fr.ptr && pc + 16 <= fr_end) {
+              v[u] = __ldcg(reinterpret_cast<const uint4*>(pc));
+            } else {                                                                        // chunk straddles the frame buffer's end
+              uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u]);
+              for (int k2 = 0; k2 < 16; ++k2)
+                if (pc + k2 >= fr.ptr && pc + k2 < fr_end) vb[k2] = __ldcg(pc + k2);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kThreads + tid;
+          if (i < vrows * chunks) {
+            const int ly = i / chunks, ch = i - ly * chunks;
+            *reinterpret_cast<uint4*>(s_raw + ly * raw_pitch + 16 * ch) = v[u];
+          }
+        }
+      }
+      __syncthreads();
+      // Stage 2: de-interleave into byte planes.  Interior groups: 12 contiguous bytes = four shared-memory words, a funnel
+      // shift and six PRMT; groups that touch the box border: REFLECT_101 per pixel (reflected pixels stay inside [px_lo, px_hi)).
       const int total = vrows * ngroups;
-      for (int base = 0; base < total; base += 4 * kThreads) {
-        uint32_t w[4][4];
-        int sh8[4];                                          // 8 * misalignment of the group, -1 = slow path
+      for (int i = tid; i < total; i += kThreads) {
+        const int ly = i / ngroups, g = i - ly * ngroups;
+        const int px = x0 - r + 4 * g;                       // box-local pixel of the group's first byte
+        int ys = v0 + ly - r4;
+        if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
+        const uint8_t* p0 = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + (m.x1 + px_lo) * 3;
+        const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(p0) & 15);          // s_raw[ly][phase] = pixel px_lo
+        const uint8_t* rrow = s_raw + ly * raw_pitch + phase;
+        uint32_t q0, q1, q2;
+        if (px >= px_lo && px + 3 < px_hi) {
+          const int off = (px - px_lo) * 3 + phase;
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_raw + ly * raw_pitch + (off & ~3));
+          const int sh8 = (off & 3) * 8;
+          const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+          const uint32_t a = __funnelshift_r(w0, w1, sh8), b = __funnelshift_r(w1, w2, sh8), c = __funnelshift_r(w2, w3, sh8);
+          q0 = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);     // bytes 0, 3, 6, 9 of the 12-byte group
+          q1 = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);     // bytes 1, 4, 7, 10
+          q2 = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);     // bytes 2, 5, 8, 11
+        } else {
+          q0 = q1 = q2 = 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = base + u * kThreads + tid;
-          sh8[u] = -1;
-          if (i < total) {
-            const int ly = i / ngroups, g = i - ly * ngroups;
-            const int px = x0 - r + 4 * g;                   // box-local pixel of the group's first byte
-            int ys = v0 + ly - r4;
-            if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
-            const int gy = m.y1 + ys;
-            // fast: four in-range pixels, read as four aligned words; the last word may reach 3 bytes past the group,
-            // which must still be inside the frame buffer
-            if (px >= 0 && px + 3 < bw && (m.x1 + px + 4 < fr.w || gy < fr.h - 1)) {
-              const uint8_t* p = img + static_cast<size_t>(gy) * fr.pitch + (m.x1 + px) * 3;
-              const uint32_t a0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 3);
-              const uint32_t* pa = reinterpret_cast<const uint32_t*>(p - a0);
-              w[u][0] = __ldcg(pa);
-              w[u][1] = __ldcg(pa + 1);
-              w[u][2] = __ldcg(pa + 2);
-              w[u][3] = a0 ? __ldcg(pa + 3) : 0u;
-              sh8[u] = static_cast<int>(a0 * 8);
-            }
+          for (int q = 0; q < 4; ++q) {
+            int xs = px + q;
+            if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
+            xs = min(max(xs, px_lo), px_hi - 1);             // (columns beyond cols + 2r feed no valid output)
+            const uint8_t* pp = rrow + (xs - px_lo) * 3;
+            q0 |= static_cast<uint32_t>(pp[0]) << (8 * q);
+            q1 |= static_cast<uint32_t>(pp[1]) << (8 * q);
+            q2 |= static_cast<uint32_t>(pp[2]) << (8 * q);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = base + u * kThreads + tid;
-          if (i >= total) continue;
-          const int ly = i / ngroups, g = i - ly * ngroups;
-          uint32_t p0, p1, p2;
-          if (sh8[u] >= 0) {
-            const uint32_t a = __funnelshift_r(w[u][0], w[u][1], sh8[u]), b = __funnelshift_r(w[u][1], w[u][2], sh8[u]),
-                           c = __funnelshift_r(w[u][2], w[u][3], sh8[u]);
-            p0 = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);     // bytes 0, 3, 6, 9 of the 12-byte group
-            p1 = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);     // bytes 1, 4, 7, 10
-            p2 = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);     // bytes 2, 5, 8, 11
-          } else {                                                       // box border: REFLECT_101 per pixel
-            int ys = v0 + ly - r4;
-            if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
-            const uint8_t* rowp = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + m.x1 * 3;
-            p0 = p1 = p2 = 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int xs = x0 - r + 4 * g + q;
-              if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
-              const uint8_t* p = rowp + xs * 3;
-              p0 |= static_cast<uint32_t>(__ldcg(p)) << (8 * q);
-              p1 |= static_cast<uint32_t>(__ldcg(p + 1)) << (8 * q);
-              p2 |= static_cast<uint32_t>(__ldcg(p + 2)) << (8 * q);
-            }
-          }
-          planes[(0 * GA_H + ly) * spanw + g] = p0;
-          planes[(1 * GA_H + ly) * spanw + g] = p1;
-          planes[(2 * GA_H + ly) * spanw + g] = p2;
-        }
+        planes[(0 * GA_H + ly) * spanw + g] = q0;
+        planes[(1 * GA_H + ly) * spanw + g] = q1;
+        planes[(2 * GA_H + ly) * spanw + g] = q2;
       }
       __syncthreads();
       // task = (channel, group of 4 virtual rows, word of 4 pixels): 16 sums h[rr][a] = sum_t q[t] * pixel(x0 + 4mm + a - r + t)
@@ -913,7 +932,8 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
     size_t a = static_cast<size_t>(GA_H0) * (GA_W0 + 2 * r) * 3;
     size_t b = static_cast<size_t>(GB_H0 + 2 * r) * GB_E0 * 2;
     if (taps.kw > 0) {
-      a = static_cast<size_t>(3) * GA_H * (GA_W / 4 + taps.kw) * 4;          // byte planes of the A tile
+      a = static_cast<size_t>(3) * GA_H * (GA_W / 4 + taps.kw) * 4 +         // byte planes of the A tile
+          static_cast<size_t>(GA_H) * ((((GA_W + 2 * r) * 3 + 15 + 15) & ~15) + 16);   // + its raw source rows
       b = static_cast<size_t>(2) * (GB_H / 4 + 1 + taps.kw) * GB_E * 4;      // HI / LO word rows of the B tile
     }
     // fused item: u8 source + u16 intermediate + the two reflect tables (bw + bh <= FUSE_MAX_PX + 1)
