@@ -22,8 +22,11 @@
 //     intersects the rectangle it reads;
 //   * a B tile waits for the A tiles of its own box that produce its scratch rows (+-radius) and for
 //     the A tiles that still have to read the frame pixels it is about to overwrite.
-// Every dependency is an item with a smaller index in the same frame, hence a smaller ticket, hence
-// already running or finished: the waits cannot deadlock (and are bounded by a watchdog bit).
+// The plan kernel fixes the ticket order of a frame's items (BoxMeta::posA / posB and the item map): the A tiles of
+// the boxes in box order, the B tiles of box j held back behind the A tiles of the next boxes (about one grid's worth
+// of tickets, so that they find their A tiles finished) but never past a later box that intersects box j.  Every
+// dependency therefore has a smaller ticket than its waiter, is already running or finished, and the waits cannot
+// deadlock (they are also bounded by a watchdog bit).
 // Frame and scratch reads use ld.global.cg because other SMs rewrite those bytes during the kernel.
 #include "common.cuh"
 
@@ -55,8 +58,11 @@ struct BoxMeta {
   int x1, y1, x2, y2;      // clipped; empty boxes have tA = tB = 0
   int tA, tB;              // fused box: tA = 1, tB = 0
   int sw, sh;              // mosaic: down-sampled size.  Gaussian dp4a path: sw = packed row groups (YG), sh = padded width
-  unsigned int item_base;  // first item of this box inside its frame
+  unsigned int item_base;  // first done-flag of this box inside its frame: A tiles, then B tiles
   int fused;
+  unsigned int posA, posB; // first TICKET-ORDER item of the A / B tiles inside the frame (plan kernel, lagged schedule)
+  int has_dep;             // 0: no earlier box of the frame intersects this one (its tiles have no writer to wait for)
+  int pad_;
   unsigned long long scratch_off;   // in u16 elements inside the frame's scratch region
 };
 
@@ -70,6 +76,7 @@ struct Ws {
   Header* hdr;
   BoxMeta* meta;       // [B][maxb]
   int* done;           // [B][items_cap] one flag per item
+  unsigned int* omap;  // [B][items_cap] ticket-order item -> (box << 1) | phase (0 = A, 1 = B)
   uint16_t* scratch;   // [B][scratch_elems]
   size_t scratch_elems;
   unsigned int items_cap;
@@ -89,7 +96,7 @@ __host__ inline size_t items_cap_for(int maxb, size_t scratch_px) { return 4 * s
 
 __host__ size_t ws_bytes(int B, int maxb, size_t scratch_px) {
   return al256(sizeof(unsigned int) * (B + 4)) + al256(sizeof(BoxMeta) * static_cast<size_t>(B) * maxb) +
-         al256(sizeof(int) * static_cast<size_t>(B) * items_cap_for(maxb, scratch_px)) +
+         2 * al256(sizeof(int) * static_cast<size_t>(B) * items_cap_for(maxb, scratch_px)) +
          al256(static_cast<size_t>(B) * scratch_px * 3 * 2) + 256;
 }
 
@@ -100,14 +107,16 @@ __host__ Ws carve(void* p0, int B, int maxb, size_t total_bytes, size_t* flag_by
   p += al256(sizeof(unsigned int) * (B + 4));
   w.meta = reinterpret_cast<BoxMeta*>(p);
   p += al256(sizeof(BoxMeta) * static_cast<size_t>(B) * maxb);
-  // split what is left: flags get 1 int per 128 scratch pixels (+ 4 per box), the rest is scratch
+  // split what is left: flags and the item map get 1 int each per 128 scratch pixels (+ 4 per box), the rest is scratch
   const size_t left = total_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(p0)) - 256;
-  const size_t fixed = sizeof(int) * static_cast<size_t>(B) * (4 * static_cast<size_t>(maxb) + 1024);
-  // scratch_px * (6 + 4/128) * B + fixed = left
-  const size_t scratch_px = static_cast<size_t>((left > fixed ? left - fixed : 0) / (static_cast<double>(B) * (6.0 + 4.0 / 128.0)));
+  const size_t fixed = 2 * sizeof(int) * static_cast<size_t>(B) * (4 * static_cast<size_t>(maxb) + 1024);
+  // scratch_px * (6 + 8/128) * B + fixed = left
+  const size_t scratch_px = static_cast<size_t>((left > fixed ? left - fixed : 0) / (static_cast<double>(B) * (6.0 + 8.0 / 128.0)));
   w.items_cap = static_cast<unsigned int>(4 * static_cast<size_t>(maxb) + scratch_px / 128 + 1024 - 8);
   w.done = reinterpret_cast<int*>(p);
   *flag_bytes = sizeof(int) * static_cast<size_t>(B) * w.items_cap;
+  p += al256(*flag_bytes);
+  w.omap = reinterpret_cast<unsigned int*>(p);
   p += al256(*flag_bytes);
   w.scratch = reinterpret_cast<uint16_t*>(p);
   const size_t used = static_cast<size_t>(p - static_cast<uint8_t*>(p0));
@@ -123,10 +132,12 @@ __global__ void __launch_bounds__(1024)
 composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float* __restrict__ det_rows,
                       const int* __restrict__ det_count, int max_det, const int* __restrict__ ext_boxes,
                       const int* __restrict__ ext_count, int max_ext, int maxb, int mode, int mosaic_level,
-                      int ksize, int fast, uint32_t* __restrict__ status, Ws ws) {
+                      int ksize, int fast, unsigned int lag_items, uint32_t* __restrict__ status, Ws ws) {
   __shared__ unsigned int s_items[1024];
   __shared__ unsigned long long s_scr[1024];
   __shared__ unsigned int s_total;
+  __shared__ int4 s_rect[1024];
+  __shared__ unsigned short s_p[1024];
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_total = 0;
@@ -224,6 +235,92 @@ composite_plan_kernel(const vd_frame_t* __restrict__ frames, int B, const float*
     if (tid == 0) {
       if (overflow || nd + ne > maxb) atomicOr(status, VD_STAT_WORK_OVERFLOW);
       ws.hdr->frame_prefix[f + 1] = overflow ? 0u : item_carry;       // item count of this frame
+    }
+    if (overflow) return;
+    __syncthreads();                                                   // this CTA's meta rows are visible to all its threads
+
+    // ---- ticket order of the frame's items (posA / posB + the item map) ----
+    // The run kernel hands items out in ticket order, and a B tile needs A tiles of its own box: scheduled right behind
+    // them it would find them still running and the CTA would sit in the flag wait.  So the B tiles of box j are held back
+    // behind the A tiles of the following boxes until at least `lag_items` of those separate them — but never past a later
+    // box that overlaps box j, whose A tiles wait for exactly these B tiles (every wait must point at a smaller ticket:
+    // that is what keeps the flag waits deadlock-free).  Group k = [B tiles placed before box k][A tiles of box k];
+    // group nbx = the B tiles left over at the end.
+    BoxMeta* fmw = ws.meta + static_cast<size_t>(f) * maxb;
+    if (nbx <= 1024 && lag_items > 0) {
+      unsigned int* s_tA = reinterpret_cast<unsigned int*>(s_scr);
+      unsigned int* s_tB = s_tA + 1024;
+      const int j = tid;
+      unsigned int tA = 0, tB = 0;
+      int4 rc = make_int4(0, 0, 0, 0);
+      if (j < nbx) {
+        const BoxMeta mj = fmw[j];
+        tA = static_cast<unsigned int>(mj.tA); tB = static_cast<unsigned int>(mj.tB);
+        rc = make_int4(mj.x1, mj.y1, mj.x2, mj.y2);
+      }
+      s_rect[j] = rc; s_tA[j] = tA; s_tB[j] = tB;
+      __syncthreads();
+      int p = nbx;                                     // group the B tiles of box j go to
+      if (tB > 0) {
+        unsigned int between = 0;
+        int k = j + 1;
+        for (; k < nbx; ++k) {
+          if (s_tA[k] + s_tB[k] == 0) continue;
+          const int4 o = s_rect[k];
+          if (max(rc.x, o.x) < min(rc.z, o.z) && max(rc.y, o.y) < min(rc.w, o.w)) break;   // box k reads what these tiles write
+          if (between >= lag_items) break;
+          between += s_tA[k];
+        }
+        p = k;
+      }
+      s_p[j] = static_cast<unsigned short>(p);
+      s_items[j] = tA;
+      __syncthreads();
+      if (tB > 0 && p < nbx) atomicAdd(&s_items[p], tB);
+      __syncthreads();
+      const unsigned int G = s_items[j];               // items of group j
+      for (int off = 1; off < 1024; off <<= 1) {
+        unsigned int a = 0;
+        if (tid >= off) a = s_items[tid - off];
+        __syncthreads();
+        s_items[tid] += a;
+        __syncthreads();
+      }
+      const unsigned int incl = s_items[j];
+      __syncthreads();
+      s_items[j] = incl - G;                           // first item of group j
+      if (j == 1023) s_total = incl;
+      __syncthreads();
+      if (j < nbx) {
+        int dep = 0;                                   // does an earlier box write into this one?
+        for (int q = 0; q < j && !dep; ++q) {
+          const int4 o = s_rect[q];
+          dep = (s_tA[q] + s_tB[q]) != 0 && max(rc.x, o.x) < min(rc.z, o.z) && max(rc.y, o.y) < min(rc.w, o.w);
+        }
+        fmw[j].has_dep = dep;
+        unsigned int posB = 0;
+        if (tB > 0) {
+          unsigned int before = 0;                     // B tiles of earlier boxes in the same group
+          for (int q = 0; q < j; ++q)
+            if (s_p[q] == p) before += s_tB[q];
+          posB = (p < nbx ? s_items[p] : s_total) + before;      // group nbx starts where the groups 0 .. nbx-1 end
+        }
+        fmw[j].posA = s_items[j] + (G - tA);
+        fmw[j].posB = posB;
+      }
+    } else {
+      for (int k = tid; k < nbx; k += 1024) {
+        fmw[k].posA = fmw[k].item_base;
+        fmw[k].posB = fmw[k].item_base + static_cast<unsigned int>(fmw[k].tA);
+        fmw[k].has_dep = 1;                            // not analysed: the run kernel scans the earlier boxes
+      }
+    }
+    __syncthreads();
+    unsigned int* omap = ws.omap + static_cast<size_t>(f) * ws.items_cap;
+    for (int k = tid >> 5; k < nbx; k += 32) {         // one warp per box
+      const BoxMeta mk = fmw[k];
+      for (int i = tid & 31; i < mk.tA; i += 32) omap[mk.posA + i] = static_cast<unsigned int>(k) << 1;
+      for (int i = tid & 31; i < mk.tB; i += 32) omap[mk.posB + i] = (static_cast<unsigned int>(k) << 1) | 1u;
     }
   }
 }
@@ -340,8 +437,7 @@ __global__ void __launch_bounds__(kThreads, VD_COMP_MINB)
 composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int mode, int ksize, Taps taps,
                      uint32_t* __restrict__ status, Ws ws) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  __shared__ unsigned int s_ticket;
-  __shared__ int s_box;
+  __shared__ unsigned int s_tk;
   __shared__ unsigned int s_fprefix[130];
   __shared__ uint16_t s_q[256];
   __shared__ uint4 s_qt[KW_MAX];                  // s_qt[j] = (qa[0][j], qa[1][j], qa[2][j], qa[3][j]): one LDS.128 per tap word
@@ -359,56 +455,35 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
   const int r4 = (r + 3) & ~3;                               // dp4a path: halo rows above / below the box
   const int gb_e = kw > 0 ? GB_E : GB_E0, gb_h = kw > 0 ? GB_H : GB_H0;   // B tile geometry of the active Gaussian path
 
+  // The top barrier doubles as the end-of-item barrier: every thread's stores -> bar.sync -> st.release.gpu of the item's
+  // flag by one thread (release is cumulative over what the barrier ordered before it).  The ticket is taken only when the
+  // CTA is free to start the item: a ticket fetched ahead would sit idle for one item's duration while its dependants wait
+  // (measured: 0.38 -> 0.53 ms on the bench boxes).
+  int* my_flag = nullptr;
   while (true) {
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&ws.hdr->ticket, 1u);
+    if (tid == 0) {
+      if (my_flag) st_release(my_flag, 1);
+      s_tk = atomicAdd(&ws.hdr->ticket, 1u);
+    }
+    my_flag = nullptr;
     __syncthreads();
-    const unsigned int t = s_ticket;
+    const unsigned int t = s_tk;
     if (t >= total) break;
     const int f = static_cast<int>(t % static_cast<unsigned int>(B));
     const unsigned int local = t / static_cast<unsigned int>(B);
     if (local >= s_fprefix[f]) continue;                           // this frame has fewer items
+    const vd_frame_t fr = frames[f];                                // (issued early: in flight behind the map / box loads)
     const BoxMeta* fm = ws.meta + static_cast<size_t>(f) * maxb;
     int* done = ws.done + static_cast<size_t>(f) * ws.items_cap;
-    // owner box of the item: warp-parallel search over the (non-decreasing) item_base array — the last
-    // box with item_base <= local that actually owns items
-    if (tid < 32) {
-      int lo = 0, hi = maxb;                       // answer in [lo, hi)
-      while (hi - lo > 32) {
-        const int step = (hi - lo + 31) / 32;
-        const int idx = min(lo + tid * step, hi - 1);
-        const bool le = fm[idx].item_base <= local;
-        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, le);
-        const int last = 31 - __clz(bal);          // lane 0 always qualifies (item_base[lo] <= local)
-        const int nlo = min(lo + last * step, hi - 1);
-        hi = min(nlo + step, hi);
-        lo = nlo;
-      }
-      const int idx = lo + tid;
-      bool own = false;
-      if (idx < hi) {
-        const BoxMeta c = fm[idx];
-        own = c.item_base <= local && local < c.item_base + static_cast<unsigned int>(c.tA + c.tB);
-      }
-      const unsigned int bal = __ballot_sync(0xFFFFFFFFu, own);
-      if (tid == 0) s_box = bal ? lo + (__ffs(bal) - 1) : -1;
-    }
-    __syncthreads();
-    int k = s_box;
-    if (k < 0) {                                   // owner sits before `lo` (run of empty boxes): walk back
-      k = 0;
-      int lo2 = 0, hi2 = maxb - 1;
-      while (lo2 < hi2) {
-        const int mid = (lo2 + hi2 + 1) >> 1;
-        if (fm[mid].item_base <= local) lo2 = mid; else hi2 = mid - 1;
-      }
-      k = lo2;
-      while (k > 0 && !(local < fm[k].item_base + static_cast<unsigned int>(fm[k].tA + fm[k].tB))) --k;
-    }
+    // owner of the item: the plan kernel's map, ticket-order item -> (box, phase)
+    const unsigned int ent = __ldg(ws.omap + static_cast<size_t>(f) * ws.items_cap + local);
+    const int k = static_cast<int>(ent >> 1);
     const BoxMeta m = fm[k];
-    const int rel = static_cast<int>(local - m.item_base);
-    const bool phaseA = rel < m.tA;
-    const int tile = phaseA ? rel : rel - m.tA;
+    const int has_dep = m.has_dep;
+    const bool phaseA = (ent & 1u) == 0;
+    const int tile = static_cast<int>(local - (phaseA ? m.posA : m.posB));
+    my_flag = done + m.item_base + (phaseA ? tile : m.tA + tile);
     const int bw = m.x2 - m.x1, bh = m.y2 - m.y1;
     const int row3 = bw * 3;
 
@@ -416,14 +491,14 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     int tx = 0, ty = 0;
     if (mode == VD_MODE_MOSAIC) {
       if (phaseA) {
-        wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
+        if (has_dep) wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
       } else {
         const int tiles_x = (bw + MB_W - 1) / MB_W;
         ty = tile / tiles_x; tx = tile - ty * tiles_x;
         for (int a = tid; a < m.tA; a += kThreads) spin_flag(done + m.item_base + a, status);
       }
     } else if (m.fused) {
-      wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
+      if (has_dep) wait_writers(fm, done, k, m.x1, m.y1, m.x2, m.y2, mode, gb_e, gb_h, status);
     } else if (kw > 0) {
       if (phaseA) {
         // reads frame pixels: columns x0 - r .. x0 + cols + r (reflected ones stay inside that range), source rows of
@@ -434,7 +509,7 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         const int cx1 = max(0, x0 - r), cx2 = min(bw, x0 + GA_W + r);
         int cy1 = v0 - r4, cy2 = v0 + GA_H - r4;
         if (cy1 < 0 || cy2 > bh) { cy1 = 0; cy2 = bh; }
-        wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
+        if (has_dep) wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
       } else {
         // a B tile (rows [y0, y0 + rows), pixels [px1, px2)) waits for the A tiles of its own box that
         //   (RAW) produce the packed rows it consumes: virtual rows [y0 + d, y0 + rows + d + 2r), same pixel columns;
@@ -466,7 +541,7 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       ty = tile / tiles_x; tx = tile - ty * tiles_x;
       const int cx1 = max(0, tx * GA_W0 - r), cx2 = min(bw, tx * GA_W0 + GA_W0 + r);
       const int cy1 = ty * GA_H0, cy2 = min(bh, ty * GA_H0 + GA_H0);
-      wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
+      if (has_dep) wait_writers(fm, done, k, m.x1 + cx1, m.y1 + cy1, m.x1 + cx2, m.y1 + cy2, mode, gb_e, gb_h, status);
     } else {
       const int tiles_x = (row3 + GB_E0 - 1) / GB_E0;
       ty = tile / tiles_x; tx = tile - ty * tiles_x;
@@ -484,7 +559,6 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
     // acquiring thread's view to the whole CTA, no fence (and no L1 invalidation) needed
     __syncthreads();
 
-    const vd_frame_t fr = frames[f];
     uint8_t* img = const_cast<uint8_t*>(fr.ptr);
     uint16_t* scr16 = ws.scratch + static_cast<size_t>(f) * ws.scratch_elems + m.scratch_off;
 
@@ -588,21 +662,23 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
       const uint8_t* fr_end = fr.ptr + static_cast<size_t>(fr.h - 1) * fr.pitch + static_cast<size_t>(fr.w) * 3;
       const int row_len = (px_hi - px_lo) * 3;
       const int chunks = (row_len + 15 + 15) >> 4;                           // 16-byte chunks per row incl. both ragged ends
-      for (int base = 0; base < vrows * chunks; base += 4 * kThreads) {
-        uint4 v[4];
+      // one warp per row (rows warp, warp + 8, ...), lanes over the row's chunks: the per-row quantities (source row,
+      // alignment phase) are computed once per row and nothing divides by a run-time value
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int ch = lane; ch < chunks; ch += 32) {          // one trip for ksize <= 33 (chunks <= 32)
+        uint4 v[GA_H / 8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = base + u * kThreads + tid;
+        for (int u = 0; u < GA_H / 8; ++u) {
+          const int ly = warp + 8 * u;
           v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (i < vrows * chunks) {
-            const int ly = i / chunks, ch = i - ly * chunks;
+          if (ly < vrows) {
             int ys = v0 + ly - r4;
             if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
             const uint8_t* p0 = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + (m.x1 + px_lo) * 3;
-            const uint8_t* pc = p0 - (reinterpret_cast<uintptr_t>(p0) & 15) + 16 * ch;      // aligned chunk
+            const uint8_t* pc = p0 - (reinterpret_cast<uintptr_t>(p0) & 15) + 16 * ch;   // aligned chunk of the row segment
             if (pc >= fr.ptr && pc + 16 <= fr_end) {
               v[u] = __ldcg(reinterpret_cast<const uint4*>(pc));
-            } else {                                                                        // chunk straddles the frame buffer's end
+            } else {                                                                  // chunk straddles the frame buffer's end
               uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u]);
               for (int k2 = 0; k2 < 16; ++k2)
                 if (pc + k2 >= fr.ptr && pc + k2 < fr_end) vb[k2] = __ldcg(pc + k2);
@@ -610,52 +686,50 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = base + u * kThreads + tid;
-          if (i < vrows * chunks) {
-            const int ly = i / chunks, ch = i - ly * chunks;
-            *reinterpret_cast<uint4*>(s_raw + ly * raw_pitch + 16 * ch) = v[u];
-          }
+        for (int u = 0; u < GA_H / 8; ++u) {
+          const int ly = warp + 8 * u;
+          if (ly < vrows) *reinterpret_cast<uint4*>(s_raw + ly * raw_pitch + 16 * ch) = v[u];
         }
       }
       __syncthreads();
       // Stage 2: de-interleave into byte planes.  Interior groups: 12 contiguous bytes = four shared-memory words, a funnel
       // shift and six PRMT; groups that touch the box border: REFLECT_101 per pixel (reflected pixels stay inside [px_lo, px_hi)).
-      const int total = vrows * ngroups;
-      for (int i = tid; i < total; i += kThreads) {
-        const int ly = i / ngroups, g = i - ly * ngroups;
-        const int px = x0 - r + 4 * g;                       // box-local pixel of the group's first byte
+      for (int ly = warp; ly < vrows; ly += 8) {
         int ys = v0 + ly - r4;
         if (ys < 0 || ys >= bh) ys = reflect101(ys, bh);
         const uint8_t* p0 = img + static_cast<size_t>(m.y1 + ys) * fr.pitch + (m.x1 + px_lo) * 3;
         const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(p0) & 15);          // s_raw[ly][phase] = pixel px_lo
         const uint8_t* rrow = s_raw + ly * raw_pitch + phase;
-        uint32_t q0, q1, q2;
-        if (px >= px_lo && px + 3 < px_hi) {
-          const int off = (px - px_lo) * 3 + phase;
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_raw + ly * raw_pitch + (off & ~3));
-          const int sh8 = (off & 3) * 8;
-          const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-          const uint32_t a = __funnelshift_r(w0, w1, sh8), b = __funnelshift_r(w1, w2, sh8), c = __funnelshift_r(w2, w3, sh8);
-          q0 = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);     // bytes 0, 3, 6, 9 of the 12-byte group
-          q1 = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);     // bytes 1, 4, 7, 10
-          q2 = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);     // bytes 2, 5, 8, 11
-        } else {
-          q0 = q1 = q2 = 0u;
+        uint32_t* prow0 = planes + ly * spanw;
+        for (int g = lane; g < ngroups; g += 32) {
+          const int px = x0 - r + 4 * g;                     // box-local pixel of the group's first byte
+          uint32_t q0, q1, q2;
+          if (px >= px_lo && px + 3 < px_hi) {
+            const int off = (px - px_lo) * 3 + phase;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_raw + ly * raw_pitch + (off & ~3));
+            const int sh8 = (off & 3) * 8;
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+            const uint32_t a = __funnelshift_r(w0, w1, sh8), b = __funnelshift_r(w1, w2, sh8), c = __funnelshift_r(w2, w3, sh8);
+            q0 = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);     // bytes 0, 3, 6, 9 of the 12-byte group
+            q1 = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);     // bytes 1, 4, 7, 10
+            q2 = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);     // bytes 2, 5, 8, 11
+          } else {
+            q0 = q1 = q2 = 0u;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int xs = px + q;
-            if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
-            xs = min(max(xs, px_lo), px_hi - 1);             // (columns beyond cols + 2r feed no valid output)
-            const uint8_t* pp = rrow + (xs - px_lo) * 3;
-            q0 |= static_cast<uint32_t>(pp[0]) << (8 * q);
-            q1 |= static_cast<uint32_t>(pp[1]) << (8 * q);
-            q2 |= static_cast<uint32_t>(pp[2]) << (8 * q);
+            for (int q = 0; q < 4; ++q) {
+              int xs = px + q;
+              if (xs < 0 || xs >= bw) xs = reflect101(xs, bw);
+              xs = min(max(xs, px_lo), px_hi - 1);           // (columns beyond cols + 2r feed no valid output)
+              const uint8_t* pp = rrow + (xs - px_lo) * 3;
+              q0 |= static_cast<uint32_t>(pp[0]) << (8 * q);
+              q1 |= static_cast<uint32_t>(pp[1]) << (8 * q);
+              q2 |= static_cast<uint32_t>(pp[2]) << (8 * q);
+            }
           }
+          prow0[g] = q0;
+          prow0[GA_H * spanw + g] = q1;
+          prow0[2 * GA_H * spanw + g] = q2;
         }
-        planes[(0 * GA_H + ly) * spanw + g] = q0;
-        planes[(1 * GA_H + ly) * spanw + g] = q1;
-        planes[(2 * GA_H + ly) * spanw + g] = q2;
       }
       __syncthreads();
       // task = (channel, group of 4 virtual rows, word of 4 pixels): 16 sums h[rr][a] = sum_t q[t] * pixel(x0 + 4mm + a - r + t)
@@ -829,10 +903,6 @@ composite_run_kernel(const vd_frame_t* __restrict__ frames, int B, int maxb, int
         }
       }
     }
-    // every thread's stores -> bar.sync -> st.release.gpu by one thread (release is cumulative over what the
-    // barrier ordered before it): no fence needed
-    __syncthreads();
-    if (tid == 0) st_release(done + local, 1);
   }
 }
 
@@ -923,9 +993,6 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
   size_t flag_bytes = 0;
   const Ws ws = carve(workspace, B, maxb, workspace_bytes, &flag_bytes);
   VD_CHECK_CUDA(cudaMemsetAsync(ws.done, 0, flag_bytes, st));
-  composite_plan_kernel<<<B, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
-                                            maxb, mode, mosaic_level, ksize, taps.kw > 0 ? 1 : 0, status, ws);
-  VD_LAUNCH_CHECK();
   const int r = ksize >> 1;
   size_t smem = 0;
   if (mode == VD_MODE_GAUSS) {
@@ -951,6 +1018,13 @@ extern "C" int vd_composite_rois(const vd_frame_t* frames, int B, const float* d
     const int cap = VD_COMP_MINB > 4 ? VD_COMP_MINB : 4;
     per_sm = fit < 1 ? 1 : (fit > cap ? cap : fit);
   }
+  // B tiles trail their box's A tiles by about one grid's worth of tickets (tickets interleave the B frames)
+  static const int lag_env = [] { const char* e = getenv("VD_COMP_LAG"); return e ? atoi(e) : -1; }();
+  const unsigned int lag_items = lag_env >= 0 ? static_cast<unsigned int>(lag_env)
+                                              : static_cast<unsigned int>((sms * per_sm + B - 1) / B);
+  composite_plan_kernel<<<B, 1024, 0, st>>>(frames, B, det_rows, det_count, max_det, ext_boxes, ext_count, max_ext,
+                                            maxb, mode, mosaic_level, ksize, taps.kw > 0 ? 1 : 0, lag_items, status, ws);
+  VD_LAUNCH_CHECK();
   composite_run_kernel<<<sms * per_sm, kThreads, smem, st>>>(frames, B, maxb, mode, ksize, taps, status, ws);
   VD_LAUNCH_CHECK();
   return VD_OK;
