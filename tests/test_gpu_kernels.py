@@ -389,6 +389,34 @@ def test_composite_large_overlapping_boxes(ops, mode, ksize):
         assert np.array_equal(got, want[i]), f"frame {i}: {(got != want[i]).sum()} bytes differ"
 
 
+@pytest.mark.parametrize("mode,ksize", [("mosaic", 0), ("gauss", 31)])
+def test_composite_planned_ticket_order(ops, mode, ksize):
+    """the plan kernel's item order: B tiles of a box are held back behind the A tiles of later boxes unless one of those
+    intersects it.  Frame 0: disjoint big boxes (every B segment is deferred) with a chain of mutually overlapping boxes
+    threaded between them (no deferral allowed along the chain); frame 1: 1100 boxes (more than the planner analyses:
+    natural order); frame 2: one box; frame 3: none."""
+    H, W = 720, 1280
+    frames = [synth.synthetic_frame(H, W, 900 + i) for i in range(4)]
+    grid = [(40 + 300 * c, 30 + 230 * r_, 40 + 300 * c + 260, 30 + 230 * r_ + 200) for r_ in range(3) for c in range(4)]
+    chain = [(20 + 90 * j, 100 + 45 * j, 20 + 90 * j + 180, 100 + 45 * j + 160) for j in range(12)]
+    b0 = []
+    for j in range(12):
+        b0 += [grid[j], chain[j]]
+    rng = np.random.default_rng(5)
+    b1 = []
+    for _ in range(1100):
+        x, y = int(rng.integers(0, W - 40)), int(rng.integers(0, H - 40))
+        b1.append((x, y, x + int(rng.integers(2, 40)), y + int(rng.integers(2, 40))))
+    b1[500] = (100, 100, 700, 600)
+    boxes = [b0, b1, [(300, 200, 900, 650)], []]
+    want = [co.composite(f, b, mode, 8, ksize) for f, b in zip(frames, boxes)]
+    dfr = _dev_frames([f.copy() for f in frames])
+    ops.composite(dfr, boxes, mode, mosaic_level=8, ksize=max(ksize, 1))
+    for i in range(4):
+        got = dfr[i].cpu().numpy()
+        assert np.array_equal(got, want[i]), f"frame {i}: {(got != want[i]).sum()} bytes differ"
+
+
 def test_gaussian_taps_match_oracle():
     from vdesens_b200 import _lib
     for k, s in [(3, 0), (5, 0), (7, 0), (9, 0), (15, 2.5), (31, 0), (51, 0), (99, 0), (31, 30.0), (255, 0)]:

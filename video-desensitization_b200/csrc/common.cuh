@@ -310,4 +310,41 @@ __device__ __forceinline__ uint32_t act2_max(uint32_t a, uint32_t b) {
 }
 #define VD_ACT2_NEG_INF 0xFF80FF80u
 #endif
+// c + a * b with a, b one half each of two packed activation-type words and c fp32: ONE instruction (FHFMA with .H0 / .H1
+// operand selectors), no unpacking.  The product of two bf16 (fp16) values is exact in fp32 and the sum is rounded once,
+// i.e. the same bits as fmaf(float(a), float(b), c).  AH / BH = 0: low half, 1: high half.
+template <int AH, int BH>
+__device__ __forceinline__ float act_fma(uint32_t a, uint32_t b, float c) {
+  float d;
+#if VD_ACT_IS_FP16
+#define VD_FHFMA_ "fma.rn.f32.f16"
+#else
+#define VD_FHFMA_ "fma.rn.f32.bf16"
+#endif
+  if constexpr (AH == 0 && BH == 0)
+    asm("{ .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n " VD_FHFMA_ " %0, al, bl, %3;\n}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  else if constexpr (AH == 0 && BH == 1)
+    asm("{ .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n " VD_FHFMA_ " %0, al, bh, %3;\n}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  else if constexpr (AH == 1 && BH == 0)
+    asm("{ .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n " VD_FHFMA_ " %0, ah, bl, %3;\n}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  else
+    asm("{ .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n " VD_FHFMA_ " %0, ah, bh, %3;\n}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+#undef VD_FHFMA_
+  return d;
+}
+// acc[0..7] += x[0..7] * w[0..7] (eight activation-type values per uint4, element-wise)
+__device__ __forceinline__ void act_fma8(float (&acc)[8], const uint4& x, const uint4& w) {
+  acc[0] = act_fma<0, 0>(x.x, w.x, acc[0]); acc[1] = act_fma<1, 1>(x.x, w.x, acc[1]);
+  acc[2] = act_fma<0, 0>(x.y, w.y, acc[2]); acc[3] = act_fma<1, 1>(x.y, w.y, acc[3]);
+  acc[4] = act_fma<0, 0>(x.z, w.z, acc[4]); acc[5] = act_fma<1, 1>(x.z, w.z, acc[5]);
+  acc[6] = act_fma<0, 0>(x.w, w.w, acc[6]); acc[7] = act_fma<1, 1>(x.w, w.w, acc[7]);
+}
+// acc[0..7] += xs * w[0..7] with xs = half XH of the word x (a broadcast scalar)
+template <int XH>
+__device__ __forceinline__ void act_fma8s(float (&acc)[8], uint32_t x, const uint4& w) {
+  acc[0] = act_fma<XH, 0>(x, w.x, acc[0]); acc[1] = act_fma<XH, 1>(x, w.x, acc[1]);
+  acc[2] = act_fma<XH, 0>(x, w.y, acc[2]); acc[3] = act_fma<XH, 1>(x, w.y, acc[3]);
+  acc[4] = act_fma<XH, 0>(x, w.z, acc[4]); acc[5] = act_fma<XH, 1>(x, w.z, acc[5]);
+  acc[6] = act_fma<XH, 0>(x, w.w, acc[6]); acc[7] = act_fma<XH, 1>(x, w.w, acc[7]);
+}
 #endif  // __CUDACC__
