@@ -24,129 +24,6 @@ __device__ __forceinline__ uint4 finish8(float (&a)[8], const float* __restrict_
   return o;
 }
 
-// same with bias / slope in shared memory (plain loads)
-__device__ __forceinline__ uint4 finish8s(float (&a)[8], const float* bias, const float* slope) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float v = a[i] + bias[i];
-    a[i] = v > 0.f ? v : v * slope[i];
-  }
-  uint4 o;
-  o.x = pack_bf16x2(a[0], a[1]);
-  o.y = pack_bf16x2(a[2], a[3]);
-  o.z = pack_bf16x2(a[4], a[5]);
-  o.w = pack_bf16x2(a[6], a[7]);
-  return o;
-}
-
-// conv_bn(3, 8, stride 2), pad 1, on the ingest layout x0 = [B][H][Wp][4] (pixel x at column x + 3, zero margins):
-// one thread = TWO adjacent output pixels = 3 rows x 5 input pixels (40 contiguous bytes per row), 2 x 16 bytes out;
-// the 216 weights sit in shared memory as stored (eight output channels per uint4) and every weight load (same address
-// for the whole warp) feeds both pixels.  All multiply-adds are FHFMA (activation-type operands, fp32 accumulate): no
-// conversion instructions.
-__global__ void __launch_bounds__(256)
-mnet_stem_kernel(const uint2* __restrict__ x0, const uint16_t* __restrict__ w, const float* __restrict__ bias,
-                 const float* __restrict__ slope, uint4* __restrict__ y, int B, int H, int W, int Wp, int Ho, int Wo) {
-  __shared__ uint4 sw[36];                            // [(r, s, c4)][8 cout] activation-type, as stored
-  for (int i = threadIdx.x; i < 36; i += blockDim.x) sw[i] = reinterpret_cast<const uint4*>(w)[i];
-  __syncthreads();
-  const int Wo2 = (Wo + 1) >> 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo2;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wp = static_cast<int>(idx % Wo2);
-    const int ho = static_cast<int>((idx / Wo2) % Ho);
-    const int b = static_cast<int>(idx / (static_cast<long long>(Wo2) * Ho));
-    const int wo = 2 * wp;
-    float a0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yi = 2 * ho - 1 + r;
-      if (yi < 0 || yi >= H) continue;
-      // input columns 2wo-1 .. 2wo+3 are padded columns 2wo+2 .. 2wo+6 (inside the row: Wp >= 2*Wo + 6); 2wo+2 is even,
-      // i.e. 16-byte aligned
-      const uint2* row = x0 + (static_cast<size_t>(b) * H + yi) * Wp + (2 * wo + 2);
-      const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(row));
-      const uint4 p23 = __ldg(reinterpret_cast<const uint4*>(row) + 1);
-      const uint2 p4 = __ldg(row + 4);
-      const uint32_t px[5][2] = {{p01.x, p01.y}, {p01.z, p01.w}, {p23.x, p23.y}, {p23.z, p23.w}, {p4.x, p4.y}};
-#pragma unroll
-      for (int sx = 0; sx < 3; ++sx) {
-        const uint4 w0 = sw[(r * 3 + sx) * 4], w1 = sw[(r * 3 + sx) * 4 + 1], w2 = sw[(r * 3 + sx) * 4 + 2];
-        act_fma8s<0>(a0, px[sx][0], w0); act_fma8s<1>(a0, px[sx][0], w1); act_fma8s<0>(a0, px[sx][1], w2);
-        act_fma8s<0>(a1, px[sx + 2][0], w0); act_fma8s<1>(a1, px[sx + 2][0], w1); act_fma8s<0>(a1, px[sx + 2][1], w2);
-      }
-    }
-    uint4* out = y + (static_cast<size_t>(b) * Ho + ho) * Wo + wo;
-    out[0] = finish8(a0, bias, slope);
-    if (wo + 1 < Wo) out[1] = finish8(a1, bias, slope);
-  }
-}
-
-// The depthwise run of one thread (see mnet_dw3x3_kernel): acc[o][0..7] for the NY outputs (ho0 + o, wo), channels 8g..8g+7.
-template <int STRIDE, int NY>
-__device__ __forceinline__ void dw_run(const uint4* __restrict__ x, int xoff, int rs, int C8, int H, bool has_l, bool has_r,
-                                       int yi0, const uint4 (&wv)[9], float (&acc)[NY][8]) {
-#pragma unroll
-  for (int o = 0; o < NY; ++o)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
-  constexpr int NIN = (NY - 1) * STRIDE + 3;               // input rows the run touches
-#pragma unroll
-  for (int ir = 0; ir < NIN; ++ir) {
-    const int yi = yi0 + ir;
-    if (yi < 0 || yi >= H) continue;
-    const uint4* row = x + (xoff + yi * rs);
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 vl = has_l ? __ldg(row - C8) : z, vc = __ldg(row), vr = has_r ? __ldg(row + C8) : z;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      // input row ir is tap row r of output o when ir = o * STRIDE + r
-      if ((ir - r) % STRIDE != 0) continue;
-      const int o = (ir - r) / STRIDE;
-      if (ir - r < 0 || o >= NY) continue;
-      if (has_l) act_fma8(acc[o], vl, wv[r * 3 + 0]);      // (a zero tap adds +0: skipping it keeps the bits)
-      act_fma8(acc[o], vc, wv[r * 3 + 1]);
-      if (has_r) act_fma8(acc[o], vr, wv[r * 3 + 2]);
-    }
-  }
-}
-
-// depthwise 3x3, pad 1, stride 1 or 2.  One thread = 8 channels x a vertical run of NY output pixels of one column:
-// the nine weight vectors stay packed in registers for the whole run, and at stride 1 every input row that is loaded
-// (three 16-byte loads: left, centre, right) feeds up to three output rows — (NY + 2) * 3 loads per NY outputs instead
-// of 9 * NY, plus 9 weight loads per run instead of per output.  Adjacent lanes hold adjacent channel groups, then
-// adjacent columns: every load and store of a warp is one contiguous 512-byte run.  All multiply-adds are FHFMA
-// (act_fma8: activation-type operands, fp32 accumulate, no conversions); per output the taps accumulate in (r, s) order.
-// grid = (ceil(Wo * C8 / 256), ceil(Ho / NY), B).
-template <int STRIDE, int NY>
-__global__ void __launch_bounds__(256)
-mnet_dw3x3_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ bias,
-                  const float* __restrict__ slope, uint4* __restrict__ y, int H, int W, int C8, int c8_shift, int Ho, int Wo) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= Wo * C8) return;
-  int g, wo;
-  if (c8_shift >= 0) { g = i & (C8 - 1); wo = i >> c8_shift; } else { wo = i / C8; g = i - wo * C8; }
-  const int ho0 = blockIdx.y * NY, b = blockIdx.z;
-  uint4 wv[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) wv[t] = __ldg(w + t * C8 + g);
-  float acc[NY][8];
-  const int xc = wo * STRIDE;                              // centre column; left = xc - 1, right = xc + 1
-  const int rs = W * C8;                                   // uint4 per input row (32-bit offsets: host checks the extent)
-  dw_run<STRIDE, NY>(x, b * H * rs + xc * C8 + g, rs, C8, H, xc >= 1, xc + 1 < W, ho0 * STRIDE - 1, wv, acc);
-  float bs[8], sl[8];
-  {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g + 1);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(slope) + 2 * g), s1 = __ldg(reinterpret_cast<const float4*>(slope) + 2 * g + 1);
-    bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
-    sl[0] = s0.x; sl[1] = s0.y; sl[2] = s0.z; sl[3] = s0.w; sl[4] = s1.x; sl[5] = s1.y; sl[6] = s1.z; sl[7] = s1.w;
-  }
-  const int yoff = (b * Ho * Wo + wo) * C8 + g, yrs = Wo * C8;
-#pragma unroll
-  for (int o = 0; o < NY; ++o)
-    if (ho0 + o < Ho) y[yoff + (ho0 + o) * yrs] = finish8s(acc[o], bs, sl);
-}
 
 // ---- pointwise 1x1 with Cin in {8, 16, 32} on the tensor cores (warp-level mma.sync; K = 8..32, N = 16..64 is far too
 // small a GEMM for the tcgen05 kernel's 128 x N tiles, and on the CUDA cores it costs Cin FMAs per output value: the
@@ -172,44 +49,215 @@ __device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[4], ui
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
 }
 
+// conv_bn(3, 8, stride 2), pad 1, on the ingest layout x0 = [B][H][Wp][4] (pixel x at column x + 3, zero margins), as a
+// GEMM on the tensor cores: M = 16 adjacent output pixels of one row per warp step, N = 8, K = 3 filter rows x 16, where
+// the 16 values of filter row r are the FOUR padded pixels 2wo+2 .. 2wo+5 of input row 2ho-1+r exactly as they lie in
+// memory (32 contiguous bytes; the fourth pixel and every fourth channel meet zero weights).  Output pixel wo+1 starts
+// 16 bytes further on, so each register of the A fragment is one coalesced 128-byte load straight from global memory
+// (12 per 16 pixels, L1 serves the overlap) and each of the two output registers one coalesced 128-byte store.
+// On the CUDA cores this layer costs 27 FMAs per output value — 105 us of FMA issue at 1080p against 60 us of HBM time.
+constexpr int STEM_RY = 4;
+__global__ void __launch_bounds__(256)
+mnet_stem_kernel(const uint8_t* __restrict__ x0, const uint16_t* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ slope, uint32_t* __restrict__ y, int B, int H, int W, int Wp, int Ho, int Wo) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  // B fragments: k = s * 4 + c (s < 3 taps, 4 channels), rows 12..15 (the fourth pixel) are zero; w = [(r, s, c4)][8]
+  uint32_t bf[3][2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int k = tig * 2;                                 // k and k + 1: same tap, channels (2 tig) % 4, + 1
+    bf[r][0] = static_cast<uint32_t>(w[(r * 12 + k) * 8 + gid]) | (static_cast<uint32_t>(w[(r * 12 + k + 1) * 8 + gid]) << 16);
+    bf[r][1] = tig < 2 ? static_cast<uint32_t>(w[(r * 12 + k + 8) * 8 + gid]) | (static_cast<uint32_t>(w[(r * 12 + k + 9) * 8 + gid]) << 16) : 0u;
+  }
+  const float2 bs = *reinterpret_cast<const float2*>(bias + tig * 2), sl = *reinterpret_cast<const float2*>(slope + tig * 2);
+  // one warp = 16 output columns x STEM_RY output rows: the 2 RY + 1 input rows it needs are all requested before the first
+  // mma (an odd input row is filter row 2 of one output row and filter row 0 of the next: loaded once)
+  const int wo0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 16, ho0 = blockIdx.y * STEM_RY, b = blockIdx.z;
+  if (wo0 >= Wo) return;
+  // rows of the fragment: output pixels wo0 + gid and wo0 + gid + 8 (clamped for the address, masked at the store)
+  const int c0 = min(wo0 + gid, Wo - 1), c1 = min(wo0 + gid + 8, Wo - 1);
+  const uint8_t* base = x0 + static_cast<size_t>(b) * H * Wp * 8 + tig * 4;
+  const int o0 = (2 * c0 + 2) * 8, o1 = (2 * c1 + 2) * 8;
+  uint32_t a[2 * STEM_RY + 1][4];
+#pragma unroll
+  for (int i = 0; i < 2 * STEM_RY + 1; ++i) {
+    const int yi = 2 * ho0 - 1 + i;
+    a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0u;            // rows outside the image: zero operand
+    if (yi >= 0 && yi < H) {
+      const uint8_t* row = base + static_cast<size_t>(yi) * Wp * 8;
+      a[i][0] = __ldg(reinterpret_cast<const uint32_t*>(row + o0));
+      a[i][1] = __ldg(reinterpret_cast<const uint32_t*>(row + o1));
+      a[i][2] = __ldg(reinterpret_cast<const uint32_t*>(row + o0 + 16));
+      a[i][3] = __ldg(reinterpret_cast<const uint32_t*>(row + o1 + 16));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < STEM_RY; ++j) {
+    const int ho = ho0 + j;
+    if (ho >= Ho) break;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) mma_k16(acc, a[2 * j + r], bf[r][0], bf[r][1]);
+    float v0 = acc[0] + bs.x, v1 = acc[1] + bs.y, v2 = acc[2] + bs.x, v3 = acc[3] + bs.y;
+    v0 = v0 > 0.f ? v0 : v0 * sl.x; v1 = v1 > 0.f ? v1 : v1 * sl.y;
+    v2 = v2 > 0.f ? v2 : v2 * sl.x; v3 = v3 > 0.f ? v3 : v3 * sl.y;
+    uint32_t* out = y + ((static_cast<size_t>(b) * Ho + ho) * Wo + wo0) * 4 + tig;      // 4 words per output pixel
+    if (wo0 + gid < Wo) out[gid * 4] = pack_bf16x2(v0, v1);
+    if (wo0 + gid + 8 < Wo) out[(gid + 8) * 4] = pack_bf16x2(v2, v3);
+  }
+}
+
+// ---- depthwise 3x3 building block ----
+// A thread owns CH (8 or 4) channels of one output column and walks a vertical run of NY outputs.  ALL the input rows the
+// run touches ((NY - 1) * STRIDE + 3 rows x left / centre / right) are requested before the first multiply-add — the
+// kernels are bound by the latency of these loads, not by their count — and at stride 1 every row feeds up to three
+// outputs.  Multiply-adds are FHFMA (activation-type operands, fp32 accumulate, no conversions); per output the taps
+// accumulate in (r, s) order; taps outside the image are skipped.
+template <int CH> struct ActVec;
+template <> struct ActVec<8> { using T = uint4; };
+template <> struct ActVec<4> { using T = uint2; };
+__device__ __forceinline__ void act_fmav(float (&acc)[8], const uint4& x, const uint4& w) { act_fma8(acc, x, w); }
+__device__ __forceinline__ void act_fmav(float (&acc)[4], const uint2& x, const uint2& w) {
+  acc[0] = act_fma<0, 0>(x.x, w.x, acc[0]); acc[1] = act_fma<1, 1>(x.x, w.x, acc[1]);
+  acc[2] = act_fma<0, 0>(x.y, w.y, acc[2]); acc[3] = act_fma<1, 1>(x.y, w.y, acc[3]);
+}
+__device__ __forceinline__ uint4 vzero(const uint4*) { return make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ uint2 vzero(const uint2*) { return make_uint2(0u, 0u); }
+// x: tensor as vectors of CH channels, CV vectors per pixel, rs vectors per row; xoff: vector index of (batch, row 0, centre
+// column, this thread's channels); yi0: first input row of the run; wtap(t): weight vector of tap t = r * 3 + s.
+template <int STRIDE, int NY, int CH>
+__device__ __forceinline__ void dw_load(const typename ActVec<CH>::T* __restrict__ x, int xoff, int rs, int CV, int H,
+                                        bool has_l, bool has_r, int yi0,
+                                        typename ActVec<CH>::T (&in)[(NY - 1) * STRIDE + 3][3]) {
+  using V = typename ActVec<CH>::T;
+  const V* row = x + (xoff + yi0 * rs);
+#pragma unroll
+  for (int ir = 0; ir < (NY - 1) * STRIDE + 3; ++ir) {
+    const bool ok = static_cast<unsigned int>(yi0 + ir) < static_cast<unsigned int>(H);
+    const V z = vzero(static_cast<const V*>(nullptr));
+    in[ir][0] = ok && has_l ? __ldg(row - CV) : z;         // taps outside the image: zero operands (their FMAs add +0)
+    in[ir][1] = ok ? __ldg(row) : z;
+    in[ir][2] = ok && has_r ? __ldg(row + CV) : z;
+    row += rs;
+  }
+}
+// acc[o][*] = bias + sum over the 9 taps, (r, s) order.  No branches: rows / columns outside the image hold zeros.
+template <int STRIDE, int NY, int CH, typename WF>
+__device__ __forceinline__ void dw_compute(const typename ActVec<CH>::T (&in)[(NY - 1) * STRIDE + 3][3], const float (&bias)[CH],
+                                           WF wtap, float (&acc)[NY][CH]) {
+#pragma unroll
+  for (int o = 0; o < NY; ++o)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[o][k] = bias[k];
+#pragma unroll
+  for (int ir = 0; ir < (NY - 1) * STRIDE + 3; ++ir) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      // input row ir is tap row r of output o when ir = o * STRIDE + r
+      if ((ir - r) % STRIDE != 0) continue;
+      const int o = (ir - r) / STRIDE;
+      if (ir - r < 0 || o >= NY) continue;
+      act_fmav(acc[o], in[ir][0], wtap(r * 3 + 0));
+      act_fmav(acc[o], in[ir][1], wtap(r * 3 + 1));
+      act_fmav(acc[o], in[ir][2], wtap(r * 3 + 2));
+    }
+  }
+}
+// slope + rounding of CH biased sums -> one packed vector
+__device__ __forceinline__ uint4 leaky_pack(float (&a)[8], const float (&slope)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = a[i] > 0.f ? a[i] : a[i] * slope[i];
+  return make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+}
+__device__ __forceinline__ uint2 leaky_pack(float (&a)[4], const float (&slope)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = a[i] > 0.f ? a[i] : a[i] * slope[i];
+  return make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+}
+template <int CH>
+__device__ __forceinline__ void load_bias_slope(const float* bias, const float* slope, int g, float (&bs)[CH], float (&sl)[CH]) {
+#pragma unroll
+  for (int q = 0; q < CH / 4; ++q) {
+    const float4 b4 = *(reinterpret_cast<const float4*>(bias) + (CH / 4) * g + q);
+    const float4 s4 = *(reinterpret_cast<const float4*>(slope) + (CH / 4) * g + q);
+    bs[4 * q] = b4.x; bs[4 * q + 1] = b4.y; bs[4 * q + 2] = b4.z; bs[4 * q + 3] = b4.w;
+    sl[4 * q] = s4.x; sl[4 * q + 1] = s4.y; sl[4 * q + 2] = s4.z; sl[4 * q + 3] = s4.w;
+  }
+}
+
+// depthwise 3x3 (+ folded BN + slope), pad 1, stride 1 or 2, for C >= 64: dw_run with the nine weight vectors in
+// registers.  Adjacent lanes hold adjacent channel vectors, then adjacent columns: every load and store of a warp is one
+// contiguous run.  grid = (ceil(Wo * CV / 256), ceil(Ho / NY), B).
+template <int STRIDE, int NY, int CH>
+__global__ void __launch_bounds__(256)
+mnet_dw3x3_kernel(const typename ActVec<CH>::T* __restrict__ x, const typename ActVec<CH>::T* __restrict__ w,
+                  const float* __restrict__ bias, const float* __restrict__ slope, typename ActVec<CH>::T* __restrict__ y,
+                  int H, int W, int CV, int cv_shift, int Ho, int Wo) {
+  using V = typename ActVec<CH>::T;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= Wo * CV) return;
+  int g, wo;
+  if (cv_shift >= 0) { g = i & (CV - 1); wo = i >> cv_shift; } else { wo = i / CV; g = i - wo * CV; }
+  const int ho0 = blockIdx.y * NY, b = blockIdx.z;
+  V wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = __ldg(w + t * CV + g);
+  float bs[CH], sl[CH];
+  load_bias_slope<CH>(bias, slope, g, bs, sl);
+  float acc[NY][CH];
+  const int xc = wo * STRIDE;                              // centre column; left = xc - 1, right = xc + 1
+  const int rs = W * CV;                                   // vectors per input row (32-bit offsets: host checks the extent)
+  V in[(NY - 1) * STRIDE + 3][3];
+  dw_load<STRIDE, NY, CH>(x, b * H * rs + xc * CV + g, rs, CV, H, xc >= 1, xc + 1 < W, ho0 * STRIDE - 1, in);
+  dw_compute<STRIDE, NY, CH>(in, bs, [&](int t) { return wv[t]; }, acc);
+  const int yoff = (b * Ho * Wo + wo) * CV + g, yrs = Wo * CV;
+#pragma unroll
+  for (int o = 0; o < NY; ++o)
+    if (ho0 + o < Ho) y[yoff + (ho0 + o) * yrs] = leaky_pack(acc[o], sl);
+}
+
 // Shared-memory layout of a pixel tile: one row of CIN (COUT) activation-type values per pixel; the row pitch keeps the
 // eight 16-byte rows of an ldmatrix 8x8 block (and the eight rows a warp's epilogue writes) on distinct banks.
 template <int C> struct PwPitch { static constexpr int value = C * 2 + (C == 8 ? 0 : 16); };
 
-// B fragments of the whole [CIN][COUT] weight matrix, per thread: (CIN / 16) k-steps x (COUT / 8) column blocks x 2 words
-// (CIN = 8: one m16n8k8 step, 1 word).
+// B fragments of the whole [CIN][COUT] weight matrix, pre-packed per lane in shared memory: word ((ks * NT + nt) * NW + h) * 32
+// + lane is the lane's register h of the (k-step ks, column block nt) fragment — (CIN / 16) k-steps x (COUT / 8) blocks x 2
+// words (CIN = 8: one m16n8k8 step, 1 word).  Read back with conflict-free 4-byte loads at every use: 16..32 registers
+// that a persistent CTA would otherwise carry through its depthwise phase.
 template <int CIN, int COUT>
-struct PwWeights {
+struct PwFrag {
   static constexpr int KS = CIN >= 16 ? CIN / 16 : 1, NT = COUT / 8, NW = CIN >= 16 ? 2 : 1;
-  uint32_t b[KS][NT][NW];
-  __device__ __forceinline__ void load(const uint16_t* w, int lane) {       // w: [CIN][COUT] (shared or global memory)
-    const int gid = lane >> 2, tig = lane & 3;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int h = 0; h < NW; ++h) {
-          const int k = ks * 16 + h * 8 + tig * 2, n = nt * 8 + gid;
-          b[ks][nt][h] = static_cast<uint32_t>(w[k * COUT + n]) | (static_cast<uint32_t>(w[(k + 1) * COUT + n]) << 16);
-        }
+  static constexpr int WORDS = KS * NT * NW * 32;
+  __device__ static void pack(uint32_t* tab, const uint16_t* w, int tid, int nthreads) {      // w: [CIN][COUT]
+    for (int e = tid; e < WORDS; e += nthreads) {
+      const int lane = e & 31, f = e >> 5;
+      const int h = f % NW, nt = (f / NW) % NT, ks = f / (NW * NT);
+      const int k = ks * 16 + h * 8 + (lane & 3) * 2, n = nt * 8 + (lane >> 2);
+      tab[e] = static_cast<uint32_t>(w[k * COUT + n]) | (static_cast<uint32_t>(w[(k + 1) * COUT + n]) << 16);
+    }
   }
 };
 
 // One warp: 16 pixels (rows of `in`, pitch PwPitch<CIN>) x COUT outputs = act(in * W + bias), written as packed rows into the
 // warp's staging area `st` (16 rows, pitch PwPitch<COUT>).  bs / sl: bias and slope in shared memory.
 template <int CIN, int COUT>
-__device__ __forceinline__ void pw_tile16(const uint8_t* in, const PwWeights<CIN, COUT>& wf, const float* bs, const float* sl,
+__device__ __forceinline__ void pw_tile16(const uint8_t* in, const uint32_t* bfrag, const float* bs, const float* sl,
                                           uint8_t* st, int lane) {
+  using F = PwFrag<CIN, COUT>;
   constexpr int PI = PwPitch<CIN>::value, PO = PwPitch<COUT>::value, NT = COUT / 8;
+  const int gid = lane >> 2, tig = lane & 3;
   float acc[NT][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  for (int nt = 0; nt < NT; ++nt) {                       // accumulators start at the bias of their two columns
+    const float2 b2 = *reinterpret_cast<const float2*>(bs + nt * 8 + tig * 2);
+    acc[nt][0] = acc[nt][2] = b2.x;
+    acc[nt][1] = acc[nt][3] = b2.y;
+  }
   if constexpr (CIN == 8) {
     uint32_t a[4];
     ldsm_x2(a, in + (lane & 15) * PI);                                  // rows 0-7 | rows 8-15, k 0-7
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) mma_k8(acc[nt], a, wf.b[0][nt][0]);
+    for (int nt = 0; nt < NT; ++nt) mma_k8(acc[nt], a, bfrag[nt * 32 + lane]);
   } else {
 #pragma unroll
     for (int ks = 0; ks < CIN / 16; ++ks) {
@@ -217,15 +265,16 @@ __device__ __forceinline__ void pw_tile16(const uint8_t* in, const PwWeights<CIN
       // lanes 0-7: rows 0-7 k 0-7 | 8-15: rows 8-15 k 0-7 | 16-23: rows 0-7 k 8-15 | 24-31: rows 8-15 k 8-15
       ldsm_x4(a, in + (lane & 15) * PI + ks * 32 + (lane >> 4) * 16);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) mma_k16(acc[nt], a, wf.b[ks][nt][0], wf.b[ks][nt][1]);
+      for (int nt = 0; nt < NT; ++nt)
+        mma_k16(acc[nt], a, bfrag[((ks * NT + nt) * 2) * 32 + lane], bfrag[((ks * NT + nt) * 2 + 1) * 32 + lane]);
     }
   }
-  const int gid = lane >> 2, tig = lane & 3;
+  (void)F::WORDS;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int col = nt * 8 + tig * 2;
-    const float2 b2 = *reinterpret_cast<const float2*>(bs + col), s2 = *reinterpret_cast<const float2*>(sl + col);
-    float v0 = acc[nt][0] + b2.x, v1 = acc[nt][1] + b2.y, v2 = acc[nt][2] + b2.x, v3 = acc[nt][3] + b2.y;
+    const float2 s2 = *reinterpret_cast<const float2*>(sl + col);
+    float v0 = acc[nt][0], v1 = acc[nt][1], v2 = acc[nt][2], v3 = acc[nt][3];
     v0 = v0 > 0.f ? v0 : v0 * s2.x; v1 = v1 > 0.f ? v1 : v1 * s2.y;
     v2 = v2 > 0.f ? v2 : v2 * s2.x; v3 = v3 > 0.f ? v3 : v3 * s2.y;
     *reinterpret_cast<uint32_t*>(st + gid * PO + col * 2) = pack_bf16x2(v0, v1);
@@ -235,79 +284,100 @@ __device__ __forceinline__ void pw_tile16(const uint8_t* in, const PwWeights<CIN
 
 // conv_dw block = depthwise 3x3 (+BN+slope) followed by pointwise 1x1 (+BN+slope) in ONE kernel for Cin <= 32: the
 // depthwise result of a TX x TY pixel tile goes to shared memory (rounded to the activation type exactly where the
-// two-kernel form stores it) and never to HBM.  Phase 1 = dw_run (one thread: 8 channels x NY vertically adjacent
-// outputs); phase 2 = pw_tile16 per 16 pixels of a tile row, staged and written back as 16-byte vectors.
-// TX * TY * (CIN / 8) = 256 * NY;  grid = (ceil(Wo / TX), ceil(Ho / TY), B).
-template <int CIN, int COUT, int STRIDE>
+// two-kernel form stores it) and never to HBM.  Persistent CTAs walk the tiles (weights, fragment table, biases are set
+// up once); per tile: phase 1 = dw_compute on input rows that were requested BEFORE the previous tile's phase 2 (the
+// kernel is bound by the latency of those loads: a first version that loaded, computed and stored tile by tile spent 39 %
+// of its warp samples waiting on them), phase 2 = pw_tile16 per 16 pixels of a tile row, staged and written back as
+// 16-byte vectors.  One thread of phase 1 = CH channels x NY vertically adjacent outputs; TX * TY * (CIN / CH) = 256 * NY.
+template <int CIN, int COUT, int STRIDE, int CH>
 struct DwpwCfg {
-  static constexpr int G = CIN / 8, NY = STRIDE == 1 ? 4 : 2;
-  static constexpr int NPX = 256 * NY / G;
+  static constexpr int GV = CIN / CH, NY = STRIDE == 1 ? 4 : 2;
+  static constexpr int NPX = 256 * NY / GV;
   static constexpr int TX = NPX >= 1024 ? 64 : (NPX >= 256 ? 32 : 16), TY = NPX / TX;
 };
 
-template <int CIN, int COUT, int STRIDE>
-__global__ void __launch_bounds__(256)
-mnet_dwpw_kernel(const uint4* __restrict__ x, const uint4* __restrict__ wdw, const float* __restrict__ bdw,
-                 const float* __restrict__ sdw, const uint16_t* __restrict__ wpw, const float* __restrict__ bpw,
-                 const float* __restrict__ spw, uint4* __restrict__ y, int H, int W, int Ho, int Wo) {
-  using Cfg = DwpwCfg<CIN, COUT, STRIDE>;
-  constexpr int G = Cfg::G, NY = Cfg::NY, TX = Cfg::TX, TY = Cfg::TY, NPX = Cfg::NPX;
+template <int CIN, int COUT, int STRIDE, int CH>
+__global__ void __launch_bounds__(256, 2)
+mnet_dwpw_kernel(const typename ActVec<CH>::T* __restrict__ x, const typename ActVec<CH>::T* __restrict__ wdw,
+                 const float* __restrict__ bdw, const float* __restrict__ sdw, const uint16_t* __restrict__ wpw,
+                 const float* __restrict__ bpw, const float* __restrict__ spw, uint4* __restrict__ y, int B, int H, int W,
+                 int Ho, int Wo) {
+  using Cfg = DwpwCfg<CIN, COUT, STRIDE, CH>;
+  using V = typename ActVec<CH>::T;
+  using F = PwFrag<CIN, COUT>;
+  constexpr int GV = Cfg::GV, NY = Cfg::NY, TX = Cfg::TX, TY = Cfg::TY, NPX = Cfg::NPX;
   constexpr int PI = PwPitch<CIN>::value, PO = PwPitch<COUT>::value;
-  static_assert(TX * G * (TY / NY) == 256 && TY % NY == 0 && TX % 16 == 0, "tile / thread mapping");
+  static_assert(TX * GV * (TY / NY) == 256 && TY % NY == 0 && TX % 16 == 0 && NPX % 16 == 0, "tile / thread mapping");
   __shared__ __align__(16) uint8_t sD[NPX * PI];        // depthwise result, one row per pixel
   __shared__ __align__(16) uint8_t sO[8 * 16 * PO];     // per-warp output staging
-  __shared__ __align__(16) uint16_t s_wpw[CIN * COUT];
-  __shared__ __align__(16) float s_b[2 * CIN + 2 * COUT];   // bdw | sdw | bpw | spw
+  __shared__ __align__(16) uint32_t s_bf[F::WORDS];     // pointwise B fragments, per lane
+  __shared__ __align__(16) float s_b[2 * COUT];         // bpw | spw
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < CIN * COUT / 8; i += 256) reinterpret_cast<uint4*>(s_wpw)[i] = reinterpret_cast<const uint4*>(wpw)[i];
-  for (int i = tid; i < CIN; i += 256) {
-    s_b[i] = bdw[i];
-    s_b[CIN + i] = sdw[i];
-  }
+  F::pack(s_bf, wpw, tid, 256);
   for (int i = tid; i < COUT; i += 256) {
-    s_b[2 * CIN + i] = bpw[i];
-    s_b[2 * CIN + COUT + i] = spw[i];
+    s_b[i] = bpw[i];
+    s_b[COUT + i] = spw[i];
   }
-  const int b = blockIdx.z;
-  const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
-  // ---- phase 1: depthwise into shared memory ----
-  {
-    const int cg = tid % (TX * G), run = tid / (TX * G);
-    const int g = cg % G, tx = cg / G;
-    const int ox = ox0 + tx, ty0 = run * NY;
-    uint4 wv[9];
+  const int ntx = (Wo + TX - 1) / TX, nty = (Ho + TY - 1) / TY;
+  const int total = B * nty * ntx;
+  // this thread's part of a tile's depthwise phase
+  const int cg = tid % (TX * GV), run = tid / (TX * GV);
+  const int g = cg % GV, tx = cg / GV, ty0 = run * NY;
+  const int rs = W * GV;
+  V wv[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wv[t] = __ldg(wdw + t * G + g);
-    float acc[NY][8];
-    const bool colok = ox < Wo;
-    if (colok && oy0 + ty0 < Ho) {
-      const int xc = ox * STRIDE, rs = W * G;
-      dw_run<STRIDE, NY>(x, b * H * rs + xc * G + g, rs, G, H, xc >= 1, xc + 1 < W, (oy0 + ty0) * STRIDE - 1, wv, acc);
-    }
-    __syncthreads();                                      // s_b is loaded
-#pragma unroll
-    for (int o = 0; o < NY; ++o) {
-      uint4 out = make_uint4(0u, 0u, 0u, 0u);
-      if (colok && oy0 + ty0 + o < Ho) out = finish8s(acc[o], s_b + g * 8, s_b + CIN + g * 8);
-      *reinterpret_cast<uint4*>(sD + ((ty0 + o) * TX + tx) * PI + g * 16) = out;
-    }
-  }
-  __syncthreads();
-  // ---- phase 2: pointwise on the tensor cores ----
-  PwWeights<CIN, COUT> wf;
-  wf.load(s_wpw, lane);
+  for (int tp = 0; tp < 9; ++tp) wv[tp] = __ldg(wdw + tp * GV + g);
+  float bsd[CH], sld[CH];
+  load_bias_slope<CH>(bdw, sdw, g, bsd, sld);
+  V in[(NY - 1) * STRIDE + 3][3];
+  // tiles t, t + gridDim.x, ... as (batch, tile row, tile column), advanced without divisions
+  int t = blockIdx.x;
+  int txi = t % ntx, tyi = (t / ntx) % nty, tb = t / (ntx * nty);
+  const int dxi = gridDim.x % ntx, dr = gridDim.x / ntx, dyi = dr % nty, db = dr / nty;
+  bool live = false;
+  auto load_tile = [&]() {                                 // request the input rows of tile (tb, tyi, txi)
+    const int ox = txi * TX + tx, xc = ox * STRIDE, oy = tyi * TY + ty0;
+    live = ox < Wo && oy < Ho;
+    if (live) dw_load<STRIDE, NY, CH>(x, tb * H * rs + xc * GV + g, rs, GV, H, xc >= 1, xc + 1 < W, oy * STRIDE - 1, in);
+  };
+  if (t < total) load_tile();
+  __syncthreads();                                       // the shared tables are complete
   uint8_t* st = sO + warp * 16 * PO;
-  for (int mt = warp; mt < NPX / 16; mt += 8) {
-    const int p0 = mt * 16, ty = p0 / TX, tx0 = p0 % TX;
-    const int oy = oy0 + ty;
-    if (oy >= Ho || ox0 + tx0 >= Wo) continue;            // (warp-uniform)
-    pw_tile16<CIN, COUT>(sD + p0 * PI, wf, s_b + 2 * CIN, s_b + 2 * CIN + COUT, st, lane);
-    __syncwarp();
-    uint4* yrow = y + (static_cast<size_t>(b) * Ho + oy) * Wo * (COUT / 8) + static_cast<size_t>(ox0 + tx0) * (COUT / 8);
-    const int npx = min(16, Wo - (ox0 + tx0));
-    for (int i = lane; i < npx * (COUT / 8); i += 32)
-      yrow[i] = *reinterpret_cast<const uint4*>(st + (i / (COUT / 8)) * PO + (i % (COUT / 8)) * 16);
-    __syncwarp();
+  while (t < total) {
+    const int cb = tb, coy0 = tyi * TY, cox0 = txi * TX;  // tile t's place
+    // ---- phase 1: depthwise of tile t (rows already requested) into shared memory ----
+    {
+      float acc[NY][CH];
+      if (live) dw_compute<STRIDE, NY, CH>(in, bsd, [&](int tap) { return wv[tap]; }, acc);
+#pragma unroll
+      for (int o = 0; o < NY; ++o) {
+        V out = vzero(static_cast<const V*>(nullptr));
+        if (live && coy0 + ty0 + o < Ho) out = leaky_pack(acc[o], sld);
+        *reinterpret_cast<V*>(sD + ((ty0 + o) * TX + tx) * PI + g * CH * 2) = out;
+      }
+    }
+    __syncthreads();
+    // ---- request the next tile's input rows; they arrive while phase 2 runs ----
+    const int tn = t + gridDim.x;
+    txi += dxi; tyi += dyi; tb += db;
+    if (txi >= ntx) { txi -= ntx; ++tyi; }
+    if (tyi >= nty) { tyi -= nty; ++tb; }
+    if (tn < total) load_tile();
+    // ---- phase 2: pointwise on the tensor cores ----
+    for (int mt = warp; mt < NPX / 16; mt += 8) {
+      const int p0 = mt * 16, ty = p0 / TX, tx0 = p0 % TX;
+      const int oy = coy0 + ty;
+      if (oy >= Ho || cox0 + tx0 >= Wo) continue;           // (warp-uniform)
+      pw_tile16<CIN, COUT>(sD + p0 * PI, s_bf, s_b, s_b + COUT, st, lane);
+      __syncwarp();
+      uint4* yrow = y + (static_cast<size_t>(cb) * Ho + oy) * Wo * (COUT / 8) + static_cast<size_t>(cox0 + tx0) * (COUT / 8);
+      const int npx = min(16, Wo - (cox0 + tx0));
+      for (int i = lane; i < npx * (COUT / 8); i += 32)
+        yrow[i] = *reinterpret_cast<const uint4*>(st + (i / (COUT / 8)) * PO + (i % (COUT / 8)) * 16);
+      __syncwarp();
+    }
+    __syncthreads();                                     // every warp is done with sD before the next tile overwrites it
+    t = tn;
   }
 }
 
@@ -320,10 +390,10 @@ mnet_pw_mma_kernel(const uint4* __restrict__ x, const uint16_t* __restrict__ w, 
   constexpr int G = CIN / 8, PI = PwPitch<CIN>::value, PO = PwPitch<COUT>::value, NPX = 256;
   __shared__ __align__(16) uint8_t sD[NPX * PI];
   __shared__ __align__(16) uint8_t sO[8 * 16 * PO];
-  __shared__ __align__(16) uint16_t s_w[CIN * COUT];
+  __shared__ __align__(16) uint32_t s_bf[PwFrag<CIN, COUT>::WORDS];
   __shared__ __align__(16) float s_b[2 * COUT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < CIN * COUT / 8; i += 256) reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(w)[i];
+  PwFrag<CIN, COUT>::pack(s_bf, w, tid, 256);
   for (int i = tid; i < COUT; i += 256) {
     s_b[i] = bias[i];
     s_b[COUT + i] = slope[i];
@@ -335,12 +405,10 @@ mnet_pw_mma_kernel(const uint4* __restrict__ x, const uint16_t* __restrict__ w, 
     *reinterpret_cast<uint4*>(sD + px * PI + g * 16) = px < n ? __ldg(x + p0 * G + i) : make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  PwWeights<CIN, COUT> wf;
-  wf.load(s_w, lane);
   uint8_t* st = sO + warp * 16 * PO;
   for (int mt = warp; mt < NPX / 16; mt += 8) {
     if (mt * 16 >= n) continue;
-    pw_tile16<CIN, COUT>(sD + mt * 16 * PI, wf, s_b, s_b + COUT, st, lane);
+    pw_tile16<CIN, COUT>(sD + mt * 16 * PI, s_bf, s_b, s_b + COUT, st, lane);
     __syncwarp();
     uint4* yrow = y + (p0 + mt * 16) * (COUT / 8);
     const int npx = min(16, n - mt * 16);
@@ -393,9 +461,10 @@ extern "C" int vd_mnet_stem(const void* x0, const void* w, const float* bias, co
   VD_REQUIRE(B > 0 && H > 0 && W > 0, "vd_mnet_stem: bad extent");
   VD_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "vd_mnet_stem: weights must be 16-byte aligned");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = static_cast<long long>(B) * Ho * ((Wo + 1) / 2);
-  mnet_stem_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint2*>(x0), static_cast<const uint16_t*>(w), bias, slope, static_cast<uint4*>(y), B, H, W,
+  VD_REQUIRE(B <= 65535 && (Ho + STEM_RY - 1) / STEM_RY <= 65535, "vd_mnet_stem: batch / height beyond the grid limits");
+  const dim3 grid(((Wo + 15) / 16 + 7) / 8, (Ho + STEM_RY - 1) / STEM_RY, B);
+  mnet_stem_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(x0), static_cast<const uint16_t*>(w), bias, slope, static_cast<uint32_t*>(y), B, H, W,
       vd_x0_pitch(W), Ho, Wo);
   VD_LAUNCH_CHECK();
   return VD_OK;
@@ -406,7 +475,7 @@ extern "C" int vd_mnet_dw3x3(const void* x, const void* w, const float* bias, co
   VD_REQUIRE(x && w && bias && slope && y, "vd_mnet_dw3x3: null argument");
   VD_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
              "vd_mnet_dw3x3: C=%d must be a multiple of 8, stride 1 or 2", C);
-  VD_REQUIRE(B <= 65535 && H <= 65535 && static_cast<long long>(B) * H * W * (C / 8) < (1ll << 31),
+  VD_REQUIRE(B <= 65535 && H <= 65535 && static_cast<long long>(B) * H * W * (C / 4) < (1ll << 31),
              "vd_mnet_dw3x3: batch / height / tensor size beyond the kernel's 32-bit indexing");
   VD_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
              "vd_mnet_dw3x3: tensors must be 16-byte aligned");
@@ -414,40 +483,62 @@ extern "C" int vd_mnet_dw3x3(const void* x, const void* w, const float* bias, co
              "vd_mnet_dw3x3: bias / slope must be 16-byte aligned");
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int C8 = C / 8;
-  int sh = -1;
-  if ((C8 & (C8 - 1)) == 0) { sh = 0; while ((1 << sh) < C8) ++sh; }
+  // 4 channels per thread (18 weight + 36 input registers at NY = 4) keeps three CTAs per SM with every load in flight
+  static const int ch_env = [] { const char* e = getenv("VD_MNET_DW_CH"); return e ? atoi(e) : 0; }();
   static const int ny_env = [] { const char* e = getenv("VD_MNET_DW_NY"); return e ? atoi(e) : 0; }();
-  const int ny = stride == 2 ? (ny_env == 1 ? 1 : 2) : (ny_env > 0 ? ny_env : 4);
-  const dim3 grid((Wo * C8 + 255) / 256, (Ho + ny - 1) / ny, B);
-  const uint4* xp = static_cast<const uint4*>(x);
-  const uint4* wp = static_cast<const uint4*>(w);
-  uint4* yp = static_cast<uint4*>(y);
-  if (stride == 1 && ny == 1) mnet_dw3x3_kernel<1, 1><<<grid, 256, 0, st>>>(xp, wp, bias, slope, yp, H, W, C8, sh, Ho, Wo);
-  else if (stride == 1 && ny == 2) mnet_dw3x3_kernel<1, 2><<<grid, 256, 0, st>>>(xp, wp, bias, slope, yp, H, W, C8, sh, Ho, Wo);
-  else if (stride == 1) mnet_dw3x3_kernel<1, 4><<<grid, 256, 0, st>>>(xp, wp, bias, slope, yp, H, W, C8, sh, Ho, Wo);
-  else if (ny == 1) mnet_dw3x3_kernel<2, 1><<<grid, 256, 0, st>>>(xp, wp, bias, slope, yp, H, W, C8, sh, Ho, Wo);
-  else mnet_dw3x3_kernel<2, 2><<<grid, 256, 0, st>>>(xp, wp, bias, slope, yp, H, W, C8, sh, Ho, Wo);
+  const int ch = ch_env == 8 ? 8 : 4;
+  const int CV = C / ch;
+  int sh = -1;
+  if ((CV & (CV - 1)) == 0) { sh = 0; while ((1 << sh) < CV) ++sh; }
+  const int ny = stride == 2 ? 2 : (ny_env == 2 ? 2 : 4);
+  const dim3 grid((Wo * CV + 255) / 256, (Ho + ny - 1) / ny, B);
+#define VD_DW_LAUNCH(S, N, CHN)                                                                                          \
+  mnet_dw3x3_kernel<S, N, CHN><<<grid, 256, 0, st>>>(static_cast<const ActVec<CHN>::T*>(x), static_cast<const ActVec<CHN>::T*>(w), \
+                                                     bias, slope, static_cast<ActVec<CHN>::T*>(y), H, W, CV, sh, Ho, Wo)
+  if (ch == 4) {
+    if (stride == 2) VD_DW_LAUNCH(2, 2, 4);
+    else if (ny == 2) VD_DW_LAUNCH(1, 2, 4);
+    else VD_DW_LAUNCH(1, 4, 4);
+  } else {
+    if (stride == 2) VD_DW_LAUNCH(2, 2, 8);
+    else if (ny == 2) VD_DW_LAUNCH(1, 2, 8);
+    else VD_DW_LAUNCH(1, 4, 8);
+  }
+#undef VD_DW_LAUNCH
   VD_LAUNCH_CHECK();
   return VD_OK;
+}
+
+template <int CIN, int COUT, int STRIDE, int CH>
+static void launch_dwpw2(const void* x, const void* wdw, const float* bdw, const float* sdw, const void* wpw,
+                         const float* bpw, const float* spw, void* y, int B, int H, int W, int Ho, int Wo, cudaStream_t st) {
+  using Cfg = DwpwCfg<CIN, COUT, STRIDE, CH>;
+  using V = typename ActVec<CH>::T;
+  static const int per_sm = [] {                          // resident CTAs per SM of this instantiation
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mnet_dwpw_kernel<CIN, COUT, STRIDE, CH>, 256, 0) != cudaSuccess || n < 1) n = 2;
+    return n;
+  }();
+  int sms = vd_num_sms();
+  if (sms <= 0) sms = 148;
+  const long long total = static_cast<long long>(B) * ((Ho + Cfg::TY - 1) / Cfg::TY) * ((Wo + Cfg::TX - 1) / Cfg::TX);
+  const int grid = static_cast<int>(total < static_cast<long long>(sms) * per_sm ? total : static_cast<long long>(sms) * per_sm);
+  mnet_dwpw_kernel<CIN, COUT, STRIDE, CH><<<grid, 256, 0, st>>>(static_cast<const V*>(x), static_cast<const V*>(wdw), bdw, sdw,
+                                                               static_cast<const uint16_t*>(wpw), bpw, spw,
+                                                               static_cast<uint4*>(y), B, H, W, Ho, Wo);
 }
 
 template <int CIN, int COUT>
 static void launch_dwpw(const void* x, const void* wdw, const float* bdw, const float* sdw, const void* wpw,
                         const float* bpw, const float* spw, void* y, int B, int H, int W, int stride, int Ho, int Wo,
                         cudaStream_t st) {
-  const uint4* xp = static_cast<const uint4*>(x);
-  const uint4* wd = static_cast<const uint4*>(wdw);
-  const uint16_t* wp = static_cast<const uint16_t*>(wpw);
-  uint4* yp = static_cast<uint4*>(y);
-  if (stride == 1) {
-    using Cfg = DwpwCfg<CIN, COUT, 1>;
-    const dim3 grid((Wo + Cfg::TX - 1) / Cfg::TX, (Ho + Cfg::TY - 1) / Cfg::TY, B);
-    mnet_dwpw_kernel<CIN, COUT, 1><<<grid, 256, 0, st>>>(xp, wd, bdw, sdw, wp, bpw, spw, yp, H, W, Ho, Wo);
+  static const int ch_env = [] { const char* e = getenv("VD_MNET_DWPW_CH"); return e ? atoi(e) : 0; }();
+  if (ch_env == 8) {
+    if (stride == 1) launch_dwpw2<CIN, COUT, 1, 8>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, Ho, Wo, st);
+    else launch_dwpw2<CIN, COUT, 2, 8>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, Ho, Wo, st);
   } else {
-    using Cfg = DwpwCfg<CIN, COUT, 2>;
-    const dim3 grid((Wo + Cfg::TX - 1) / Cfg::TX, (Ho + Cfg::TY - 1) / Cfg::TY, B);
-    mnet_dwpw_kernel<CIN, COUT, 2><<<grid, 256, 0, st>>>(xp, wd, bdw, sdw, wp, bpw, spw, yp, H, W, Ho, Wo);
+    if (stride == 1) launch_dwpw2<CIN, COUT, 1, 4>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, Ho, Wo, st);
+    else launch_dwpw2<CIN, COUT, 2, 4>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, Ho, Wo, st);
   }
 }
 
@@ -456,11 +547,12 @@ extern "C" int vd_mnet_dwpw(const void* x, const void* wdw, const float* bdw, co
                             int stride, vd_stream_t stream) {
   VD_REQUIRE(x && wdw && bdw && sdw && wpw && bpw && spw && y, "vd_mnet_dwpw: null argument");
   VD_REQUIRE(((reinterpret_cast<uintptr_t>(wdw) | reinterpret_cast<uintptr_t>(wpw) | reinterpret_cast<uintptr_t>(x) |
-               reinterpret_cast<uintptr_t>(y)) & 15) == 0, "vd_mnet_dwpw: tensors and weights must be 16-byte aligned");
+               reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bdw) | reinterpret_cast<uintptr_t>(sdw)) & 15) == 0,
+             "vd_mnet_dwpw: tensors, weights and depthwise bias / slope must be 16-byte aligned");
   VD_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && (stride == 1 || stride == 2), "vd_mnet_dwpw: bad extent / stride");
-  VD_REQUIRE(Cin > 0 && static_cast<long long>(B) * H * W * (Cin / 8) < (1ll << 31), "vd_mnet_dwpw: tensor beyond the kernel's 32-bit indexing");
+  VD_REQUIRE(Cin > 0 && static_cast<long long>(B) * H * W * (Cin / 4) < (1ll << 31), "vd_mnet_dwpw: tensor beyond the kernel's 32-bit indexing");
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  VD_REQUIRE((Ho + 7) / 8 <= 65535, "vd_mnet_dwpw: image too tall");
+  VD_REQUIRE(static_cast<long long>(B) * ((Ho + 3) / 4) * ((Wo + 15) / 16) < (1ll << 31), "vd_mnet_dwpw: too many tiles");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cin == 8 && Cout == 16) launch_dwpw<8, 16>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, stride, Ho, Wo, st);
   else if (Cin == 16 && Cout == 32) launch_dwpw<16, 32>(x, wdw, bdw, sdw, wpw, bpw, spw, y, B, H, W, stride, Ho, Wo, st);
