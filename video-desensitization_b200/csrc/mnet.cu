@@ -2,10 +2,14 @@
 //
 // Reference: detect_face/nets/mobilenet025.py:3-19 — conv_bn(3, 8, stride 2) and the conv_dw blocks
 // (depthwise 3x3 + BN + LeakyReLU(0.1), pointwise 1x1 + BN + LeakyReLU(0.1)).  These layers move 8..32-channel
-// tensors at 1/2 and 1/4 resolution: a few MACs per byte, HBM-bound — streaming kernels on the CUDA cores with
-// 16-byte accesses (the rule for this tier: do not reshape byte-bound work into GEMMs).  Pointwise layers with
-// Cin % 64 == 0 and everything after the backbone run on the tcgen05 kernel (conv_tcgen05.cu, VD_CONV_SLOPE).
-// All kernels: activation-type NHWC in/out, fp32 accumulate, folded-BN bias, y = v > 0 ? v : v * slope[c].
+// tensors at 1/2 and 1/4 resolution: HBM-bound by their bytes, but only if the arithmetic stays out of the way —
+//   * depthwise: FHFMA (fma.rn.f32.bf16 / .f16: activation-type operands with .H0/.H1 selectors, fp32 accumulate; measured
+//     at the full FFMA issue rate on B200, tools/probes/fma_rate.cu) — no conversion instructions at all;
+//   * the dense parts (stem 3 -> 8, pointwise Cin <= 32) on warp-level mma.sync: they ARE small GEMMs (K = 8..48,
+//     N = 8..64), 27 resp. Cin FMAs per output value on the CUDA cores would cost 2-3x their HBM time.
+// Pointwise layers with Cin % 64 == 0 and everything after the backbone run on the tcgen05 kernel (conv_tcgen05.cu,
+// VD_CONV_SLOPE).  All kernels: activation-type NHWC in/out, fp32 accumulate starting from the folded-BN bias,
+// y = v > 0 ? v : v * slope[c].
 #include "common.cuh"
 
 namespace {
@@ -185,8 +189,11 @@ __device__ __forceinline__ void load_bias_slope(const float* bias, const float* 
   }
 }
 
-// depthwise 3x3 (+ folded BN + slope), pad 1, stride 1 or 2, for C >= 64: dw_run with the nine weight vectors in
-// registers.  Adjacent lanes hold adjacent channel vectors, then adjacent columns: every load and store of a warp is one
+// depthwise 3x3 (+ folded BN + slope), pad 1, stride 1 or 2, for C >= 64: dw_load + dw_compute with the nine weight vectors
+// in registers.  (A rolling-window form — one thread walks a column segment with a ring of six input rows, 3 loads per output
+// instead of 4.5 — was measured on the same box at segment lengths 12 / 17 / 23 / whole column: 0.055-0.089 ms against
+// 0.043 ms for this kernel on the 64-channel layer and 0.025-0.029 against 0.0225 ms on the 128-channel ones; many
+// short-lived threads hide the load latency better than few long-lived ones.)  Adjacent lanes hold adjacent channel vectors, then adjacent columns: every load and store of a warp is one
 // contiguous run.  grid = (ceil(Wo * CV / 256), ceil(Ho / NY), B).
 template <int STRIDE, int NY, int CH>
 __global__ void __launch_bounds__(256)
