@@ -1,0 +1,11 @@
+#!/bin/bash
+# MobileNet variant, artefacts of record: per-op times (bf16 + fp16), FMA issue-rate probe, ncu captures of the fused block,
+# a depthwise layer and the stem
+mkdir -p gpurun_out
+python tools/layer_times_mnet.py 16 1080 1920 10 bf16 2>/dev/null | grep -v Warning > gpurun_out/r02_layer_times_mnet_B16_1080p.log
+python tools/layer_times_mnet.py 16 1080 1920 10 fp16 2>/dev/null | grep -v Warning > gpurun_out/r02_layer_times_mnet_B16_1080p_fp16.log
+head -1 gpurun_out/r02_layer_times_mnet_B16_1080p.log; tail -2 gpurun_out/r02_layer_times_mnet_B16_1080p.log | head -1
+./build/fma_rate > gpurun_out/r02_fma_rate_probe.log 2>&1
+bash tools/gpu_ncu_mnet.sh body.stage1.3 r02dwpw3c
+bash tools/gpu_ncu_mnet.sh body.stage1.5.dw r02dw5c
+bash tools/gpu_ncu_mnet.sh body.stage1.0 r02stemc

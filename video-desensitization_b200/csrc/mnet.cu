@@ -60,7 +60,7 @@ __device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[4], ui
 // 16 bytes further on, so each register of the A fragment is one coalesced 128-byte load straight from global memory
 // (12 per 16 pixels, L1 serves the overlap) and each of the two output registers one coalesced 128-byte store.
 // On the CUDA cores this layer costs 27 FMAs per output value — 105 us of FMA issue at 1080p against 60 us of HBM time.
-constexpr int STEM_RY = 4;
+constexpr int STEM_RY = 4, STEM_NB = 4;
 __global__ void __launch_bounds__(256)
 mnet_stem_kernel(const uint8_t* __restrict__ x0, const uint16_t* __restrict__ w, const float* __restrict__ bias,
                  const float* __restrict__ slope, uint32_t* __restrict__ y, int B, int H, int W, int Wp, int Ho, int Wo) {
@@ -74,40 +74,45 @@ mnet_stem_kernel(const uint8_t* __restrict__ x0, const uint16_t* __restrict__ w,
     bf[r][1] = tig < 2 ? static_cast<uint32_t>(w[(r * 12 + k + 8) * 8 + gid]) | (static_cast<uint32_t>(w[(r * 12 + k + 9) * 8 + gid]) << 16) : 0u;
   }
   const float2 bs = *reinterpret_cast<const float2*>(bias + tig * 2), sl = *reinterpret_cast<const float2*>(slope + tig * 2);
-  // one warp = 16 output columns x STEM_RY output rows: the 2 RY + 1 input rows it needs are all requested before the first
-  // mma (an odd input row is filter row 2 of one output row and filter row 0 of the next: loaded once)
-  const int wo0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 16, ho0 = blockIdx.y * STEM_RY, b = blockIdx.z;
-  if (wo0 >= Wo) return;
-  // rows of the fragment: output pixels wo0 + gid and wo0 + gid + 8 (clamped for the address, masked at the store)
-  const int c0 = min(wo0 + gid, Wo - 1), c1 = min(wo0 + gid + 8, Wo - 1);
-  const uint8_t* base = x0 + static_cast<size_t>(b) * H * Wp * 8 + tig * 4;
-  const int o0 = (2 * c0 + 2) * 8, o1 = (2 * c1 + 2) * 8;
-  uint32_t a[2 * STEM_RY + 1][4];
+  // one warp step = 16 output columns x STEM_RY output rows: the 2 RY + 1 input rows it needs are all requested before the
+  // first mma (an odd input row is filter row 2 of one output row and filter row 0 of the next: loaded once).  A warp
+  // takes STEM_NB consecutive column blocks, so the fragment / bias set-up above is paid once per 64 x 4 outputs.
+  const int ho0 = blockIdx.y * STEM_RY, b = blockIdx.z;
+  const int roww = Wp * 2;                                 // words per padded input row (32-bit offsets: host checks the extent)
+  const uint32_t* xrow = reinterpret_cast<const uint32_t*>(x0) + ((b * H + 2 * ho0 - 1) * roww + 4 + tig);
+  uint32_t* yrow = y + (b * Ho + ho0) * Wo * 4 + tig;      // 4 words per output pixel
+#pragma unroll 1
+  for (int nb = 0; nb < STEM_NB; ++nb) {
+    const int wo0 = ((blockIdx.x * 8 + (threadIdx.x >> 5)) * STEM_NB + nb) * 16;
+    if (wo0 >= Wo) return;
+    // rows of the fragment: output pixels wo0 + gid and wo0 + gid + 8 (clamped for the address, masked at the store)
+    const int c0 = min(wo0 + gid, Wo - 1), c1 = min(wo0 + gid + 8, Wo - 1);
+    const uint32_t* p0 = xrow + 4 * c0;
+    const uint32_t* p1 = xrow + 4 * c1;
+    uint32_t a[2 * STEM_RY + 1][4];
 #pragma unroll
-  for (int i = 0; i < 2 * STEM_RY + 1; ++i) {
-    const int yi = 2 * ho0 - 1 + i;
-    a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0u;            // rows outside the image: zero operand
-    if (yi >= 0 && yi < H) {
-      const uint8_t* row = base + static_cast<size_t>(yi) * Wp * 8;
-      a[i][0] = __ldg(reinterpret_cast<const uint32_t*>(row + o0));
-      a[i][1] = __ldg(reinterpret_cast<const uint32_t*>(row + o1));
-      a[i][2] = __ldg(reinterpret_cast<const uint32_t*>(row + o0 + 16));
-      a[i][3] = __ldg(reinterpret_cast<const uint32_t*>(row + o1 + 16));
+    for (int i = 0; i < 2 * STEM_RY + 1; ++i) {
+      const bool ok = static_cast<unsigned int>(2 * ho0 - 1 + i) < static_cast<unsigned int>(H);   // outside the image: zero operand
+      a[i][0] = ok ? __ldg(p0) : 0u;
+      a[i][1] = ok ? __ldg(p1) : 0u;
+      a[i][2] = ok ? __ldg(p0 + 4) : 0u;
+      a[i][3] = ok ? __ldg(p1 + 4) : 0u;
+      p0 += roww;
+      p1 += roww;
     }
-  }
+    uint32_t* out = yrow + wo0 * 4;
 #pragma unroll
-  for (int j = 0; j < STEM_RY; ++j) {
-    const int ho = ho0 + j;
-    if (ho >= Ho) break;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < STEM_RY; ++j) {
+      if (ho0 + j >= Ho) break;
+      float acc[4] = {bs.x, bs.y, bs.x, bs.y};             // accumulators start at the bias of their two columns
 #pragma unroll
-    for (int r = 0; r < 3; ++r) mma_k16(acc, a[2 * j + r], bf[r][0], bf[r][1]);
-    float v0 = acc[0] + bs.x, v1 = acc[1] + bs.y, v2 = acc[2] + bs.x, v3 = acc[3] + bs.y;
-    v0 = v0 > 0.f ? v0 : v0 * sl.x; v1 = v1 > 0.f ? v1 : v1 * sl.y;
-    v2 = v2 > 0.f ? v2 : v2 * sl.x; v3 = v3 > 0.f ? v3 : v3 * sl.y;
-    uint32_t* out = y + ((static_cast<size_t>(b) * Ho + ho) * Wo + wo0) * 4 + tig;      // 4 words per output pixel
-    if (wo0 + gid < Wo) out[gid * 4] = pack_bf16x2(v0, v1);
-    if (wo0 + gid + 8 < Wo) out[(gid + 8) * 4] = pack_bf16x2(v2, v3);
+      for (int r = 0; r < 3; ++r) mma_k16(acc, a[2 * j + r], bf[r][0], bf[r][1]);
+      const float v0 = acc[0] > 0.f ? acc[0] : acc[0] * sl.x, v1 = acc[1] > 0.f ? acc[1] : acc[1] * sl.y;
+      const float v2 = acc[2] > 0.f ? acc[2] : acc[2] * sl.x, v3 = acc[3] > 0.f ? acc[3] : acc[3] * sl.y;
+      if (wo0 + gid < Wo) out[gid * 4] = pack_bf16x2(v0, v1);
+      if (wo0 + gid + 8 < Wo) out[(gid + 8) * 4] = pack_bf16x2(v2, v3);
+      out += Wo * 4;
+    }
   }
 }
 
@@ -469,7 +474,8 @@ extern "C" int vd_mnet_stem(const void* x0, const void* w, const float* bias, co
   VD_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "vd_mnet_stem: weights must be 16-byte aligned");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   VD_REQUIRE(B <= 65535 && (Ho + STEM_RY - 1) / STEM_RY <= 65535, "vd_mnet_stem: batch / height beyond the grid limits");
-  const dim3 grid(((Wo + 15) / 16 + 7) / 8, (Ho + STEM_RY - 1) / STEM_RY, B);
+  VD_REQUIRE(static_cast<long long>(B) * H * vd_x0_pitch(W) * 2 < (1ll << 31), "vd_mnet_stem: input beyond the kernel's 32-bit indexing");
+  const dim3 grid(((Wo + 15) / 16 + 8 * STEM_NB - 1) / (8 * STEM_NB), (Ho + STEM_RY - 1) / STEM_RY, B);
   mnet_stem_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(x0), static_cast<const uint16_t*>(w), bias, slope, static_cast<uint32_t*>(y), B, H, W,
       vd_x0_pitch(W), Ho, Wo);
