@@ -38,7 +38,7 @@ int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 4096);
   const char* names[3] = {"FFMA (16 chains)", "FFMA2 (8 chains x 2)", "FHFMA.BF16 (16 chains)"};
-  for (int warps = 1; warps <= 16; warps *= 2) {
+  for (int warps = 1; warps <= 8; warps *= 2) {
     for (int mode = 0; mode < 3; ++mode) {
       long long h = 0;
       for (int rep = 0; rep < 2; ++rep) {
