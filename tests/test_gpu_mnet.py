@@ -99,7 +99,11 @@ def test_mnet_pointwise(ops, cin, cout, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("cin,cout,stride,shape", [(8, 16, 1, (2, 23, 31)), (16, 32, 2, (2, 23, 31)), (32, 32, 1, (1, 40, 64)),
-                                                   (32, 64, 2, (3, 33, 17)), (32, 64, 2, (2, 67, 121)), (8, 16, 1, (1, 8, 32))])
+                                                   (32, 64, 2, (3, 33, 17)), (32, 64, 2, (2, 67, 121)), (8, 16, 1, (1, 8, 32)),
+                                                   # more tiles than resident CTAs: the persistent kernel's tile loop, its
+                                                   # prefetch across tiles and the division-free tile walk
+                                                   (8, 16, 1, (4, 270, 480)), (16, 32, 2, (4, 270, 480)),
+                                                   (32, 32, 1, (2, 135, 241)), (32, 64, 2, (3, 135, 239))])
 def test_mnet_fused_dwpw_is_bit_identical_to_two_kernels(ops, cin, cout, stride, shape, dtype):
     B, H, W = shape
     g = torch.Generator().manual_seed(cin * cout + stride + H)
@@ -111,6 +115,32 @@ def test_mnet_fused_dwpw_is_bit_identical_to_two_kernels(ops, cin, cout, stride,
     want = ops.mnet_pw(ops.mnet_dw3x3(x, wdw, bdw, sdw, stride), wpw, bpw, spw)
     got = ops.mnet_dwpw(x, wdw, bdw, sdw, wpw, bpw, spw, stride)
     assert got.shape == want.shape and torch.equal(got, want), float((got.float() - want.float()).abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,stride,shape", [(8, 16, 1, (3, 200, 333)), (32, 64, 2, (3, 135, 239))])
+def test_mnet_fused_dwpw_against_torch(ops, cin, cout, stride, shape, dtype):
+    """the fused conv_dw block at a size with several tiles per persistent CTA against torch (fp32 math, the depthwise
+    result rounded to the storage type where the kernel rounds it)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(11 * cin + cout + W)
+    x = torch.randn(B, cin, H, W, generator=g).to(dtype)
+    wdw = (torch.randn(cin, 1, 3, 3, generator=g) * 0.3).to(dtype)
+    bdw, sdw = torch.randn(cin, generator=g), torch.rand(cin, generator=g)
+    wpw = (torch.randn(cout, cin, generator=g) * 0.2).to(dtype)
+    bpw, spw = torch.randn(cout, generator=g), torch.rand(cout, generator=g)
+    got = ops.mnet_dwpw(x.permute(0, 2, 3, 1).contiguous().to(DEV), wdw[:, 0].permute(1, 2, 0).reshape(9, cin).contiguous().to(DEV),
+                        bdw.to(DEV), sdw.to(DEV), wpw.t().contiguous().to(DEV), bpw.to(DEV), spw.to(DEV), stride)
+    d = _act(F.conv2d(x.float(), wdw.float(), bdw, stride, 1, 1, cin), sdw).to(dtype).float()
+    want = _act(F.conv2d(d, wpw.float().view(cout, cin, 1, 1), bpw), spw)
+    got = got.cpu().permute(0, 3, 1, 2).float()
+    assert got.shape == want.shape
+    step = 2.0 ** (-8 if dtype == torch.bfloat16 else -11)
+    err = (got - want).abs()
+    # one rounding step of the output plus what a flipped rounding of a depthwise value moves it (|w| <= ~0.8, |d| step)
+    tol = want.abs() * (2 * step) + d.abs().max() * step * 1.0 + 1e-5
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.3e}, worst excess {float((err - tol).max()):.3e}"
+    assert float((err.pow(2).mean().sqrt() / want.pow(2).mean().sqrt())) <= 2 * step
 
 
 def test_mnet_kernel_argument_errors(ops):
