@@ -332,13 +332,6 @@ __device__ __forceinline__ float act_fma(uint32_t a, uint32_t b, float c) {
 #undef VD_FHFMA_
   return d;
 }
-// acc[0..7] += x[0..7] * w[0..7] (eight activation-type values per uint4, element-wise)
-__device__ __forceinline__ void act_fma8(float (&acc)[8], const uint4& x, const uint4& w) {
-  acc[0] = act_fma<0, 0>(x.x, w.x, acc[0]); acc[1] = act_fma<1, 1>(x.x, w.x, acc[1]);
-  acc[2] = act_fma<0, 0>(x.y, w.y, acc[2]); acc[3] = act_fma<1, 1>(x.y, w.y, acc[3]);
-  acc[4] = act_fma<0, 0>(x.z, w.z, acc[4]); acc[5] = act_fma<1, 1>(x.z, w.z, acc[5]);
-  acc[6] = act_fma<0, 0>(x.w, w.w, acc[6]); acc[7] = act_fma<1, 1>(x.w, w.w, acc[7]);
-}
 // acc[0..7] += xs * w[0..7] with xs = half XH of the word x (a broadcast scalar)
 template <int XH>
 __device__ __forceinline__ void act_fma8s(float (&acc)[8], uint32_t x, const uint4& w) {
