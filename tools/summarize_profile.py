@@ -40,7 +40,7 @@ for r in rows:
 tot = sum(t for _, t in agg.values())
 out.append("## 1. Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 700`)\n")
 out.append("Per-launch times are cold-cache and serialised: compare SHARES with bench.py's live CUDA-event segments "
-           f"(`profiles/{tag}_bench_final.log`, `segments_ms`).\n")
+           f"(`profiles/{tag}_bench_final.json`, `segments_ms`).\n")
 out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / tot:.1f} % |")
