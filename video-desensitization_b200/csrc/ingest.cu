@@ -103,14 +103,15 @@ constexpr int ID_PAIRS = 4;                                  // pairs per thread
 constexpr int ID_PAIRS_PER_BLOCK = ID_THREADS * ID_PAIRS;    // 1024 pairs = 2048 columns = 6144 source bytes
 constexpr int ID_SMEM_BYTES = 6 * ID_PAIRS_PER_BLOCK + 64;   // + alignment slack on both sides
 
+// ROWS rows per CTA: the (at most two per thread and row) 16-byte loads of all rows are issued before the first store, so a
+// CTA keeps ROWS x 5.7 KB in flight instead of one row's worth.
+template <int ROWS>
 __global__ void __launch_bounds__(ID_THREADS)
 ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, const vd_frame_t* __restrict__ copy_dst,
                           uint4* __restrict__ x0, int H, int W, int Wp, float m0, float m1, float m2) {
-  __shared__ __align__(16) uint8_t s_raw[ID_SMEM_BYTES];
+  __shared__ __align__(16) uint8_t s_raw_all[ROWS][ID_SMEM_BYTES];
   const int b = blockIdx.z;
-  const int y = blockIdx.y;
   const vd_frame_t fr = frames[b];
-  const uint8_t* __restrict__ src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
   const int npairs = Wp >> 1;
   const int j0 = blockIdx.x * ID_PAIRS_PER_BLOCK;
   const int j1 = min(j0 + ID_PAIRS_PER_BLOCK, npairs);
@@ -118,72 +119,105 @@ ingest_x0_identity_kernel(const vd_frame_t* __restrict__ frames, const vd_frame_
   // bytes [lo, hi) of the row feed pairs [j0, j1): pixels 2*j0 - 3 .. 2*j1 - 4 (clipped to the row); consecutive
   // blocks' ranges tile the row, so with copy_dst every byte of it is copied
   const int lo = max(0, 6 * j0 - 9), hi = min(row_bytes, 6 * j1 - 9);
-  // shared-memory byte i holds row byte s_base + i; s_base keeps the row's own 16-byte phase so that the vector
-  // loads are aligned on both sides
-  const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15);
-  const int s_base = ((lo + phase) & ~15) - phase;          // <= lo, and (src + s_base) is 16-byte aligned
-  uint8_t* dst_row = nullptr;
-  if (copy_dst) {
-    const vd_frame_t fd = copy_dst[b];
-    dst_row = const_cast<uint8_t*>(fd.ptr) + static_cast<size_t>(y) * fd.pitch;
-  }
-  if (hi > lo) {
+  vd_frame_t fd;
+  fd.ptr = nullptr; fd.pitch = 0;
+  if (copy_dst) fd = copy_dst[b];
+  int s_base_r[ROWS];
+  uint4 v[ROWS][2];
+  // ---- phase 1a: request the aligned 16-byte vectors of every row ----
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int y = blockIdx.y * ROWS + rr;
+    s_base_r[rr] = 0;
+    if (y >= H || hi <= lo) continue;
+    const uint8_t* __restrict__ src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
+    // shared-memory byte i holds row byte s_base + i; s_base keeps the row's own 16-byte phase so that the vector
+    // loads are aligned on both sides
+    const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15);
+    const int s_base = ((lo + phase) & ~15) - phase;        // <= lo, and (src + s_base) is 16-byte aligned
+    s_base_r[rr] = s_base;
     const int v_lo = s_base < 0 ? s_base + 16 : s_base;     // first 16-byte vector fully inside the row
     const int v_hi = s_base + ((hi - s_base) & ~15);        // end of the last one
-    // vectors
-    for (int o = v_lo + 16 * static_cast<int>(threadIdx.x); o < v_hi; o += 16 * ID_THREADS) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + o));
-      *reinterpret_cast<uint4*>(s_raw + (o - s_base)) = v;
-      if (dst_row) {
-        if ((reinterpret_cast<uintptr_t>(dst_row + o) & 15) == 0) {
-          *reinterpret_cast<uint4*>(dst_row + o) = v;
-        } else {
-          const uint8_t* vb = reinterpret_cast<const uint8_t*>(&v);
-          for (int k = 0; k < 16; ++k) dst_row[o + k] = vb[k];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {                           // (6144 + 64) / 16 <= 2 * ID_THREADS vectors per row chunk
+      const int o = v_lo + 16 * (static_cast<int>(threadIdx.x) + q * ID_THREADS);
+      if (o < v_hi) v[rr][q] = __ldg(reinterpret_cast<const uint4*>(src + o));
+    }
+  }
+  // ---- phase 1b: into shared memory (and the frame copy), ragged ends byte by byte ----
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int y = blockIdx.y * ROWS + rr;
+    if (y >= H || hi <= lo) continue;
+    const uint8_t* __restrict__ src = fr.ptr + static_cast<size_t>(y) * fr.pitch;
+    uint8_t* s_raw = s_raw_all[rr];
+    const int s_base = s_base_r[rr];
+    uint8_t* dst_row = fd.ptr ? const_cast<uint8_t*>(fd.ptr) + static_cast<size_t>(y) * fd.pitch : nullptr;
+    const int v_lo = s_base < 0 ? s_base + 16 : s_base;
+    const int v_hi = s_base + ((hi - s_base) & ~15);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int o = v_lo + 16 * (static_cast<int>(threadIdx.x) + q * ID_THREADS);
+      if (o < v_hi) {
+        *reinterpret_cast<uint4*>(s_raw + (o - s_base)) = v[rr][q];
+        if (dst_row) {
+          if ((reinterpret_cast<uintptr_t>(dst_row + o) & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst_row + o) = v[rr][q];
+          } else {
+            const uint8_t* vb = reinterpret_cast<const uint8_t*>(&v[rr][q]);
+            for (int k = 0; k < 16; ++k) dst_row[o + k] = vb[k];
+          }
         }
       }
     }
     // ragged head and tail of the segment (and everything, if v_hi <= v_lo)
     const int head_end = min(max(v_lo, lo), hi), tail_begin = max(min(v_hi, hi), head_end);
     for (int o = lo + static_cast<int>(threadIdx.x); o < head_end; o += ID_THREADS) {
-      const uint8_t v = __ldg(src + o);
-      s_raw[o - s_base] = v;
-      if (dst_row) dst_row[o] = v;
+      const uint8_t bv = __ldg(src + o);
+      s_raw[o - s_base] = bv;
+      if (dst_row) dst_row[o] = bv;
     }
     for (int o = tail_begin + static_cast<int>(threadIdx.x); o < hi; o += ID_THREADS) {
-      const uint8_t v = __ldg(src + o);
-      s_raw[o - s_base] = v;
-      if (dst_row) dst_row[o] = v;
+      const uint8_t bv = __ldg(src + o);
+      s_raw[o - s_base] = bv;
+      if (dst_row) dst_row[o] = bv;
     }
   }
   __syncthreads();
-  uint4* row = x0 + (static_cast<size_t>(b) * H + y) * npairs;
-  const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_raw);
+  // ---- phase 2: x0 rows ----
 #pragma unroll
-  for (int p = 0; p < ID_PAIRS; ++p) {
-    const int j = j0 + p * ID_THREADS + static_cast<int>(threadIdx.x);
-    if (j >= j1) continue;
-    const int xa = 2 * j - 3;                       // pixel of column 2j; xa + 1 is the pixel of column 2j + 1
-    const bool va = xa >= 0 && xa < W, vb = xa + 1 >= 0 && xa + 1 < W;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (va || vb) {
-      const int off = 3 * xa - s_base;              // shared-memory byte of the pair's first byte (may be < 0 if !va)
-      const int w = off >> 2;                       // arithmetic shift: floor
-      const uint32_t sh = static_cast<uint32_t>(off & 3) * 8u;
-      // words outside the staged range are never selected into a VALID pixel's bytes
-      const uint32_t w0 = w >= 0 ? s_w[w] : 0u, w1 = s_w[w + 1], w2 = (4 * (w + 2) < ID_SMEM_BYTES) ? s_w[w + 2] : 0u;
-      const uint32_t lo4 = __funnelshift_r(w0, w1, sh);     // bytes 0..3 of the pair
-      const uint32_t hi4 = __funnelshift_r(w1, w2, sh);     // bytes 4..7 (4, 5 used)
-      if (va) {
-        o.x = pack_bf16x2(static_cast<float>(lo4 & 0xFFu) - m0, static_cast<float>((lo4 >> 8) & 0xFFu) - m1);
-        o.y = pack_bf16x2(static_cast<float>((lo4 >> 16) & 0xFFu) - m2, 0.f);
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int y = blockIdx.y * ROWS + rr;
+    if (y >= H) continue;
+    const int s_base = s_base_r[rr];
+    uint4* row = x0 + (static_cast<size_t>(b) * H + y) * npairs;
+    const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_raw_all[rr]);
+#pragma unroll
+    for (int p = 0; p < ID_PAIRS; ++p) {
+      const int j = j0 + p * ID_THREADS + static_cast<int>(threadIdx.x);
+      if (j >= j1) continue;
+      const int xa = 2 * j - 3;                       // pixel of column 2j; xa + 1 is the pixel of column 2j + 1
+      const bool va = xa >= 0 && xa < W, vb = xa + 1 >= 0 && xa + 1 < W;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (va || vb) {
+        const int off = 3 * xa - s_base;              // shared-memory byte of the pair's first byte (may be < 0 if !va)
+        const int w = off >> 2;                       // arithmetic shift: floor
+        const uint32_t sh = static_cast<uint32_t>(off & 3) * 8u;
+        // words outside the staged range are never selected into a VALID pixel's bytes
+        const uint32_t w0 = w >= 0 ? s_w[w] : 0u, w1 = s_w[w + 1], w2 = (4 * (w + 2) < ID_SMEM_BYTES) ? s_w[w + 2] : 0u;
+        const uint32_t lo4 = __funnelshift_r(w0, w1, sh);     // bytes 0..3 of the pair
+        const uint32_t hi4 = __funnelshift_r(w1, w2, sh);     // bytes 4..7 (4, 5 used)
+        if (va) {
+          o.x = pack_bf16x2(static_cast<float>(lo4 & 0xFFu) - m0, static_cast<float>((lo4 >> 8) & 0xFFu) - m1);
+          o.y = pack_bf16x2(static_cast<float>((lo4 >> 16) & 0xFFu) - m2, 0.f);
+        }
+        if (vb) {
+          o.z = pack_bf16x2(static_cast<float>(lo4 >> 24) - m0, static_cast<float>(hi4 & 0xFFu) - m1);
+          o.w = pack_bf16x2(static_cast<float>((hi4 >> 8) & 0xFFu) - m2, 0.f);
+        }
       }
-      if (vb) {
-        o.z = pack_bf16x2(static_cast<float>(lo4 >> 24) - m0, static_cast<float>(hi4 & 0xFFu) - m1);
-        o.w = pack_bf16x2(static_cast<float>((hi4 >> 8) & 0xFFu) - m2, 0.f);
-      }
+      row[j] = o;
     }
-    row[j] = o;
   }
 }
 
@@ -226,8 +260,9 @@ static int ingest_identity(const vd_frame_t* frames, const vd_frame_t* copy_dst,
   VD_REQUIRE(frames && x0 && mean, "vd_ingest_u8hwc_identity: null argument");
   VD_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "vd_ingest_u8hwc_identity: bad extent");
   const int Wp = vd_x0_pitch(W);
-  dim3 grid(vd_cdiv(Wp / 2, ID_PAIRS_PER_BLOCK), H, B);        // 1080p: one block per row (968 pairs)
-  ingest_x0_identity_kernel<<<grid, ID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  // two rows per CTA (measured on one box, ingest + frame copy of 16 x 1080p: 1 row 0.0810 ms, 2 rows 0.0803, 4 rows 0.0822)
+  dim3 grid(vd_cdiv(Wp / 2, ID_PAIRS_PER_BLOCK), vd_cdiv(H, 2), B);      // 1080p: one block per row pair (968 column pairs)
+  ingest_x0_identity_kernel<2><<<grid, ID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       frames, copy_dst, static_cast<uint4*>(x0), H, W, Wp, mean[0], mean[1], mean[2]);
   VD_LAUNCH_CHECK();
   return VD_OK;
