@@ -185,8 +185,10 @@ int vd_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, vd_strea
 int vd_maxpool3x3s2_split(const void* x, void* y, int B, int H, int W, int C, vd_stream_t stream);
 
 /* ---- MobileNet0.25 variant (Retinaface(backbone="mobilenet"), reference detect_face/nets/mobilenet025.py) ----------
- * The layers whose channel count is below the tensor-core kernel's 64-channel granule are HBM-bound streaming
- * kernels on the CUDA cores (bf16/fp16 NHWC in and out, fp32 accumulate, folded BN bias, per-channel slope):
+ * The layers whose channel count is below the tcgen05 kernel's 64-channel granule are HBM-bound streaming kernels
+ * (bf16/fp16 NHWC in and out, fp32 accumulate, folded BN bias, per-channel slope): depthwise taps as mixed-precision
+ * FMAs on the CUDA cores, the stem and the pointwise layers with Cin in {8, 16, 32} as warp-level mma.sync GEMMs.
+ * Every tensor, weight, bias and slope pointer must be 16-byte aligned; tensors up to 2^31 16-byte vectors.
  *   vd_mnet_stem   conv_bn(3, 8, stride 2) on the ingest layout x0            (mobilenet025.py:3-8, :26)
  *   vd_mnet_dw3x3  depthwise 3x3, stride 1 or 2, pad 1, C % 8 == 0            (conv_dw first half, :10-14)
  *   vd_mnet_pw     pointwise 1x1, Cin % 8 == 0, Cout % 8 == 0, Cin*Cout <= 4096 (conv_dw second half, :16-18)
