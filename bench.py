@@ -336,6 +336,74 @@ def short_summary(name, precision, dev, steps, warmup=3):
     return out
 
 
+def mobilenet_extra(dev, precision, steps=10, warmup=3):
+    """the same 16 x 1080p step with Retinaface(backbone="mobilenet") — device-timed frames/s, the
+    network segment, and the network's algorithmic HBM traffic (every op: input read once + output written once) over that
+    segment against the measured copy peak.  Its convolution launches are HBM-bound, not tensor-bound."""
+    from vdesens_b200 import arch_mnet, synth
+    from vdesens_b200.engine import DetectorEngine
+    wl = WORKLOADS["c2"]
+    H, W, B = wl["H"], wl["W"], wl["batch"]
+    sd = synth.synthetic_state_dict(0, face_rate=wl["face_rate"], backbone="mobilenet")
+    eng = DetectorEngine(sd, B, H, W, device=dev, confidence=0.5, nms_iou=0.4, precision=precision, backbone="mobilenet")
+    frames = torch.from_numpy(np.stack([synth.synthetic_frame(H, W, 1000 + i) for i in range(B)])).to(dev)
+    work = torch.empty_like(frames)
+    from vdesens_b200 import ops
+    desc = ops.frame_descriptors([frames[i] for i in range(B)])
+    eng.set_frames(work)
+    eng.set_ext_boxes([plate_boxes(wl, 50 + i) for i in range(B)])
+    st = eng.stream
+
+    def step(ev=None):
+        with torch.cuda.stream(st):
+            eng.enqueue_ingest(src_desc=desc)
+            if ev:
+                ev[0].record(st)
+            eng.enqueue_network()
+            if ev:
+                ev[1].record(st)
+            eng.enqueue_postprocess()
+            eng.enqueue_composite(wl["mode"], ksize=wl["ksize"] or 31)
+
+    for _ in range(warmup):
+        step()
+    st.synchronize()
+    eng.fetch_results()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    e0.record(st)
+    for i in range(steps):
+        step(seg[i])
+    e1.record(st)
+    st.synchronize()
+    _, counts = eng.fetch_results()
+    ms = e0.elapsed_time(e1) / steps
+    net_ms = sum(a.elapsed_time(b) for a, b in seg) / steps
+    ops_, _ = arch_mnet.build_graph(fuse_dwpw=eng.fuse_dwpw)
+
+    def nbytes(name):
+        if name == "x0":
+            return B * H * W * 8                  # 4 channels x 2 bytes per pixel of the ingest layout
+        t = eng.buf[name]
+        return t.numel() * t.element_size()
+
+    by = 0
+    for op in ops_:
+        by += nbytes(op.src)
+        if op.kind == "heads":
+            by += nbytes(op.src2) + eng.heads[op.level].numel() * 4
+        else:
+            by += nbytes(op.dst) + (nbytes(op.upsample_add) if op.upsample_add else 0)
+    hbm_peak, _, _ = load_peaks()
+    out = {"what": "BASELINE configs[1] with backbone='mobilenet' (MobileNet0.25 RetinaFace), same frames, boxes and blur",
+           "dtype": DTYPE_NAME[precision], "frames_per_s": B / ms * 1e3, "ms_per_step": ms, "network_ms": net_ms,
+           "network_algorithmic_bytes": by, "network_gbs": by / net_ms / 1e6, "network_frac_of_hbm_peak": by / net_ms / 1e6 / hbm_peak,
+           "launches_per_step": eng.launches_per_forward + 2, "faces_per_frame": float(np.mean(counts)), "steps": steps, "warmup": warmup}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_baseline(dev, wl, sd, frames, plates, steps=3):
     """The 'kernel to beat' (SURVEY §8d): the reference's own GPU execution model on this B200 — PyTorch + cuDNN with
     TF32 allowed (torch's default, what `cuda=True` runs) for the network, torchvision NMS with one sync per frame,
@@ -616,6 +684,7 @@ def run_ours(args):
                                   for p in ("bf16", "fp16", "fp32x") if p != precision}
             line["other_configs"] = {c: short_summary(c, precision, dev, 5) for c in ("c3", "c5") if c != args.config}
             line["ingest_letterbox"] = letterbox_ingest_extra(dev, precision)
+            line["mobilenet"] = mobilenet_extra(dev, precision)
             line["tensor_peak_probe"] = tensor_peak_probe(dev)
             pk = line["tensor_peak_probe"].get({"fp16": "fp16", "bf16": "bf16"}.get(precision, "bf16") + "_tflops_sustained")
             if pk:
