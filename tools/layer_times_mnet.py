@@ -18,6 +18,7 @@ precision = sys.argv[5] if len(sys.argv) > 5 else "bf16"
 
 sd = synth.synthetic_state_dict(0, face_rate="r01", backbone="mobilenet")
 eng = DetectorEngine(sd, B, H, W, backbone="mobilenet", precision=precision)
+eng.use_graph = False                # per-op timing: eager launches (a graph would be captured inside the timed loops)
 frames = torch.stack([torch.from_numpy(synth.synthetic_frame(H, W, 1000 + i)) for i in range(B)]).cuda()
 eng.set_frames(frames)
 eng.forward()

@@ -9,6 +9,7 @@ name = sys.argv[1]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 eng = DetectorEngine(synth.synthetic_state_dict(0, face_rate="r01", backbone="mobilenet"), B, 1080, 1920, backbone="mobilenet")
+eng.use_graph = False                # per-op timing: eager launches (a graph would be captured inside the timed loops)
 frames = torch.stack([torch.from_numpy(synth.synthetic_frame(1080, 1920, 1000 + i)) for i in range(B)]).cuda()
 eng.set_frames(frames)
 eng.forward()                       # real activations in every buffer

@@ -79,6 +79,8 @@ class DetectorEngine:
         assert cand_cap >= 64 and (cand_cap & (cand_cap - 1)) == 0 and cand_cap <= _lib.VD_NMS_MAX_CAND
         self.cap, self.max_det, self.max_ext = int(cand_cap), int(max_det), int(max_ext)
         self.launches_per_forward = 0
+        self.use_graph = os.environ.get("VD_GRAPH", "1") != "0"   # replay the network's launches from a CUDA graph
+        self._graph, self._graph_key, self._graph_key_seen, self._net_calls = None, None, None, 0
         with torch.cuda.device(self.device):
             sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
             self._check(self.lib.vd_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), "vd_device_info")
@@ -392,6 +394,34 @@ class DetectorEngine:
 
     @_on_device
     def enqueue_network(self, upto=None):
+        """the network's launches on the engine stream.  From the third call on (same plan list, no `upto`) they are replayed
+        from a CUDA graph captured on the second: every argument of these launches is fixed for the engine's lifetime
+        (internal buffers, weights, tensor maps), and a graph launch removes the per-kernel launch latency between the
+        ~65 dependent kernels.  VD_GRAPH=0 keeps the eager launches."""
+        if upto is None and self.use_graph:
+            key = (id(self.plans), len(self.plans))
+            if self._graph is not None and self._graph_key == key:
+                with torch.cuda.stream(self.stream):
+                    self._graph.replay()
+                return
+            self._net_calls = self._net_calls + 1 if self._graph_key_seen == key else 1
+            self._graph_key_seen = key
+            if self._net_calls == 2:                      # the first call warmed every kernel up (function attributes, caches)
+                g = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                        self._enqueue_network_eager(None)
+                    self._graph, self._graph_key = g, key
+                    with torch.cuda.stream(self.stream):
+                        g.replay()
+                    return
+                except Exception:                         # capture not possible here: stay eager, loudly once
+                    import warnings
+                    warnings.warn("vdesens_b200: CUDA graph capture of the network failed, launching eagerly")
+                    self.use_graph = False
+        self._enqueue_network_eager(upto)
+
+    def _enqueue_network_eager(self, upto=None):
         s = C.c_void_p(self.stream.cuda_stream)
         for kind, h, name in self.plans:
             if kind == "conv":
