@@ -1483,12 +1483,16 @@ extern "C" int vd_conv_plan_info(const vd_conv_plan_t* plan, int* TW, int* TH, i
   return VD_OK;
 }
 
-// VD_CONV_PDL=1 enables programmatic dependent launch (prologue of kernel k+1 overlaps the tail of kernel k).
-// Measured on B200: no difference within run-to-run noise (1351 vs 1357 frames/s), so it stays off by default.
+// Programmatic dependent launch (prologue of kernel k+1 — barrier init, TMEM allocation, descriptor prefetch — overlaps the
+// tail of kernel k; no global memory is touched before griddepcontrol.wait).  Round 1, eager launches: no difference
+// within run-to-run noise (1351 vs 1357 frames/s), left off.  Round 2, with the network replayed from a CUDA graph (the
+// launch latency that used to hide the effect is gone): network segment 8.72 -> 8.69 and 8.77 -> 8.69 ms on one box, so it
+// is ON by default; VD_CONV_PDL=0 disables it.
 static const bool g_conv_pdl = [] {
   const char* e = getenv("VD_CONV_PDL");
-  return e && atoi(e) == 1;
+  return !(e && atoi(e) == 0);
 }();
+
 
 template <int BN, bool RES, int ROWB = 128, bool CHAIN = false>
 static int launch_conv(const vd_conv_plan* pl, cudaStream_t st) {
