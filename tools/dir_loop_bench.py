@@ -73,5 +73,54 @@ same = all(open(os.path.join(tmp, "device", f), "rb").read() == open(os.path.joi
 res["device_files_identical_to_host_files"] = bool(same)
 res["device_over_host"] = res["device"]["frames_per_s"] / res["host"]["frames_per_s"]
 res["device_over_reference_schedule"] = res["device"]["frames_per_s"] / res["reference_schedule"]["frames_per_s"]
+
+
+# ---- video stage: the same frames as a Motion-JPEG AVI ------------------------------------------
+def video_stage():
+    from vdesens_b200 import avi
+    video = os.path.join(tmp, "in.avi")
+    with avi.AviWriter(video, W, H, 60) as wr:
+        for f in sorted(os.listdir(src)):
+            wr.write(open(os.path.join(src, f), "rb").read())
+
+
+    def reference_video_chain(path, out_path):
+        """reference :597-646 restated around this repo's detector: video -> JPEG files (here a plain demux; the reference
+        transcodes through an ffmpeg subprocess) -> its loop schedule over the files -> JPEG files -> cv2.VideoWriter
+        (its `.avi` codec list, XVID first) re-encoding every file"""
+        d_in, d_out = os.path.join(tmp, "v_frames"), os.path.join(tmp, "v_processed")
+        n = cd.convert_video_to_frames(path, d_in)
+        reference_schedule(d_in, d_out)
+        files = sorted(os.listdir(d_out))
+        wr, _ = cd._open_cv2_writer(out_path, 60, W, H)
+        for f in files:
+            wr.write(cv2.imread(os.path.join(d_out, f)))
+        wr.release()
+        return n
+
+
+    cd.process_video_pipeline(video, os.path.join(tmp, "warm.avi"), det, None, batch_size=B, mode="gauss", ksize=31)
+    vres = {}
+    for name, fn in (("resident", lambda o: cd.process_video_pipeline(video, o, det, None, batch_size=B, mode="gauss", ksize=31)[1]),
+                     ("reference_chain", lambda o: reference_video_chain(video, o))):
+        out = os.path.join(tmp, name + ".avi")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = fn(out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        vres[name] = {"frames_per_s": n / dt, "seconds": dt, "output_MB": os.path.getsize(out) / 1e6}
+    with avi.AviReader(os.path.join(tmp, "resident.avi")) as rd:
+        names = sorted(os.listdir(os.path.join(tmp, "device")))
+        vres["frames_identical_to_directory_loop_files"] = bool(
+            len(rd) == len(names) and all(rd.frame(i) == open(os.path.join(tmp, "device", f), "rb").read() for i, f in enumerate(names)))
+    vres["resident_over_reference_chain"] = vres["resident"]["frames_per_s"] / vres["reference_chain"]["frames_per_s"]
+    res["video"] = vres
+
+
+try:
+    video_stage()
+except Exception as e:                        # noqa: BLE001: keep the directory numbers
+    res["video"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 print(json.dumps(res))
 shutil.rmtree(tmp, ignore_errors=True)
