@@ -139,7 +139,11 @@ def composite(img, boxes, mode="mosaic", mosaic_level=8, ksize=31, sigma=0.0):
 # INTER_LINEAR uint8 (cv2.resize, down-scale / identity) and the reference letterbox
 # (detect_face/utils/utils.py:8-18)
 # ----------------------------------------------------------------------------------------------
-def _linear_coeffs(dst_n, src_n):
+def _linear_coeffs(dst_n, src_n, clamp=True):
+    """cv2 resize.cpp coefficient tables.  Along x (clamp=True) a tap that starts left of the row or on its last pixel is
+    replaced by that pixel with weight 1; along y (clamp=False) the weights are KEPT and the two row indices are clipped
+    instead — when up-scaling, the first / last output rows therefore blend the border row with itself, and the two
+    separately truncated products can come out one below the single full-weight product."""
     scale = np.float64(src_n) / np.float64(dst_n)
     idx = np.zeros(dst_n, np.int64)
     a0 = np.zeros(dst_n, np.int64)
@@ -148,10 +152,11 @@ def _linear_coeffs(dst_n, src_n):
         fx = np.float32((d + 0.5) * scale - 0.5)
         sx = int(math.floor(fx))
         fx = np.float32(fx - sx)
-        if sx < 0:
-            fx, sx = np.float32(0), 0
-        if sx >= src_n - 1:
-            fx, sx = np.float32(0), src_n - 1
+        if clamp:
+            if sx < 0:
+                fx, sx = np.float32(0), 0
+            if sx >= src_n - 1:
+                fx, sx = np.float32(0), src_n - 1
         idx[d] = sx
         # cv: saturate_cast<short>(v * INTER_RESIZE_COEF_SCALE) with cvRound (half-to-even)
         a0[d] = int(np.rint(np.float32(np.float32(1.0) - fx) * np.float32(2048)))
@@ -160,17 +165,20 @@ def _linear_coeffs(dst_n, src_n):
 
 
 def resize_linear_u8(img, dst_w, dst_h):
-    """== cv2.resize(img, (dst_w,dst_h)) for uint8 HxWx3 when not up-scaling."""
+    """== cv2.resize(img, (dst_w,dst_h)) (INTER_LINEAR) for uint8 HxWx3, down- and up-scaling.  An exact 2x reduction in
+    both directions is what OpenCV turns into its fast INTER_AREA path ((a+b+c+d+2)>>2), which the bilinear arithmetic
+    below reproduces bit for bit (both taps 1024: no truncation loss)."""
     h, w = img.shape[:2]
     if (dst_w, dst_h) == (w, h):
         return img.copy()
     xi, xa0, xa1 = _linear_coeffs(dst_w, w)
-    yi, ya0, ya1 = _linear_coeffs(dst_h, h)
+    yi, ya0, ya1 = _linear_coeffs(dst_h, h, clamp=False)
     s = img.astype(np.int64)
     x1 = np.minimum(xi + 1, w - 1)
     rows = s[:, xi, :] * xa0[None, :, None] + s[:, x1, :] * xa1[None, :, None]     # (h,dst_w,3), x2048
-    y1 = np.minimum(yi + 1, h - 1)
-    r0, r1 = rows[yi], rows[y1]
+    y0 = np.clip(yi, 0, h - 1)
+    y1 = np.clip(yi + 1, 0, h - 1)
+    r0, r1 = rows[y0], rows[y1]
     b0, b1 = ya0[:, None, None], ya1[:, None, None]
     out = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8)

@@ -39,6 +39,9 @@ def _dev_frames(frames):
     ([(480, 640)], (640, 640)),                     # C1: pure pad
     ([(135, 241)], (135, 241)),                     # odd width (tail path), identity
     ([(270, 480), (300, 300)], (160, 224)),
+    ([(96, 128)], (256, 256)),                      # up-scale 2x (cv2 clips the ROW indices at the borders, keeps the weights)
+    ([(60, 100), (100, 60), (33, 47)], (160, 224)), # up-scale by non-integer factors, mixed sizes
+    ([(480, 640)], (1280, 1280)),                   # VGA frames into the reference's default input_shape
 ])
 def test_ingest_exact(ops, case):
     sizes, (H, W) = case

@@ -103,6 +103,16 @@ def test_cv_live_against_this_image():
         ref = cv2.resize(a, (dst, dst), interpolation=cv2.INTER_NEAREST)
         m = co.nearest_map(dst, src)
         assert np.array_equal(a[m][:, m], ref)
+    # INTER_LINEAR (the letterbox's resize, utils.py:12): down-scaling, the exact 2x reduction OpenCV hands to its fast
+    # area path, and UP-scaling, where the first / last output rows blend the border row with itself (VERDICT r1 row a3:
+    # "up-scale still unpinned" — the y axis keeps its weights and clips the row indices, the x axis clamps the weights)
+    for (h, w), (dh, dw) in [((40, 60), (20, 30)), ((40, 60), (80, 120)), ((40, 60), (57, 83)), ((33, 47), (66, 94)),
+                             ((45, 77), (90, 100)), ((30, 30), (31, 31)), ((64, 64), (16, 16)), ((48, 64), (128, 171)),
+                             ((7, 9), (50, 64)), ((1, 1), (5, 5)), ((2, 3), (7, 9)), ((37, 91), (36, 200)),
+                             ((91, 37), (200, 36)), ((480, 640), (960, 1280))]:
+        a = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        assert np.array_equal(co.resize_linear_u8(a, dw, dh), cv2.resize(a, (dw, dh), interpolation=cv2.INTER_LINEAR)), \
+            ((h, w), (dh, dw))
 
 
 def test_oracle_on_default_init_weights_matches_the_executed_reference(golden_dir):

@@ -60,6 +60,7 @@ def test_mosaic_random_boxes(ref):
 
 def test_letterbox(ref):
     face, _ = ref
-    for ih, iw, W, H in [(480, 640, 640, 640), (1080, 1920, 640, 640), (270, 480, 480, 270), (333, 517, 320, 256)]:
+    for ih, iw, W, H in [(480, 640, 640, 640), (1080, 1920, 640, 640), (270, 480, 480, 270), (333, 517, 320, 256),
+                         (480, 640, 1280, 1280), (120, 160, 320, 256), (200, 100, 256, 300)]:      # the last three up-scale
         img = synth.synthetic_frame(ih, iw, ih + iw)
         assert np.array_equal(face.letterbox_image(img, [W, H]), co.letterbox(img, W, H).astype(np.float64))

@@ -7,8 +7,13 @@ plus what BASELINE.json's north_star adds:
   composite_frames(...)                   batched sequential compositing on the device
   batch_process_frames(...)               the frame loop on in-memory frames (no JPEG hand-off)
 
-Everything outside the per-frame arithmetic (record unpacking, ffmpeg extraction, muxing, config,
-logging: reference :21-89, :279-990) is out of scope.
+and the video stage either side of it, same signatures and return values as the reference:
+  process_video_pipeline(input, output, face_detector, plate_detector, temp_dir, fps, batch_size)   :597-646
+  process_single_video(...) :648-699, convert_video_to_frames(...) :279-476, create_video(...) :479-595
+  Motion-JPEG AVI runs demux -> device decode -> detect + composite -> device encode -> mux with the frames resident in
+  HBM (vdesens_b200/avi.py + vdesens_b200/jpeg.py); other codecs go through OpenCV's libavcodec at that end.
+
+Record unpacking, config, logging and the CLI (reference :21-89, :701-990) are out of scope.
 """
 import os
 import queue

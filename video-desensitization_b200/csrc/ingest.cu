@@ -31,12 +31,20 @@ __device__ __forceinline__ LetterGeom letter_geom(int ih, int iw, int H, int W) 
   return g;
 }
 
+// cv2 resize.cpp treats the two axes differently at the borders (only reachable when UP-scaling): along x a tap pair
+// that starts left of the row, or on its last pixel, becomes that pixel with weight 1 (CLAMP = true); along y the weights
+// are kept and the two ROW INDICES are clipped — the first / last output rows blend the border row with itself, and the
+// two separately truncated products can come out one below the full-weight product.  lin_coeff returns the unclipped s0
+// for CLAMP = false; the caller clips s0 and s0 + 1 into [0, n-1].
+template <bool CLAMP>
 __device__ __forceinline__ void lin_coeff(int d, double scale, int n, int& s0, int& a0, int& a1) {
   float f = static_cast<float>((d + 0.5) * scale - 0.5);
   int s = static_cast<int>(floorf(f));
   f -= s;
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= n - 1) { f = 0.f; s = n - 1; }
+  if (CLAMP) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n - 1) { f = 0.f; s = n - 1; }
+  }
   s0 = s;
   a0 = __float2int_rn((1.f - f) * 2048.f);   // cvRound: half to even
   a1 = __float2int_rn(f * 2048.f);
@@ -54,10 +62,11 @@ __device__ __forceinline__ void letter_pixel(const vd_frame_t& fr, const LetterG
     v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
     return;
   }
-  int x0, xa0, xa1, y0, yb0, yb1;
-  lin_coeff(xx, g.sx, fr.w, x0, xa0, xa1);
-  lin_coeff(yy, g.sy, fr.h, y0, yb0, yb1);
-  const int x1 = min(x0 + 1, fr.w - 1), y1 = min(y0 + 1, fr.h - 1);
+  int x0, xa0, xa1, ys, yb0, yb1;
+  lin_coeff<true>(xx, g.sx, fr.w, x0, xa0, xa1);
+  lin_coeff<false>(yy, g.sy, fr.h, ys, yb0, yb1);
+  const int x1 = min(x0 + 1, fr.w - 1);
+  const int y0 = min(max(ys, 0), fr.h - 1), y1 = min(max(ys + 1, 0), fr.h - 1);
   const uint8_t* r0 = fr.ptr + static_cast<size_t>(y0) * fr.pitch;
   const uint8_t* r1 = fr.ptr + static_cast<size_t>(y1) * fr.pitch;
 #pragma unroll
@@ -105,9 +114,9 @@ ingest_x0_rows_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__
     }
     return;
   }
-  int y0 = yy, yb0 = 2048, yb1 = 0;
-  if (!same) lin_coeff(yy, g.sy, fr.h, y0, yb0, yb1);
-  const int y1 = min(y0 + 1, fr.h - 1);
+  int ys = yy, yb0 = 2048, yb1 = 0;
+  if (!same) lin_coeff<false>(yy, g.sy, fr.h, ys, yb0, yb1);
+  const int y0 = min(max(ys, 0), fr.h - 1), y1 = min(max(ys + 1, 0), fr.h - 1);
   // ---- stage source rows y0 and y1: s_rows[r][phase_r + i] = byte i of the row ----
   const uint8_t* fr_end = fr.ptr + static_cast<size_t>(fr.h - 1) * fr.pitch + nbytes;
   const uint8_t* src[2] = {fr.ptr + static_cast<size_t>(y0) * fr.pitch, fr.ptr + static_cast<size_t>(y1) * fr.pitch};
@@ -155,7 +164,7 @@ ingest_x0_rows_kernel(const vd_frame_t* __restrict__ frames, uint2* __restrict__
         v[0] = r0[xx * 3]; v[1] = r0[xx * 3 + 1]; v[2] = r0[xx * 3 + 2];
       } else {
         int xs, xa0, xa1;
-        lin_coeff(xx, g.sx, fr.w, xs, xa0, xa1);
+        lin_coeff<true>(xx, g.sx, fr.w, xs, xa0, xa1);
         const int x1 = min(xs + 1, fr.w - 1);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

@@ -81,6 +81,12 @@ class DetectorEngine:
         self.launches_per_forward = 0
         self.use_graph = os.environ.get("VD_GRAPH", "1") != "0"   # replay the network's launches from a CUDA graph
         self._graph, self._graph_key, self._graph_key_seen, self._net_calls = None, None, None, 0
+        # VD_BRANCH=1: the SSH + head launches of pyramid levels 2 and 3 (few tiles each, latency-bound) run on two side
+        # streams next to the level-1 launches instead of behind them (fork / join by events; inside the CUDA graph these
+        # become parallel branches).  Same kernels, same arguments: results are bit-identical.
+        self.branch = os.environ.get("VD_BRANCH", "0") != "0" and backbone != "mobilenet"
+        self._deps = {}      # plan name -> (lane, input buffers, output buffers)
+        self._lanes = None
         with torch.cuda.device(self.device):
             sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
             self._check(self.lib.vd_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), "vd_device_info")
@@ -243,6 +249,9 @@ class DetectorEngine:
                 d.upadd = up.data_ptr() if up is not None else None
                 d.y = self.buf[op.dst].data_ptr()
                 self.plans.append(("conv", self._make_plan(d, c.name), c.name))
+                lane = 1 if c.name.startswith("ssh2") else 2 if c.name.startswith("ssh3") else 0
+                self._deps[c.name] = (lane, [b for b in (op.src, op.src2, op.residual, op.upsample_add) if b],
+                                      [b for b in (op.dst, op.chain_dst, op.sibling_dst) if b])
             elif op.kind == "maxpool":
                 self.plans.append(("maxpool", (op.src, op.dst), "maxpool"))
             elif op.kind == "heads":
@@ -261,6 +270,7 @@ class DetectorEngine:
                 d.x, d.w, d.bias = self.buf[op.src].data_ptr(), wt.data_ptr(), bt.data_ptr()
                 d.y = self.heads[op.level].data_ptr()
                 self.plans.append(("conv", self._make_plan(d, f"heads.{op.level}"), f"heads.{op.level}"))
+                self._deps[f"heads.{op.level}"] = (op.level, [op.src], [f"heads.out{op.level}"])
 
     def _build_post(self, scratch_frames):
         dev, B, H, W = self.device, self.B, self.H, self.W
@@ -423,8 +433,27 @@ class DetectorEngine:
 
     def _enqueue_network_eager(self, upto=None):
         s = C.c_void_p(self.stream.cuda_stream)
+        branch = self.branch and upto is None
+        if branch and self._lanes is None:
+            self._lanes = [self.stream, torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        writers, last = {}, {}                    # buffer -> [(lane, event)]; side lane -> its last event
         for kind, h, name in self.plans:
             if kind == "conv":
+                if branch and name in self._deps:
+                    lane, ins, outs = self._deps[name]
+                    st = self._lanes[lane]
+                    for b in ins:
+                        for wl, ev in writers.get(b, ()):
+                            if wl != lane:
+                                st.wait_event(ev)
+                    self._check(self.lib.vd_conv_run(h, C.c_void_p(st.cuda_stream)), f"vd_conv_run({name})")
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    for b in outs:
+                        writers.setdefault(b, []).append((lane, ev))
+                    if lane:
+                        last[lane] = ev
+                    continue
                 self._check(self.lib.vd_conv_run(h, s), f"vd_conv_run({name})")
             elif kind == "dwpw":
                 op = h
@@ -453,6 +482,8 @@ class DetectorEngine:
                 self._check(pool(_ptr(self.buf[src]), _ptr(self.buf[dst]), self.B, hh, ww, cc, s), "vd_maxpool3x3s2")
             if upto is not None and name == upto:
                 break
+        for ev in last.values():                  # join: decode / NMS follow on the engine stream
+            self.stream.wait_event(ev)
 
     @_on_device
     def enqueue_postprocess(self):

@@ -1,7 +1,12 @@
-"""Host half of the device-resident JPEG ingest: libvdesens' entropy decoder behind numpy arrays.
-`decode_coefficients(data)` returns the quantised DCT coefficients of a baseline JPEG as int16 planes; the device half
-(IDCT, up-sampling, colour conversion — bit-exact with the libjpeg-turbo behind cv2.imread, reference
-combine_detect.py:167-180) is not written yet, so nothing in the frame loop uses this module so far."""
+"""JPEG codec on the device (csrc/jpeg_dec.cu, csrc/jpeg_enc.cu, csrc/jpeg_host.cu behind the C-ABI).
+
+  JpegDecoder   file bytes -> resident RGB frames, pixels identical to cv2.imread + BGR->RGB (reference
+                combine_detect.py:167-173): host header parse, parallel self-synchronising Huffman decode, IDCT, fancy
+                up-sampling and colour conversion on the GPU; files the device path does not take fall back to cv2
+  JpegEncoder   resident RGB frames -> file bytes identical to cv2.imwrite's (reference :176-180)
+  read_header / decode_coefficients / reconstruct_from_coefficients   the host entropy decoder and the test hooks
+Used by combine_detect.batch_process_images(io="device") and by the video stage (process_video_pipeline, row N3), where
+the "files" are the chunks of a Motion-JPEG AVI (vdesens_b200/avi.py)."""
 import ctypes as C
 
 import numpy as np
