@@ -14,10 +14,13 @@
 //     window starts two input pixels after pixel i-1's), exactly as in conv_tcgen05.cu's stem path;
 //   * consecutive c1 rows share 5 of their 7 input rows: input rows travel through a ring of row PAIRS, each
 //     fetched once per unit by one TMA box, so the fabric carries ~4.3 KB per c1 row instead of 14 KB;
-//   * epilogue: TMEM -> +bias -> ReLU -> bf16 -> a 4-deep ring of c1 rows in shared memory; after every second
-//     row the 3x3/2 max over the last three rows is taken straight from shared memory and stored (32 B per
-//     thread, 1 KB contiguous per warp).  Positions outside c1 are written as 0, which is neutral for a max
-//     over ReLU outputs (PyTorch pads with -inf: every window holds at least one real value >= 0).
+//   * epilogue: TMEM -> +bias -> ReLU -> bf16.  An epilogue thread owns the SAME c1 column in every row, so the vertical
+//     half of the 3x3/2 max stays in registers (the packed values of the previous two rows); only after every second
+//     row the column-wise maximum of the last three rows goes to shared memory (two alternating 16 KB buffers), and
+//     the horizontal max over three columns is taken from there and stored (32 B per thread, 1 KB contiguous per
+//     warp): a third of the shared-memory reads and half of the writes of keeping every c1 row there (the first
+//     version; shared-memory bandwidth is what bounds this kernel).  Positions outside c1 count as 0, which is
+//     neutral for a max over ReLU outputs (PyTorch pads with -inf: every window holds at least one real value >= 0).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue + pool.
 #include <cuda.h>
@@ -37,7 +40,7 @@ constexpr int SP_PAIR_BYTES = 2 * SP_ROW_BYTES;  // 4352
 constexpr int SP_RING = 8;                       // input row pairs in flight
 constexpr int SP_W_BYTES = 7 * 64 * 64;          // resident weights: 7 filter rows x [64 cout][8 taps x 4 ch]
 constexpr int SP_C1_BYTES = 128 * 128;           // one c1 row of the strip: 128 pixels x 64 channels
-constexpr int SP_C1_RING = 4;
+constexpr int SP_C1_RING = 2;                    // column-max rows (one per pooled row), alternating
 constexpr int SP_A_BYTES = SP_RING * SP_PAIR_BYTES;                    // 34816
 constexpr int SP_SMEM = SP_A_BYTES + SP_W_BYTES + SP_C1_RING * SP_C1_BYTES + 1024 /*bias + barriers*/ + 1024;
 constexpr int SP_THREADS = 320;
@@ -50,7 +53,7 @@ struct StemPoolParams {
   uint4* y;                                      // [B][Hp][Wpo][64]
 };
 
-// c1 ring layout: 16-byte chunk c of strip pixel r lives at r*128 + ((c ^ c1_swz(r)) << 4), c1_swz = (r & 7) with
+// column-max row layout: 16-byte chunk c of strip pixel r lives at r*128 + ((c ^ c1_swz(r)) << 4), c1_swz = (r & 7) with
 // bits 0 and 1 swapped.  Writes (8 consecutive pixels, one chunk) hit 8 distinct 16-byte slots; pool reads (pixels
 // r and r+2, four channel groups x one chunk parity) do too, because r -> r+2 always flips bit 0 of c1_swz.
 __device__ __forceinline__ int c1_swz(int r) { return ((r >> 1) & 1) | ((r & 1) << 1) | (r & 4); }
@@ -184,6 +187,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ppx = etid >> 2;                        // pooled column inside the strip (pool phase, etid < 240)
     const int cg = etid & 3;                          // 16-channel group
     uint32_t rowctr = 0;
+    uint32_t vctr = 0;                                // pooled rows produced so far (selects the column-max buffer)
     float bias_r[32];                                 // this thread's 32 output channels
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias_r[j] = sBias[half * 32 + j];
@@ -199,6 +203,9 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool xvalid = (X >= 0) && (X < p.Wc);
       const int opx = SP_PCOLS * t + ppx;
       const bool pool_thread = (etid < 4 * SP_PCOLS) && (opx < p.Wpo);
+      uint4 he[4], ho[4];                             // this column's packed values of the last even / odd c1 row
+#pragma unroll
+      for (int j = 0; j < 4; ++j) he[j] = ho[j] = make_uint4(0u, 0u, 0u, 0u);
       for (int i = 0; i < nrows; ++i, ++rowctr) {
         const int Y = 2 * py0 - 1 + i;
         const bool valid = xvalid && (Y >= 0) && (Y < p.Hc);
@@ -211,7 +218,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);     // accumulator is free for the row after next
-        const uint32_t crow = sC_u32 + (rowctr & (SP_C1_RING - 1)) * SP_C1_BYTES + row * 128;
+        uint4 o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float f[8];
@@ -219,25 +226,38 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
 #pragma unroll
           for (int e = 0; e < 8; e += 2) fadd2(f[e], f[e + 1], bias_r[8 * j + e], bias_r[8 * j + e + 1]);   // ReLU: in the conversion
-          uint4 o;
-          o.x = pack_bf16x2_relu(f[0], f[1]);
-          o.y = pack_bf16x2_relu(f[2], f[3]);
-          o.z = pack_bf16x2_relu(f[4], f[5]);
-          o.w = pack_bf16x2_relu(f[6], f[7]);
-          if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-          sts128(crow + (((half * 4 + j) ^ c1_swz(row)) << 4), o);
+          o[j].x = pack_bf16x2_relu(f[0], f[1]);
+          o[j].y = pack_bf16x2_relu(f[2], f[3]);
+          o[j].z = pack_bf16x2_relu(f[4], f[5]);
+          o[j].w = pack_bf16x2_relu(f[6], f[7]);
+          if (!valid) o[j] = make_uint4(0u, 0u, 0u, 0u);
         }
-        named_bar_sync(1, 256);
-        if (i >= 2 && !(i & 1) && pool_thread) {
-          // pooled row py0 + i/2 - 1 = max over c1 rows i-2, i-1, i and strip columns 2*ppx + 7 .. + 9
-          uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;          // 0 is neutral: every value is >= 0
+        if (i & 1) {
 #pragma unroll
-          for (int dr = 0; dr < 3; ++dr) {
-            const uint32_t buf = sC_u32 + ((rowctr - 2 + dr) & (SP_C1_RING - 1)) * SP_C1_BYTES;
+          for (int j = 0; j < 4; ++j) ho[j] = o[j];
+          continue;
+        }
+        if (i >= 2) {
+          // column-wise max over c1 rows i-2, i-1, i -> shared memory; then pooled row py0 + i/2 - 1 = the max over
+          // strip columns 2*ppx + 7 .. + 9 of that row
+          const uint32_t vbuf = sC_u32 + (vctr & 1u) * SP_C1_BYTES;
+          const uint32_t crow = vbuf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 m;
+            m.x = act2_max(act2_max(o[j].x, ho[j].x), he[j].x);
+            m.y = act2_max(act2_max(o[j].y, ho[j].y), he[j].y);
+            m.z = act2_max(act2_max(o[j].z, ho[j].z), he[j].z);
+            m.w = act2_max(act2_max(o[j].w, ho[j].w), he[j].w);
+            sts128(crow + (((half * 4 + j) ^ c1_swz(row)) << 4), m);
+          }
+          named_bar_sync(1, 256);
+          if (pool_thread) {
+            uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;        // 0 is neutral: every value is >= 0
 #pragma unroll
             for (int dc = 0; dc < 3; ++dc) {
               const int lc = 2 * ppx + (SP_HALO - 1) + dc;
-              const uint32_t px = buf + lc * 128;
+              const uint32_t px = vbuf + lc * 128;
               const uint4 a0 = lds128(px + (((2 * cg) ^ c1_swz(lc)) << 4));
               const uint4 a1 = lds128(px + (((2 * cg + 1) ^ c1_swz(lc)) << 4));
               m0.x = act2_max(m0.x, a0.x); m0.y = act2_max(m0.y, a0.y);
@@ -245,12 +265,15 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               m1.x = act2_max(m1.x, a1.x); m1.y = act2_max(m1.y, a1.y);
               m1.z = act2_max(m1.z, a1.z); m1.w = act2_max(m1.w, a1.w);
             }
+            const int py = py0 + (i >> 1) - 1;
+            uint4* dst = p.y + ((static_cast<size_t>(b) * p.Hp + py) * p.Wpo + opx) * 8 + cg * 2;
+            dst[0] = m0;
+            dst[1] = m1;
           }
-          const int py = py0 + (i >> 1) - 1;
-          uint4* dst = p.y + ((static_cast<size_t>(b) * p.Hp + py) * p.Wpo + opx) * 8 + cg * 2;
-          dst[0] = m0;
-          dst[1] = m1;
+          ++vctr;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) he[j] = o[j];
       }
     }
   }
