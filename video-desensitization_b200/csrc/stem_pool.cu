@@ -14,6 +14,14 @@
 //     window starts two input pixels after pixel i-1's), exactly as in conv_tcgen05.cu's stem path;
 //   * consecutive c1 rows share 5 of their 7 input rows: input rows travel through a ring of row PAIRS, each
 //     fetched once per unit by one TMA box, so the fabric carries ~4.3 KB per c1 row instead of 14 KB;
+//   * TWO c1 rows per accumulator (a "group" = c1 rows 2k-1 and 2k of the unit).  What bounds this kernel is the
+//     shared-memory pipe (ncu: UTCHMMA issue stalled on MIO half of the time, the pool's LDS waiting behind it), and
+//     an N = 64 MMA re-reads 4 KB of A for 2 KB of B.  Input row t of a group (t = 0..8) feeds filter row t of the
+//     odd c1 row and filter row t-2 of the even one, so for t = 2..6 ONE MMA with B = [W_t ; W_{t-2}] (N = 128,
+//     accumulator columns 0..63 = odd row, 64..127 = even row) reads the A window once for both: 11 N = 128 + 7
+//     N = 64 MMAs per two rows instead of 28 N = 64 (operand fetch 520 instead of 672 clk per row).  Every row still
+//     accumulates its filter rows in the order 0..6, so results stay bit-identical; the even row's columns are
+//     zeroed by the group's first MMA, whose B is [W_0 ; 0];
 //   * epilogue: TMEM -> +bias -> ReLU -> bf16.  An epilogue thread owns the SAME c1 column in every row, so the vertical
 //     half of the 3x3/2 max stays in registers (the packed values of the previous two rows); only after every second
 //     row the column-wise maximum of the last three rows goes to shared memory (two alternating 16 KB buffers), and
@@ -38,13 +46,15 @@ constexpr int SP_CHUNKS = 17;                    // 2*128 + 6 = 262 input pixels
 constexpr int SP_ROW_BYTES = SP_CHUNKS * 128;    // 2176
 constexpr int SP_PAIR_BYTES = 2 * SP_ROW_BYTES;  // 4352
 constexpr int SP_RING = 8;                       // input row pairs in flight
-constexpr int SP_W_BYTES = 7 * 64 * 64;          // resident weights: 7 filter rows x [64 cout][8 taps x 4 ch]
+constexpr int SP_WBLK = 64 * 64;                 // one filter row: [64 cout][8 taps x 4 ch] = 4 KB
+// resident weights as six 8 KB row pairs: block 0 = [W_0 ; 0], block t-1 = [W_t ; W_{t-2}] for t = 2..6
+constexpr int SP_W_BYTES = 12 * SP_WBLK;
 constexpr int SP_C1_BYTES = 128 * 128;           // one c1 row of the strip: 128 pixels x 64 channels
 constexpr int SP_C1_RING = 2;                    // column-max rows (one per pooled row), alternating
 constexpr int SP_A_BYTES = SP_RING * SP_PAIR_BYTES;                    // 34816
 constexpr int SP_SMEM = SP_A_BYTES + SP_W_BYTES + SP_C1_RING * SP_C1_BYTES + 1024 /*bias + barriers*/ + 1024;
 constexpr int SP_THREADS = 320;
-constexpr int SP_TMEM_COLS = 128;                // two 64-column accumulators
+constexpr int SP_TMEM_COLS = 256;                // two accumulators of 2 c1 rows x 64 columns
 
 struct StemPoolParams {
   int B, Hin, Hc, Wc, Hp, Wpo;
@@ -78,6 +88,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x < 64) sBias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if (threadIdx.x < SP_WBLK / 16) sts128(smem_u32(sB) + SP_WBLK + threadIdx.x * 16, make_uint4(0u, 0u, 0u, 0u));
+  fence_proxy_async_smem();                           // the zero half of block 0 is read by the tensor core
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -107,8 +119,12 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(wfull, SP_W_BYTES);
-      for (int r = 0; r < 7; ++r) tma_load_2d(sB + r * 4096, &tmB, wfull, r * 32, 0);
+      mbar_expect_tx(wfull, 11 * SP_WBLK);
+      tma_load_2d(sB, &tmB, wfull, 0, 0);                                        // block 0 = [W_0 ; 0]
+      for (int t = 2; t < 7; ++t) {                                              // block t-1 = [W_t ; W_{t-2}]
+        tma_load_2d(sB + (t - 1) * 2 * SP_WBLK, &tmB, wfull, t * 32, 0);
+        tma_load_2d(sB + (t - 1) * 2 * SP_WBLK + SP_WBLK, &tmB, wfull, (t - 2) * 32, 0);
+      }
     }
     __syncwarp();
     uint32_t g = 0;                                   // running pair counter (ring position)
@@ -134,49 +150,81 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t kFmt = VD_ACT_IS_FP16 ? 0u : 1u;
-    constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(64 >> 3) << 17) |
-                               (static_cast<uint32_t>(128 >> 4) << 24);
+    constexpr uint32_t idesc64 = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(64 >> 3) << 17) |
+                                 (static_cast<uint32_t>(128 >> 4) << 24);
+    constexpr uint32_t idesc128 = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
+                                  (static_cast<uint32_t>(128 >> 4) << 24);
     constexpr uint32_t hi_raw = (128u >> 4) | (1u << 14);                       // SBO 128 B, no swizzle
     constexpr uint32_t hi_w = (512u >> 4) | (1u << 14) | (4u << 29);            // SBO 8 x 64 B, SWIZZLE_64B
+    constexpr uint32_t WB = SP_WBLK >> 4;                                       // one filter row in descriptor units
     const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);       // LBO 16 B
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
     mbar_wait(wfull, 0);
-    uint32_t g = 0;
-    uint32_t rowctr = 0;
+    uint32_t g = 0;                                   // ring position of the unit's first input row pair
+    uint32_t grp = 0;                                 // running group counter (accumulator buffer, phases)
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int seg = u % p.n_segs;
       const int py0 = seg * p.seg_rows;
       const int py1 = min(py0 + p.seg_rows, p.Hp);
-      const int nrows = 2 * (py1 - py0) + 1;
-      for (int k = 0; k < 3; ++k) mbar_wait(&full[(g + k) & (SP_RING - 1)], ((g + k) >> 3) & 1u);
-      for (int i = 0; i < nrows; ++i, ++rowctr) {
-        const uint32_t pn = g + i + 3;                // newest pair this c1 row needs
-        mbar_wait(&full[pn & (SP_RING - 1)], (pn >> 3) & 1u);
-        const uint32_t acc = rowctr & 1u;
-        mbar_wait(&tempty[acc], ((rowctr >> 1) & 1u) ^ 1u);
+      const int ngroups = (py1 - py0) + 1;            // group k = c1 rows 2k-1 and 2k; group 0 has the even row only
+      for (int k = 0; k < 4; ++k) mbar_wait(&full[(g + k) & (SP_RING - 1)], ((g + k) >> 3) & 1u);
+      for (int k = 0; k < ngroups; ++k, ++grp) {
+        // input row t of the group (t = 0..8) lives in pair P0 + ((t + 1) >> 1), sub-row (t + 1) & 1; P0 = 2k - 1
+        const uint32_t P0 = g + static_cast<uint32_t>(2 * k) - 1u;
+        if (k > 0) {
+          mbar_wait(&full[(P0 + 3) & (SP_RING - 1)], ((P0 + 3) >> 3) & 1u);
+          mbar_wait(&full[(P0 + 4) & (SP_RING - 1)], ((P0 + 4) >> 3) & 1u);
+        }
+        const uint32_t acc = grp & 1u;
+        mbar_wait(&tempty[acc], ((grp >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + acc * 64u;
+          const uint32_t d_lo = tmem_base + acc * 128u;           // odd row: columns 0..63, even row: 64..127
+          const uint32_t d_hi = d_lo + 64u;
 #pragma unroll
-          for (int r = 0; r < 7; ++r) {
-            // filter row r reads input row 4*py0 - 5 + 2i + r = pair i + (r+1)/2, sub-row (r+1)&1
-            const uint32_t slot = (g + i + ((r + 1) >> 1)) & (SP_RING - 1);
-            const uint32_t al = a_lo0 + ((slot * SP_PAIR_BYTES + ((r + 1) & 1) * SP_ROW_BYTES) >> 4);
-            const uint32_t bl = b_lo0 + static_cast<uint32_t>(r * (4096 >> 4));
-            umma_bf16_words(d_tmem, al, hi_raw, bl, hi_w, idesc, static_cast<uint32_t>(r != 0));
-            umma_bf16_words(d_tmem, al + 2, hi_raw, bl + 2, hi_w, idesc, 1u);
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t slot = (P0 + ((t + 1) >> 1)) & (SP_RING - 1);
+            const uint32_t al = a_lo0 + ((slot * SP_PAIR_BYTES + ((t + 1) & 1) * SP_ROW_BYTES) >> 4);
+            if (k == 0) {
+              // the even row alone: filter row t - 2 (W_0 = block 0, W_1 = upper half of block 2, W_r = block r-1)
+              if (t < 2) continue;
+              const int r = t - 2;
+              const uint32_t bl = b_lo0 + (r == 0 ? 0u : r == 1 ? 5u * WB : static_cast<uint32_t>(2 * (r - 1)) * WB);
+              umma_bf16_words(d_hi, al, hi_raw, bl, hi_w, idesc64, static_cast<uint32_t>(r != 0));
+              umma_bf16_words(d_hi, al + 2, hi_raw, bl + 2, hi_w, idesc64, 1u);
+            } else if (t == 0) {
+              umma_bf16_words(d_lo, al, hi_raw, b_lo0, hi_w, idesc128, 0u);      // [W_0 ; 0]: zeroes the even row
+              umma_bf16_words(d_lo, al + 2, hi_raw, b_lo0 + 2, hi_w, idesc64, 1u);
+            } else if (t == 1) {
+              umma_bf16_words(d_lo, al, hi_raw, b_lo0 + 5u * WB, hi_w, idesc64, 1u);
+              umma_bf16_words(d_lo, al + 2, hi_raw, b_lo0 + 5u * WB + 2, hi_w, idesc64, 1u);
+            } else if (t < 7) {
+              const uint32_t bl = b_lo0 + static_cast<uint32_t>(2 * (t - 1)) * WB;     // [W_t ; W_{t-2}]
+              umma_bf16_words(d_lo, al, hi_raw, bl, hi_w, idesc128, 1u);
+              umma_bf16_words(d_lo, al + 2, hi_raw, bl + 2, hi_w, idesc128, 1u);
+            } else {
+              const uint32_t bl = b_lo0 + static_cast<uint32_t>(2 * (t - 3)) * WB;     // W_{t-2} = lower half of block t-3
+              umma_bf16_words(d_hi, al, hi_raw, bl, hi_w, idesc64, 1u);
+              umma_bf16_words(d_hi, al + 2, hi_raw, bl + 2, hi_w, idesc64, 1u);
+            }
           }
-          umma_commit(&empty[(g + i) & (SP_RING - 1)]);            // oldest pair is not needed again
-          if (i == nrows - 1) {                                     // end of the unit: release its last pairs
-            umma_commit(&empty[(g + i + 1) & (SP_RING - 1)]);
-            umma_commit(&empty[(g + i + 2) & (SP_RING - 1)]);
-            umma_commit(&empty[(g + i + 3) & (SP_RING - 1)]);
+          // input pairs no later group needs: group 0 -> pair 0; group k -> pairs 2k-1 and 2k
+          if (k == 0) {
+            umma_commit(&empty[g & (SP_RING - 1)]);
+          } else {
+            umma_commit(&empty[P0 & (SP_RING - 1)]);
+            umma_commit(&empty[(P0 + 1) & (SP_RING - 1)]);
+          }
+          if (k == ngroups - 1) {                                  // end of the unit: release its last three pairs
+            umma_commit(&empty[(P0 + 2) & (SP_RING - 1)]);
+            umma_commit(&empty[(P0 + 3) & (SP_RING - 1)]);
+            umma_commit(&empty[(P0 + 4) & (SP_RING - 1)]);
           }
           umma_commit(&tfull[acc]);
         }
         __syncwarp();
       }
-      g += static_cast<uint32_t>(nrows + 3);
+      g += static_cast<uint32_t>(2 * ngroups + 2);     // = c1 rows + 3 pairs
     }
   } else {
     // ===================== epilogue + pool (warps 2..9) =====================
@@ -186,7 +234,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int etid = threadIdx.x - 64;
     const int ppx = etid >> 2;                        // pooled column inside the strip (pool phase, etid < 240)
     const int cg = etid & 3;                          // 16-channel group
-    uint32_t rowctr = 0;
+    uint32_t grp = 0;                                 // running group counter (accumulator buffer, phases)
     uint32_t vctr = 0;                                // pooled rows produced so far (selects the column-max buffer)
     float bias_r[32];                                 // this thread's 32 output channels
 #pragma unroll
@@ -198,47 +246,53 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int b = u / (p.n_segs * p.n_strips);
       const int py0 = seg * p.seg_rows;
       const int py1 = min(py0 + p.seg_rows, p.Hp);
-      const int nrows = 2 * (py1 - py0) + 1;
       const int X = SP_STRIP * t - SP_HALO + row;
       const bool xvalid = (X >= 0) && (X < p.Wc);
       const int opx = SP_PCOLS * t + ppx;
       const bool pool_thread = (etid < 4 * SP_PCOLS) && (opx < p.Wpo);
+      const int ngroups = (py1 - py0) + 1;
       uint4 he[4], ho[4];                             // this column's packed values of the last even / odd c1 row
 #pragma unroll
       for (int j = 0; j < 4; ++j) he[j] = ho[j] = make_uint4(0u, 0u, 0u, 0u);
-      for (int i = 0; i < nrows; ++i, ++rowctr) {
-        const int Y = 2 * py0 - 1 + i;
-        const bool valid = xvalid && (Y >= 0) && (Y < p.Hc);
-        const uint32_t acc = rowctr & 1u;
-        mbar_wait(&tfull[acc], (rowctr >> 1) & 1u);
+      for (int k = 0; k < ngroups; ++k, ++grp) {
+        const uint32_t acc = grp & 1u;
+        mbar_wait(&tfull[acc], (grp >> 1) & 1u);
         tcgen05_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64u + static_cast<uint32_t>(half * 32), v);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);     // accumulator is free for the row after next
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128u + static_cast<uint32_t>(half * 32);
         uint4 o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float f[8];
+        for (int h = 0; h < 2; ++h) {                 // h = 0: odd c1 row 2k-1 (not in group 0), h = 1: even row 2k
+          if (h == 0 && k == 0) continue;
+          const int Y = 2 * py0 - 1 + 2 * k - 1 + h;
+          const bool valid = xvalid && (Y >= 0) && (Y < p.Hc);
+          uint32_t v[32];
+          tmem_ld_32x32(tcol + static_cast<uint32_t>(h * 64), v);
+          tmem_ld_wait();
+          if (h == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]); // accumulator is free for the group after next
+          }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) fadd2(f[e], f[e + 1], bias_r[8 * j + e], bias_r[8 * j + e + 1]);   // ReLU: in the conversion
-          o[j].x = pack_bf16x2_relu(f[0], f[1]);
-          o[j].y = pack_bf16x2_relu(f[2], f[3]);
-          o[j].z = pack_bf16x2_relu(f[4], f[5]);
-          o[j].w = pack_bf16x2_relu(f[6], f[7]);
-          if (!valid) o[j] = make_uint4(0u, 0u, 0u, 0u);
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) fadd2(f[e], f[e + 1], bias_r[8 * j + e], bias_r[8 * j + e + 1]);   // ReLU: in the conversion
+            o[j].x = pack_bf16x2_relu(f[0], f[1]);
+            o[j].y = pack_bf16x2_relu(f[2], f[3]);
+            o[j].z = pack_bf16x2_relu(f[4], f[5]);
+            o[j].w = pack_bf16x2_relu(f[6], f[7]);
+            if (!valid) o[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ho[j] = o[j];
+          }
         }
-        if (i & 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ho[j] = o[j];
-          continue;
-        }
-        if (i >= 2) {
-          // column-wise max over c1 rows i-2, i-1, i -> shared memory; then pooled row py0 + i/2 - 1 = the max over
+        if (k > 0) {
+          // column-wise max over c1 rows 2k-2, 2k-1, 2k -> shared memory; then pooled row py0 + k - 1 = the max over
           // strip columns 2*ppx + 7 .. + 9 of that row
           const uint32_t vbuf = sC_u32 + (vctr & 1u) * SP_C1_BYTES;
           const uint32_t crow = vbuf + row * 128;
@@ -265,7 +319,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               m1.x = act2_max(m1.x, a1.x); m1.y = act2_max(m1.y, a1.y);
               m1.z = act2_max(m1.z, a1.z); m1.w = act2_max(m1.w, a1.w);
             }
-            const int py = py0 + (i >> 1) - 1;
+            const int py = py0 + k - 1;
             uint4* dst = p.y + ((static_cast<size_t>(b) * p.Hp + py) * p.Wpo + opx) * 8 + cg * 2;
             dst[0] = m0;
             dst[1] = m1;
