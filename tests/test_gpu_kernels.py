@@ -1332,3 +1332,35 @@ def test_conditioned_weights_1080p_fp16_every_anchor_iou_099(sd_np):
     assert len(strong_w) > 100
     assert all(_iou(r[:4], got[:, :4]).max(initial=0) >= 0.99 for r in strong_w)
     assert all(_iou(r[:4], want[:, :4]).max(initial=0) >= 0.99 for r in strong_g)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2r: 3x3 64 -> 64 convolution with two output rows per accumulator (csrc/conv3x3_rows.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(1, 68, 120), (2, 67, 120), (1, 33, 240), (2, 270, 480), (3, 2, 125), (1, 1, 128),
+                                   (16, 135, 240), (5, 9, 113)], ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_rows_is_bit_identical_to_the_generic_kernel(ops, shape, dt, monkeypatch):
+    """layer1's conv2 / SSH's conv7x7_3 (3x3, stride 1, 64 -> 64) through the row-pair kernel (two output rows share one
+    N = 128 MMA per tap where their filter rows overlap) against the generic halo-patch kernel on the same operands: same
+    accumulation order per output row, so every bit must agree — even / odd heights, one to four 128-column strips, a
+    partial last strip, more CTAs than work, ReLU on and off, a channel slice of a wider destination — and against
+    F.conv2d within the activation type's rounding"""
+    B, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H * 7 + W)
+    x = torch.randn((B, H, W, 64), generator=g).to(dt).to(DEV)
+    w = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(dt).to(DEV)
+    bias = torch.randn((64,), generator=g).to(DEV)
+    wp = w.permute(0, 2, 3, 1).reshape(64, -1).contiguous()
+    outs = {}
+    for rows in ("0", "1"):
+        monkeypatch.setenv("VD_CONV_ROWS", rows)
+        dense = ops.conv2d(x, wp, bias, 3, 1, 1, relu=True)
+        wide = torch.full((B, H, W, 256), 3.0, dtype=dt, device=DEV)
+        ops.conv2d(x, wp, bias, 3, 1, 1, relu=False, out=wide, dst_coff=192)
+        torch.cuda.synchronize()
+        outs[rows] = (dense, wide)
+    assert torch.equal(outs["0"][0], outs["1"][0])
+    assert torch.equal(outs["0"][1], outs["1"][1]) and bool((outs["1"][1][..., :192] == 3).all())
+    want = _ref_conv(x, w, bias, 1, 1, True, None, None)
+    assert torch.allclose(outs["1"][0].float(), want, atol=2.0 ** -6, rtol=2.0 ** -7)

@@ -921,6 +921,7 @@ void* vd_tensor_map_encoder() { return reinterpret_cast<void*>(get_encode_fn());
 
 struct vd_conv_plan {
   vd_stem_pool_plan* fused = nullptr;      // VD_CONV_POOL: the plan lives in stem_pool.cu
+  vd_conv_rows_plan* rows = nullptr;       // 3x3 64 -> 64: the plan lives in conv3x3_rows.cu
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmY;
@@ -1147,6 +1148,20 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
   vd_conv_plan* pl = new (std::nothrow) vd_conv_plan();
   VD_REQUIRE(pl, "out of host memory");
   pl->desc = *d;
+  if (vd_conv_rows_eligible(d)) {           // 3x3 64 -> 64: two output rows per accumulator (conv3x3_rows.cu)
+    memset(&pl->kp, 0, sizeof(pl->kp));
+    pl->kp.flags = d->flags;
+    pl->BN = 128;
+    const int rc = vd_conv_rows_create(d, &pl->rows);
+    if (rc != VD_OK) {
+      delete pl;
+      return rc;
+    }
+    vd_conv_rows_info(pl->rows, &pl->kp.num_tiles, &pl->grid);
+    pl->kp.TW = 128; pl->kp.TH = 2; pl->kp.NB = 1;
+    *out = pl;
+    return VD_OK;
+  }
   ConvKParams& k = pl->kp;
   memset(&k, 0, sizeof(k));
   int BN = d->Cout >= 256 ? 256 : d->Cout;
@@ -1467,6 +1482,7 @@ extern "C" int vd_conv_plan_create(const vd_conv_desc_t* d, vd_conv_plan_t** out
 
 extern "C" int vd_conv_plan_destroy(vd_conv_plan_t* plan) {
   if (plan && plan->fused) vd_stem_pool_destroy(plan->fused);
+  if (plan && plan->rows) vd_conv_rows_destroy(plan->rows);
   delete plan;
   return VD_OK;
 }
@@ -1519,6 +1535,7 @@ extern "C" int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream) {
   VD_REQUIRE(plan, "vd_conv_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (plan->fused) return vd_stem_pool_run(plan->fused, st);
+  if (plan->rows) return vd_conv_rows_run(plan->rows, st);
   const bool res = (plan->kp.flags & VD_CONV_RESIDUAL) != 0;
   if (plan->kp.flags & VD_CONV_IN_X0) return launch_conv<64, false, 64>(plan, st);
   if (plan->kp.flags & VD_CONV_CHAIN)
