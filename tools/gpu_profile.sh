@@ -8,9 +8,9 @@ $CMD > gpurun_out/prof_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k 'regex:conv_igemm|stem_pool' -s $((3 * NCONV)) -c $NCONV --csv --log-file gpurun_out/conv_step.csv $CMD > gpurun_out/ncu_convstep.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k 'regex:conv_igemm|stem_pool|conv3x3_rows' -s $((3 * NCONV)) -c $NCONV --csv --log-file gpurun_out/conv_step.csv $CMD > gpurun_out/ncu_convstep.log 2>&1
 echo "conv step exit $?"
 $CMD > gpurun_out/prof_plain3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:conv_igemm|stem_pool' -s $((3 * NCONV)) -c 24 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:conv_igemm|stem_pool|conv3x3_rows' -s $((3 * NCONV)) -c 24 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
 ls -la gpurun_out | tail -12

@@ -5,5 +5,5 @@ mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3"
 NCONV=${NCONV:-69}
 $CMD > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k 'regex:conv_igemm|stem_pool' -s $((3 * NCONV)) -c $NCONV --csv --log-file gpurun_out/conv_step.csv $CMD > gpurun_out/ncu_convstep.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k 'regex:conv_igemm|stem_pool|conv3x3_rows' -s $((3 * NCONV)) -c $NCONV --csv --log-file gpurun_out/conv_step.csv $CMD > gpurun_out/ncu_convstep.log 2>&1
 echo "conv step exit $?"

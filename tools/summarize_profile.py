@@ -44,10 +44,10 @@ out.append("Per-launch times are cold-cache and serialised: compare SHARES with 
 out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / tot:.1f} % |")
-conv = sum(t for k, (n, t) in agg.items() if "conv_igemm" in k or "stem_pool" in k or "maxpool" in k)
+conv = sum(t for k, (n, t) in agg.items() if "conv_igemm" in k or "stem_pool" in k or "conv3x3_rows" in k or "maxpool" in k)
 # warm-up + timed + end-to-end steps all run the same kernels, so shares over the whole list are shares of a step
 comp = sum(t for k, (n, t) in agg.items() if "composite" in k)
-out.append(f"\nconvolution (conv_igemm + stem_pool) share: {100 * conv / tot:.1f} %; compositing share: {100 * comp / tot:.1f} %.")
+out.append(f"\nconvolution (conv_igemm + stem_pool + conv3x3_rows) share: {100 * conv / tot:.1f} %; compositing share: {100 * comp / tot:.1f} %.")
 out.append(f"Raw list: `profiles/{tag}_launches_bench_steps2.csv`.\n")
 with open(os.path.join(P, f"{tag}_launches_bench_steps2.csv"), "w") as f:
     f.write("id,kernel,grid,block,us\n")
