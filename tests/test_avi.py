@@ -240,3 +240,45 @@ def test_video_pipeline_argument_checks(tmp_path):
         cd.process_video_pipeline("a.avi", "b.avi", None, None, on_error="ignore")
     assert cd.process_single_video(str(tmp_path / "noext"), str(tmp_path), None, None) is False
     assert cd.process_single_video(str(tmp_path / "missing.avi"), str(tmp_path), None, None) is False
+
+
+def test_abbreviated_mjpeg_frames_get_the_standard_huffman_tables(tmp_path):
+    """capture hardware and the Windows MJPG codec store frames WITHOUT a DHT segment (the T.81 Annex K tables are implied):
+    classic libjpeg refuses such a file, ffmpeg and newer libjpeg-turbo assume the tables.  AviReader splices them in, after which the frame is the
+    complete file libjpeg wrote (cv2 uses exactly these tables), decodes to the same pixels, and is what the device
+    decoder's host parser takes"""
+    import struct
+    from vdesens_b200 import jpeg as vjpeg
+
+    def strip_dht(blob):
+        out, pos = bytearray(blob[:2]), 2
+        while True:
+            m, L = blob[pos + 1], struct.unpack(">H", blob[pos + 2:pos + 4])[0]
+            if m == 0xDA:
+                return bytes(out) + blob[pos:]
+            if m != 0xC4:
+                out += blob[pos:pos + 2 + L]
+            pos += 2 + L
+
+    full = [_jpeg(f) for f in _frames(4, 96, 128, seed=90)]
+    short = [strip_dht(b) for b in full]
+    assert all(len(s) == len(b) - 4 * 4 - 416 for s, b in zip(short, full))          # four DHT segments gone
+    raw = cv2.imdecode(np.frombuffer(short[0], np.uint8), cv2.IMREAD_COLOR)    # classic libjpeg: "table not defined" (None);
+    assert raw is None or np.array_equal(raw[..., ::-1], _decode(full[0]))       # libjpeg-turbo >= 2.1 assumes Annex K too
+    with pytest.raises(RuntimeError):                                            # the device decoder's parser wants the tables
+        vjpeg.prepare_device(short[0])
+    fixed = avi.ensure_dht(short[0])
+    assert np.array_equal(_decode(fixed), _decode(full[0])) and len(fixed) == len(short[0]) + len(avi.STD_DHT)
+    assert avi.ensure_dht(full[0]) is full[0] and avi.ensure_dht(b"RIFF") == b"RIFF" and avi.ensure_dht(b"") == b""
+    assert avi.ensure_dht(b"\xff\xd8\xff\xd9") == b"\xff\xd8\xff\xd9"
+    hdr = vjpeg.prepare_device(fixed)
+    assert (hdr.width, hdr.height) == (128, 96)
+    path = tmp_path / "abbr.avi"
+    with avi.AviWriter(str(path), 128, 96, 30) as wr:
+        for b in short:
+            wr.write(b)
+    with avi.AviReader(str(path)) as rd:
+        got = list(rd)
+    assert all(np.array_equal(_decode(g), _decode(f)) for g, f in zip(got, full))
+    _, shown = _capture_all(path)                                   # ffmpeg plays the abbreviated stream as well
+    assert len(shown) == 4 and all(_closest(s, [_decode(f) for f in full]) == i for i, s in enumerate(shown))

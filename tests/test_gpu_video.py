@@ -166,3 +166,35 @@ def test_other_containers_go_through_opencv_at_either_end(tmp_path):
     # a file OpenCV cannot open: (False, 0, 0, 0) like the reference's failed extraction (:614-616)
     (tmp_path / "junk.mkv").write_bytes(b"not a video")
     assert combine_detect.process_video_pipeline(str(tmp_path / "junk.mkv"), str(tmp_path / "j.avi"), det, None) == (False, 0, 0, 0)
+
+
+def test_abbreviated_mjpeg_stream_is_decoded_on_the_device(tmp_path):
+    """frames without Huffman tables of their own (capture hardware, the Windows MJPG codec): AviReader splices the standard
+    tables in, the device decoder takes every frame (no host fallback), and the output equals the reference chain's"""
+    import struct
+    import combine_detect
+    from vdesens_b200.jpeg import JpegDecoder
+    H, W = 160, 224
+    det = _detector(H, W, 4)
+
+    def strip_dht(blob):
+        out, pos = bytearray(blob[:2]), 2
+        while True:
+            m, L = blob[pos + 1], struct.unpack(">H", blob[pos + 2:pos + 4])[0]
+            if m == 0xDA:
+                return bytes(out) + blob[pos:]
+            if m != 0xC4:
+                out += blob[pos:pos + 2 + L]
+            pos += 2 + L
+
+    full = [_jpeg(synth.synthetic_frame(H, W, 8800 + i)) for i in range(6)]
+    _write_avi(tmp_path / "abbr.avi", [strip_dht(b) for b in full], W, H)
+    with avi.AviReader(str(tmp_path / "abbr.avi")) as rd:
+        dec = JpegDecoder(4, device="cuda:0")
+        frames, on_cpu = dec.decode(rd.frames(range(4)))
+        assert on_cpu == [] and all(np.array_equal(frames[i].cpu().numpy(), _decode(full[i])) for i in range(4))
+    want, want_faces, _ = _expected(det, [_decode(b) for b in full], None, 4, mode="gauss", ksize=15)
+    assert combine_detect.process_video_pipeline(str(tmp_path / "abbr.avi"), str(tmp_path / "o.avi"), det, None, batch_size=4,
+                                                 mode="gauss", ksize=15) == (True, 6, want_faces, 0)
+    with avi.AviReader(str(tmp_path / "o.avi")) as rd:
+        assert list(rd) == want

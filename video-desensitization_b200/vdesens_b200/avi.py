@@ -24,8 +24,47 @@ _MASTER_ENTRIES = 256               # super-index slots reserved in the header (
 _MJPG_HANDLERS = (b"MJPG", b"mjpg", b"MJPA", b"mjpa", b"JPEG", b"jpeg", b"AVRn", b"AVDJ", b"dmb1", b"IJPG")
 
 
+# The four "typical" Huffman tables of ITU-T T.81 Annex K.3 as one DHT segment (DC / AC luminance, DC / AC chrominance):
+# what libjpeg writes when it does not optimise its tables, and what an ABBREVIATED Motion-JPEG frame (no DHT segment of
+# its own: capture hardware, the Windows MJPG codec, "AVI1" streams) implies.
+STD_DHT = bytes.fromhex(
+    "ffc401a20000010501010101010100000000000000000102030405060708090a0b100002010303020403050504040000017d0102030004110512"
+    "2131410613516107227114328191a1082342b1c11552d1f02433627282090a161718191a25262728292a3435363738393a434445464748494a53"
+    "5455565758595a636465666768696a737475767778797a838485868788898a92939495969798999aa2a3a4a5a6a7a8a9aab2b3b4b5b6b7b8b9ba"
+    "c2c3c4c5c6c7c8c9cad2d3d4d5d6d7d8d9dae1e2e3e4e5e6e7e8e9eaf1f2f3f4f5f6f7f8f9fa0100030101010101010101010000000000000102"
+    "030405060708090a0b1100020102040403040705040400010277000102031104052131061241510761711322328108144291a1b1c109233352f0"
+    "156272d10a162434e125f11718191a262728292a35363738393a434445464748494a535455565758595a636465666768696a737475767778797a"
+    "82838485868788898a92939495969798999aa2a3a4a5a6a7a8a9aab2b3b4b5b6b7b8b9bac2c3c4c5c6c7c8c9cad2d3d4d5d6d7d8d9dae2e3e4e5"
+    "e6e7e8e9eaf2f3f4f5f6f7f8f9fa")
+
+
 class AviError(ValueError):
     pass
+
+
+def ensure_dht(blob):
+    """A Motion-JPEG frame that carries no Huffman tables gets the standard ones spliced in before its scan, which makes
+    it a complete JPEG file for libjpeg and for the device decoder (ffmpeg's mjpeg decoder assumes the same tables; its
+    `mjpeg2jpeg` bitstream filter does this splice).  Frames that define tables — or are not JPEG — come back unchanged."""
+    n = len(blob)
+    if n < 4 or blob[0] != 0xFF or blob[1] != 0xD8:
+        return blob
+    pos = 2
+    while pos + 4 <= n:
+        if blob[pos] != 0xFF:
+            return blob                           # not a marker where one has to be: leave it to the decoder
+        m = blob[pos + 1]
+        if m == 0xFF:                             # fill byte
+            pos += 1
+        elif m == 0xC4:
+            return blob
+        elif m == 0xDA:
+            return blob[:pos] + STD_DHT + blob[pos:]
+        elif m == 0x01 or 0xD0 <= m <= 0xD8:      # markers without a length
+            pos += 2
+        else:
+            pos += 2 + ((blob[pos + 2] << 8) | blob[pos + 3])
+    return blob
 
 
 def _u32(buf, pos):
@@ -134,9 +173,11 @@ class AviReader:
         return len(self._frames)
 
     def frame(self, i):
-        """bytes of frame i (one complete JPEG file when is_mjpeg)"""
+        """bytes of frame i — one complete JPEG file when is_mjpeg (an abbreviated frame gets the standard Huffman
+        tables, `ensure_dht`)"""
         off, n = self._frames[i]
-        return self._m[off:off + n]
+        blob = self._m[off:off + n]
+        return ensure_dht(blob) if self.is_mjpeg else blob
 
     def frames(self, indices):
         return [self.frame(i) for i in indices]
