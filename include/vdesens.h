@@ -125,7 +125,8 @@ int vd_ingest_u8hwc_nchw_f32(const vd_frame_t* frames, int B, float* out, int H,
 #define VD_CONV_REVERSE 1024u   /* scheduling hint, no effect on results: the persistent CTAs walk the output tiles from the
                                   last to the first.  A layer that reads what its predecessor has JUST written finds the
                                   tail of that tensor still in the 126 MB L2 if it starts there; the executor alternates
-                                  the direction along the layer chain.  Ignored with VD_CONV_CHAIN / VD_CONV_POOL */
+                                  the direction along the layer chain.  Ignored with VD_CONV_CHAIN / VD_CONV_POOL and by the row-pair
+                                  kernel (3x3 64 -> 64 layers, see vd_conv_plan_create) */
 #define VD_CONV_TWO_DST 2048u  /* two sibling layers that read the same tensor run as ONE convolution over the concatenated
                                   filters (Cout = Cout1 + Cout2 in {128, 192}): output channels [0, Cout1) go to y
                                   (dst_C, dst_coff), channels [Cout1, Cout) to y_b (dst_b_C, dst_b_coff).  The SSH module's
@@ -171,7 +172,11 @@ typedef struct vd_conv_desc {
 
 typedef struct vd_conv_plan vd_conv_plan_t;
 
-/* Encodes the TMA tensor maps and picks the tiling; host-only work, no device access. */
+/* Encodes the TMA tensor maps and picks the kernel and its tiling; host-only work, no device access.  Besides the generic
+ * implicit-GEMM kernel there are two specialised ones behind the same three calls: the fused stem (VD_CONV_POOL) and, for
+ * 3x3 / stride 1 / pad 1 / Cin = Cout = 64 layers with no flag other than VD_CONV_RELU whose width fills its 128-column
+ * strips to >= 87 %, a kernel that computes two output rows per accumulator (plan_info reports TW = 128, TH = 2, BN = 128);
+ * its results are bit-identical to the generic kernel's, VD_CONV_ROWS=0 in the environment disables it. */
 int vd_conv_plan_create(const vd_conv_desc_t* desc, vd_conv_plan_t** plan);
 int vd_conv_plan_destroy(vd_conv_plan_t* plan);
 int vd_conv_run(const vd_conv_plan_t* plan, vd_stream_t stream);
