@@ -43,6 +43,9 @@ constexpr int CR_W_BYTES = 11 * CR_WBLK;
 constexpr int CR_A_BYTES = CR_RING * CR_ROW_BYTES;
 constexpr int CR_SMEM = CR_A_BYTES + CR_W_BYTES + 1024 /*bias + barriers*/ + 1024 /*alignment*/;
 constexpr int CR_THREADS = 320;
+#ifndef CR_QUAD_STORES
+#define CR_QUAD_STORES 0              // measured alternative for the epilogue's stores, see the epilogue
+#endif
 constexpr int CR_TMEM_COLS = 256;                 // two accumulators of 2 rows x 64 columns
 
 struct RowsParams {
@@ -269,12 +272,53 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o[j].w = pack_bf16x2(f[6], f[7]);
             }
           }
+          // What the epilogue's stores cost was measured with tools/probes/umma_mix.cu (profiles/r02_umma_mix_probe.log): this
+          // kernel's MMA stream alone runs at 2 770 clk per group (ideal 2 688), with the ring's bulk loads, the tcgen05.ld
+          // readers and the accumulator hand-shake at 2 990 — and at 3 980 once the readers also store 64 B per thread with
+          // the lanes 128 B apart, as below (a warp instruction touches 32 lines with 16 bytes each); lane-contiguous
+          // stores of the same bytes: 3 005.  CR_QUAD_STORES=1 (12 shuffles per row and thread, 8 half-lines per
+          // instruction) measured 0.134 instead of 0.140 ms per layer1 launch: kept as an option, not the default; staging
+          // the row in shared memory for a TMA store is the variant still to be measured.
+#if CR_QUAD_STORES
+          // 4 x 4 transpose of the 16-byte chunks inside each lane quad: lane a of a quad ends up with chunk a of the
+          // quad's four pixels, so that the quad writes the 64 contiguous bytes of ONE pixel per instruction (a warp
+          // instruction touches 8 half-lines instead of 32 lines with 16 bytes each)
+          {
+            const int a = lane & 3;
+            const uint4 own = a == 0 ? o[0] : a == 1 ? o[1] : a == 2 ? o[2] : o[3];
+            uint4 tq[4] = {own, own, own, own};                       // tq[a] = this pixel's chunk a; the others arrive below
+#pragma unroll
+            for (int r = 1; r < 4; ++r) {
+              const int si = (a + 4 - r) & 3;                         // chunk this lane sends: the receiver's quad index
+              const uint4 snd = si == 0 ? o[0] : si == 1 ? o[1] : si == 2 ? o[2] : o[3];
+              const int src = (lane & ~3) | ((a + r) & 3);
+              uint4 rcv;
+              rcv.x = __shfl_sync(0xffffffffu, snd.x, src);
+              rcv.y = __shfl_sync(0xffffffffu, snd.y, src);
+              rcv.z = __shfl_sync(0xffffffffu, snd.z, src);
+              rcv.w = __shfl_sync(0xffffffffu, snd.w, src);
+              const int di = (a + r) & 3;                             // pixel (inside the quad) the chunk belongs to
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j == di) tq[j] = rcv;
+            }
+            if (Y < p.H) {
+              const int X0 = X - a;
+              uint8_t* base = p.y + ((static_cast<size_t>(run.b) * p.H + Y) * p.W + X0) * pix_bytes +
+                              static_cast<size_t>(p.dst_coff + half * 32) * 2 + a * 16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (X0 + j < p.W) *reinterpret_cast<uint4*>(base + j * pix_bytes) = tq[j];
+            }
+          }
+#else
           if (xvalid && Y < p.H) {
             uint8_t* dst = p.y + ((static_cast<size_t>(run.b) * p.H + Y) * p.W + X) * pix_bytes +
                            static_cast<size_t>(p.dst_coff + half * 32) * 2;
             stg256(dst, o[0], o[1]);
             stg256(dst + 32, o[2], o[3]);
           }
+#endif
         }
       }
       pos += ngroups;
