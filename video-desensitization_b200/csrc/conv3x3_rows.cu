@@ -41,8 +41,12 @@ constexpr int CR_RING = 7;
 constexpr int CR_WBLK = 64 * 128;                 // one filter tap: [64 cout][64 cin] = 8 KB
 constexpr int CR_W_BYTES = 11 * CR_WBLK;
 constexpr int CR_A_BYTES = CR_RING * CR_ROW_BYTES;
-constexpr int CR_SMEM = CR_A_BYTES + CR_W_BYTES + 1024 /*bias + barriers*/ + 1024 /*alignment*/;
+constexpr int CR_STAGE_BYTES = 128 * 128;        // one output row of the strip: 128 pixels x 64 channels
+constexpr int CR_SMEM = CR_A_BYTES + CR_W_BYTES + CR_STAGE_BYTES + 1024 /*bias + barriers*/ + 1024 /*alignment*/;
 constexpr int CR_THREADS = 320;
+#ifndef CR_TMA_STORE
+#define CR_TMA_STORE 0               // epilogue variant: stage each output row in shared memory, one TMA store per row
+#endif
 #ifndef CR_STG256
 #define CR_STG256 0                  // 32-byte stores (STG.E.ENL2.256): measured 0.136 instead of 0.140 ms per layer1 launch, off
 #endif
@@ -88,12 +92,13 @@ __device__ __forceinline__ void stg256(uint8_t* ptr, const uint4& a, const uint4
 
 __global__ void __launch_bounds__(CR_THREADS, 1)
 conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const RowsParams p) {
+                    const __grid_constant__ CUtensorMap tmY, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + CR_A_BYTES;
-  float* sBias = reinterpret_cast<float*>(sB + CR_W_BYTES);
+  uint8_t* sStage = sB + CR_W_BYTES;                // 1 KB aligned: CR_A_BYTES and CR_W_BYTES are multiples of 1 KB
+  float* sBias = reinterpret_cast<float*>(sStage + CR_STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + 64);
   uint64_t* empty = full + CR_RING;
   uint64_t* tfull = empty + CR_RING;
@@ -114,6 +119,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -286,10 +292,28 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // kernel's MMA stream alone runs at 2 770 clk per group (ideal 2 688), with the ring's bulk loads, the tcgen05.ld
           // readers and the accumulator hand-shake at 2 990 — and at 3 980 once the readers also store 64 B per thread with
           // the lanes 128 B apart, as below (a warp instruction touches 32 lines with 16 bytes each); lane-contiguous
-          // stores of the same bytes: 3 005.  CR_QUAD_STORES=1 (12 shuffles per row and thread, 8 half-lines per
-          // instruction) measured 0.134 instead of 0.140 ms per layer1 launch: kept as an option, not the default; staging
-          // the row in shared memory for a TMA store is the variant still to be measured.
-#if CR_QUAD_STORES
+          // stores of the same bytes: 3 005.  In the kernel itself three remedies all land within 4 % of the plain stores
+          // (0.140 ms per layer1 launch): CR_QUAD_STORES=1 (12 shuffles per row and thread, 8 half-lines per instruction)
+          // 0.134, CR_TMA_STORE=1 (staging tile + one TMA store per row) 0.134, CR_STG256=1 (32-byte stores) 0.136 — the
+          // launch is paced by the SM clock the 1 kW power cap allows under tensor load, not by these cycles.  All three
+          // are kept as compile-time options; the default is the build the committed ncu captures were taken on.
+#if CR_TMA_STORE
+          // the row goes through a 16 KB staging tile (SWIZZLE_128B: chunk c of pixel i at i*128 + ((c ^ (i & 7)) << 4)) and
+          // leaves with ONE TMA store, which also clips columns >= W and rows >= H
+          {
+            if (threadIdx.x == 64) tma_store_wait_read<0>();          // the previous row's store has read the tile
+            named_bar_sync(1, 256);
+            const uint32_t srow = smem_u32(sStage) + col * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sts128(srow + (((half * 4 + j) ^ (col & 7)) << 4), o[j]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (threadIdx.x == 64) {
+              tma_store_4d(&tmY, sStage, p.dst_coff, CR_COLS * run.t, Y, run.b);
+              tma_store_commit();
+            }
+          }
+#elif CR_QUAD_STORES
           // 4 x 4 transpose of the 16-byte chunks inside each lane quad: lane a of a quad ends up with chunk a of the
           // quad's four pixels, so that the quad writes the 64 contiguous bytes of ONE pixel per instruction (a warp
           // instruction touches 8 half-lines instead of 32 lines with 16 bytes each)
@@ -333,6 +357,9 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       pos += ngroups;
     }
+#if CR_TMA_STORE
+    if (threadIdx.x == 64) tma_store_wait_all<0>();
+#endif
   }
 
   tcgen05_fence_before();
@@ -346,7 +373,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }  // namespace
 
 struct vd_conv_rows_plan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   RowsParams kp;
   int grid;
 };
@@ -411,6 +438,18 @@ int vd_conv_rows_create(const vd_conv_desc_t* d, vd_conv_rows_plan** out) {
     delete pl;
     return VD_ERR_CUDA;
   }
+  cuuint64_t ydim[4] = {static_cast<cuuint64_t>(d->dst_C), static_cast<cuuint64_t>(d->Wout), static_cast<cuuint64_t>(d->Hout),
+                        static_cast<cuuint64_t>(d->B)};
+  cuuint64_t ystr[3] = {static_cast<cuuint64_t>(d->dst_C) * 2, static_cast<cuuint64_t>(d->dst_C) * 2 * d->Wout,
+                        static_cast<cuuint64_t>(d->dst_C) * 2 * d->Wout * d->Hout};
+  cuuint32_t ybox[4] = {64, CR_COLS, 1, 1};
+  r = enc(&pl->tmY, dt, 4, d->y, ydim, ystr, ybox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vd_set_error("cuTensorMapEncodeTiled(rows Y) failed: CUresult %d", static_cast<int>(r));
+    delete pl;
+    return VD_ERR_CUDA;
+  }
   *out = pl;
   return VD_OK;
 }
@@ -424,7 +463,7 @@ void vd_conv_rows_info(const vd_conv_rows_plan* pl, int* groups, int* grid) {
 
 int vd_conv_rows_run(const vd_conv_rows_plan* pl, cudaStream_t st) {
   VD_SET_FUNC_ATTR_ONCE_PER_DEVICE(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM);
-  conv3x3_rows_kernel<<<pl->grid, CR_THREADS, CR_SMEM, st>>>(pl->tmA, pl->tmB, pl->kp);
+  conv3x3_rows_kernel<<<pl->grid, CR_THREADS, CR_SMEM, st>>>(pl->tmA, pl->tmB, pl->tmY, pl->kp);
   VD_LAUNCH_CHECK();
   return VD_OK;
 }
