@@ -34,16 +34,6 @@
 
 namespace {
 
-constexpr int CR_COLS = 128;                      // output columns per strip (M)
-constexpr int CR_IN_PX = CR_COLS + 2;             // input pixels per row incl. the halo
-constexpr int CR_ROW_BYTES = 136 * 128;           // ring slot: 130 pixels x 128 B, padded to the 1 KB swizzle atom
-constexpr int CR_RING = 7;
-constexpr int CR_WBLK = 64 * 128;                 // one filter tap: [64 cout][64 cin] = 8 KB
-constexpr int CR_W_BYTES = 11 * CR_WBLK;
-constexpr int CR_A_BYTES = CR_RING * CR_ROW_BYTES;
-constexpr int CR_STAGE_BYTES = 128 * 128;        // one output row of the strip: 128 pixels x 64 channels
-constexpr int CR_SMEM = CR_A_BYTES + CR_W_BYTES + CR_STAGE_BYTES + 1024 /*bias + barriers*/ + 1024 /*alignment*/;
-constexpr int CR_THREADS = 320;
 #ifndef CR_TMA_STORE
 #define CR_TMA_STORE 0               // epilogue variant: stage each output row in shared memory, one TMA store per row
 #endif
@@ -53,6 +43,16 @@ constexpr int CR_THREADS = 320;
 #ifndef CR_QUAD_STORES
 #define CR_QUAD_STORES 0              // measured alternative for the epilogue's stores, see the epilogue
 #endif
+constexpr int CR_COLS = 128;                      // output columns per strip (M)
+constexpr int CR_IN_PX = CR_COLS + 2;             // input pixels per row incl. the halo
+constexpr int CR_ROW_BYTES = 136 * 128;           // ring slot: 130 pixels x 128 B, padded to the 1 KB swizzle atom
+constexpr int CR_RING = 7;
+constexpr int CR_WBLK = 64 * 128;                 // one filter tap: [64 cout][64 cin] = 8 KB
+constexpr int CR_W_BYTES = 11 * CR_WBLK;
+constexpr int CR_A_BYTES = CR_RING * CR_ROW_BYTES;
+constexpr int CR_STAGE_BYTES = CR_TMA_STORE ? 128 * 128 : 0;   // CR_TMA_STORE: one output row of the strip (128 pixels x 64 channels)
+constexpr int CR_SMEM = CR_A_BYTES + CR_W_BYTES + CR_STAGE_BYTES + 1024 /*bias + barriers*/ + 1024 /*alignment*/;
+constexpr int CR_THREADS = 320;
 constexpr int CR_TMEM_COLS = 256;                 // two accumulators of 2 rows x 64 columns
 
 struct RowsParams {
